@@ -1,0 +1,62 @@
+"""The oracle against fixtures produced by the reference's own code (tests/golden/make_golden.py).
+
+CPU only.  Integer outputs (indices, masks, integer-valued demand/load) must be identical;
+floats agree to a few ulp (same numpy kernels on both sides, op order as the reference writes it).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from oracle import restatement as O
+from tests.helpers import GOLDEN_INDEX, load_golden
+
+ROLLOUT_CASES = sorted(GOLDEN_INDEX)
+
+
+def _crc(p):
+    crc = 0
+    for k in sorted(p):
+        crc = zlib.crc32(np.ascontiguousarray(p[k]).tobytes(), crc)
+    return crc
+
+
+@pytest.mark.parametrize("name", ROLLOUT_CASES)
+def test_rollout_matches_reference_code(name):
+    fx, args, params = load_golden(name)
+    assert _crc(params) == int(fx["param_crc"]), "weights regenerated from the seed differ from the fixture's"
+    meta = GOLDEN_INDEX[name]
+    res = O.rollout(params, args, fx["data"], meta["decode_type"],
+                    uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"), keep_probs=True)
+    np.testing.assert_array_equal(res.idxs, fx["idxs"])
+    np.testing.assert_array_equal(res.masks, fx["masks"])
+    np.testing.assert_array_equal(res.final_state.demand, fx["final_demand"])
+    np.testing.assert_array_equal(res.final_state.load, fx["final_load"])
+    np.testing.assert_array_equal(res.final_state.mask, fx["final_mask"])
+    np.testing.assert_allclose(res.logits, fx["logits"], rtol=2e-6, atol=2e-6)
+    np.testing.assert_allclose(res.probs, fx["probs"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(res.logprobs, fx["logprobs"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(res.actions, fx["actions"], rtol=0, atol=0)
+    np.testing.assert_allclose(res.R, fx["R"], rtol=1e-6)
+    if args["task_name"] == "vrptw":
+        np.testing.assert_array_equal(res.final_state.time, fx["final_time"])
+
+
+@pytest.mark.parametrize("name,task,W", [("env_vrptw10", "vrptw10", 1), ("env_vrp10", "vrp10", 1),
+                                         ("env_vrptw10_beam", "vrptw10", 3)])
+def test_env_matches_reference_code(name, task, W):
+    fx, _, _ = load_golden(name)
+    args = O.default_args(task)
+    env = O.EnvOracle(args, fx["data"])
+    st = env.reset(W)
+    np.testing.assert_array_equal(st.mask, fx["mask"][0])
+    np.testing.assert_array_equal(st.load, fx["load"][0])
+    for t in range(fx["idx_seq"].shape[0]):
+        par = fx["parent_seq"][t][:, None] if "parent_seq" in fx else None
+        st = env.step(fx["idx_seq"][t][:, None], par)
+        np.testing.assert_array_equal(st.mask, fx["mask"][t + 1], err_msg=f"mask step {t}")
+        np.testing.assert_array_equal(st.demand, fx["demand"][t + 1])
+        np.testing.assert_array_equal(st.load, fx["load"][t + 1])
+        np.testing.assert_array_equal(st.d_sat, fx["d_sat"][t + 1])
+        if args["task_name"] == "vrptw":
+            np.testing.assert_array_equal(st.time, fx["time"][t + 1])
