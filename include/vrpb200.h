@@ -1,0 +1,161 @@
+/*
+ * vrpb200.h - C ABI of libvrpb200.so: the B200 (sm_100a) implementation of the batched
+ * attention-policy rollout of jpoulletXaccount/MIT_rl-vrptw.
+ *
+ * The reference has no FFI: its seam is the Python protocol (Env, Attention*Actor, RNNDecodeStep,
+ * RLAgent.build_model) selected in main.py:17-53 and consumed by model/attention_agent.py:13-66.
+ * Each entry point below names the reference code it replaces (paths relative to the reference
+ * repository root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side; `mit_rl-vrptw_b200/` is that binding plus the reference-named host classes.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative VRPB200_E_* code otherwise; the message of
+ *    the last error of a handle is vrpb200_last_error(handle); nothing throws across the boundary;
+ *  - plain pointers and sizes only; `d_` arguments are DEVICE pointers of the handle's device,
+ *    `h_` arguments are HOST pointers; the caller owns every buffer, the library allocates only
+ *    its weight blob (set_weights) and, for the *_host call, its own pinned/device staging;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are
+ *    asynchronous on it unless stated otherwise;
+ *  - a handle is not thread-safe; handles on different devices are independent;
+ *  - rows: R = B * W, beam-major (row = w*B + b) exactly as model/attention_agent.py:173-174 and
+ *    VRPTW/vrptw_utils.py:225 lay them out; node N-1 is the depot;
+ *  - there is no CPU fallback: without a CUDA device vrpb200_create fails with VRPB200_E_CUDA.
+ */
+#ifndef VRPB200_H_
+#define VRPB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VRPB200_OK 0
+#define VRPB200_E_ARG (-1)      /* bad argument / unsupported configuration */
+#define VRPB200_E_CUDA (-2)     /* CUDA runtime error (message in last_error) */
+#define VRPB200_E_WEIGHTS (-3)  /* weights missing / wrong shape */
+#define VRPB200_E_STATE (-4)    /* call order (e.g. rollout before set_weights) */
+
+#define VRPB200_TASK_VRP 0      /* input_dim 3: x, y, demand            (VRP/vrp_utils.py) */
+#define VRPB200_TASK_VRPTW 1    /* input_dim 5: x, y, b_tw, e_tw, demand (VRPTW/vrptw_utils.py, UPS twin) */
+
+#define VRPB200_GREEDY 0        /* model/attention_agent.py:146-147 */
+#define VRPB200_STOCHASTIC 1    /* model/attention_agent.py:148-167 */
+#define VRPB200_BEAM 2          /* model/attention_agent.py:169-205 */
+
+/* args[...] keys read by Env.__init__ (VRPTW/vrptw_utils.py:172-181), RLAgent.__init__
+ * (model/attention_agent.py:47-64) and task_specific_params.py:22-115. */
+typedef struct vrpb200_config {
+    int32_t task;            /* VRPB200_TASK_* */
+    int32_t n_nodes;         /* N  (<= 128) */
+    int32_t n_cust;          /* N - 1 */
+    int32_t input_dim;       /* 3 or 5 */
+    int32_t embedding_dim;   /* E  (<= 128) */
+    int32_t hidden_dim;      /* H  (128 in this build) */
+    int32_t decode_len;      /* T */
+    int32_t n_glimpses;      /* shared/decode_step.py:41-46 */
+    int32_t use_tanh;        /* C*tanh(u) on the pointer logits, shared/decode_step.py:49-53 */
+    int32_t mask_glimpses;   /* shared/decode_step.py:222-223 */
+    int32_t mask_pointer;    /* shared/decode_step.py:231-232 */
+    int32_t rows_per_cta;    /* 0 = choose; else 16/32/48/64 (tuning knob, no effect on results) */
+    float capacity;
+    float tanh_exploration;  /* C */
+    float forget_bias;       /* BasicLSTMCell forget_bias, shared/decode_step.py:175 */
+} vrpb200_config;
+
+typedef struct vrpb200_handle vrpb200_handle;
+
+/* Optional per-step dumps of a rollout (test instrumentation; any pointer may be NULL).
+ * With any of logits/probs/masks set, every node is evaluated at every step (no early exit). */
+typedef struct vrpb200_trace {
+    float* d_logits;        /* [T, R, N] pointer logits after masking (shared/decode_step.py:230-232) */
+    float* d_probs;         /* [T, R, N] exp(log_softmax)            (shared/decode_step.py:125-126) */
+    float* d_masks;         /* [T, R, N] Env.mask seen by step t, float counts 0..3 */
+    float* d_final_demand;  /* [R, N] */
+    float* d_final_load;    /* [R] */
+    float* d_final_time;    /* [R]  (VRPTW only) */
+    float* d_final_mask;    /* [R, N] */
+    int32_t* d_steps;       /* [gridDim] decode steps each instance block actually executed */
+} vrpb200_trace;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out);
+int vrpb200_destroy(vrpb200_handle* h);
+const char* vrpb200_last_error(const vrpb200_handle* h); /* h may be NULL: last create error */
+int vrpb200_version(void);
+
+/* Weights by TF-1 variable name (what tf.train.Saver stores, model/attention_agent.py:79-80):
+ *   Actor/Embedding/conv1d/{kernel,bias}                                   shared/embeddings.py:37-38
+ *   Actor/Decoder/LSTM/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/{kernel,bias}  shared/decode_step.py:175-180
+ *   Actor/Decoder/Attention/{v, emb_d, emb_ld, emb_time, proj_d, proj_ld, proj_t, proj_q, proj_ref}/...
+ *   Actor/Glimpse<i>/...   (same set)                                      VRPTW/vrptw_attention.py:10-24
+ * h_data[i] is a host fp32 array of n_elem[i] elements in TF layout.  Synchronous. */
+int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names,
+                        const float* const* h_data, const int64_t* n_elem);
+
+/* ---- the hot path: RLAgent.build_model(decode_type) + evaluate_batch --------------------- *
+ * (model/attention_agent.py:84-240, 475-518).  d_input [B, N, input_dim] fp32.
+ * d_uniforms / d_uniforms_retry [T, R] in [0,1): the two tf.random_uniform draws of my_multinomial
+ * (attention_agent.py:163-167), STOCHASTIC only (NULL: counter-based in-kernel stream from `seed`).
+ * Outputs (any may be NULL except d_cost): d_idx [T, R] int32 chosen node; d_cost [R] tour length
+ * (reward_func, depot=None branch, VRPTW/vrptw_utils.py:397-414), beam rows back-tracked as
+ * attention_agent.py:222-231; d_logprob [T, R] log(prob[row, idx]) (attention_agent.py:214);
+ * d_beam_parent [T, R] int32 (BEAM only). */
+int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode, int beam_width,
+                    const float* d_uniforms, const float* d_uniforms_retry, uint64_t seed,
+                    int32_t* d_idx, float* d_cost, float* d_logprob, int32_t* d_beam_parent,
+                    const vrpb200_trace* trace, void* stream);
+
+/* The same call with HOST buffers (what evaluate_batch's sess.run(feed_dict) is to a caller):
+ * pinned staging, H2D of h_input, the rollout, D2H of h_cost (and h_idx when not NULL).
+ * Synchronous; returns after the results are in host memory. */
+int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int mode, int beam_width,
+                         uint64_t seed, int32_t* h_idx, float* h_cost);
+
+/* ---- Env (VRPTW/vrptw_utils.py:161-358, VRP/vrp_utils.py:133-255) ------------------------- *
+ * State arrays are the Env attributes of the same name, fp32, R rows:
+ *   demand [R,N], load [R], time [R] (VRPTW), mask [R,N], prev_xy [R,2] (previous_x, previous_y).
+ * env_reset: Env.reset(beam_width) (vrptw_utils.py:199-252).
+ * env_step:  Env.step(idx, beam_parent) (vrptw_utils.py:254-358); d_idx [R] int64, d_beam_parent
+ *            [R] int64 or NULL; d_sat [R] out (may be NULL).  With beam_parent the state is gathered
+ *            from the *_in arrays into the *_out arrays (they must not alias); without it in == out
+ *            is allowed. */
+int vrpb200_env_reset(vrpb200_handle* h, const float* d_input, int64_t B, int beam_width,
+                      float* d_demand, float* d_load, float* d_time, float* d_mask, float* d_prev_xy,
+                      void* stream);
+int vrpb200_env_step(vrpb200_handle* h, const float* d_input, int64_t B, int beam_width,
+                     const int64_t* d_idx, const int64_t* d_beam_parent,
+                     const float* d_demand_in, const float* d_load_in, const float* d_time_in,
+                     const float* d_prev_xy_in,
+                     float* d_demand, float* d_load, float* d_time, float* d_mask, float* d_prev_xy,
+                     float* d_sat, void* stream);
+
+/* ---- standalone model pieces (drop-in surface; as-written arithmetic, not the fused path) -- *
+ * embed:       LinearEmbedding.__call__ (shared/embeddings.py:40-46): d_input_pnt [M, D-1] -> [M, E].
+ * attention:   Attention*Actor.__call__(query, ref, env) (VRPTW/vrptw_attention.py:30-84,
+ *              VRP/vrp_attention.py:27-76): att = -1 pointer ("Actor/Decoder/Attention"), i>=0 glimpse i;
+ *              d_query [R,H], d_ref [R,N,E], env demand/load/time -> d_e [R,N,H] (may be NULL), d_logits [R,N].
+ * decode_step: RNNDecodeStep.step (shared/decode_step.py:97-128,182-234): d_decoder_inp [R,E],
+ *              d_context [R,N,E], env demand/load/time/mask, d_c/d_h [R,H] in-out ->
+ *              d_logit, d_prob, d_logprob [R,N]. */
+int vrpb200_embed(vrpb200_handle* h, const float* d_input_pnt, int64_t M, float* d_emb, void* stream);
+int vrpb200_attention(vrpb200_handle* h, int att, int64_t R, const float* d_query, const float* d_ref,
+                      const float* d_demand, const float* d_load, const float* d_time,
+                      float* d_e, float* d_logits, void* stream);
+int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp, const float* d_context,
+                        const float* d_demand, const float* d_load, const float* d_time, const float* d_mask,
+                        float* d_c, float* d_h, float* d_logit, float* d_prob, float* d_logprob, void* stream);
+
+/* reward_func(sample_solution) depot=None branch (VRPTW/vrptw_utils.py:397-414): d_actions [T, R, A]
+ * (first two columns x, y) -> d_cost [R]. */
+int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t R, int A, float* d_cost,
+                   void* stream);
+
+/* Launch statistics of the last rollout on this handle (for bench.py): grid size, block size,
+ * dynamic shared memory bytes, rows per CTA, number of kernels launched. */
+int vrpb200_last_launch(const vrpb200_handle* h, int32_t out[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VRPB200_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of libvrpb200.so (include/vrpb200.h) and its in-tree build recipe.
+
+The library is the product: there is no Python/CPU fallback.  ``load()`` raises if the shared
+object is missing (run ``python __graft_entry__.py build`` or ``build_library()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libvrpb200.so")
+HEADER = os.path.join(ROOT, "include", "vrpb200.h")
+
+TASK_VRP, TASK_VRPTW = 0, 1
+GREEDY, STOCHASTIC, BEAM = 0, 1, 2
+DECODE_MODES = {"greedy": GREEDY, "stochastic": STOCHASTIC, "beam_search": BEAM}
+
+
+class Config(C.Structure):
+    """struct vrpb200_config"""
+    _fields_ = [(n, C.c_int32) for n in (
+        "task", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
+        "use_tanh", "mask_glimpses", "mask_pointer", "rows_per_cta")] + [
+        ("capacity", C.c_float), ("tanh_exploration", C.c_float), ("forget_bias", C.c_float)]
+
+
+class Trace(C.Structure):
+    """struct vrpb200_trace (device pointers)"""
+    _fields_ = [(n, C.c_void_p) for n in (
+        "d_logits", "d_probs", "d_masks", "d_final_demand", "d_final_load", "d_final_time", "d_final_mask", "d_steps")]
+
+
+EXPORTS = (
+    "vrpb200_create", "vrpb200_destroy", "vrpb200_last_error", "vrpb200_version", "vrpb200_set_weights",
+    "vrpb200_rollout", "vrpb200_rollout_host", "vrpb200_env_reset", "vrpb200_env_step", "vrpb200_embed",
+    "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_last_launch",
+)
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -> mit_rl-vrptw_b200/lib/libvrpb200.so (sm_100a only; cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "vrpb200_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the library and declare every prototype of include/vrpb200.h."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                           "(there is no CPU fallback for the rollout path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, u64, f32p = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_void_p
+    lib.vrpb200_create.argtypes = [C.POINTER(Config), i32, C.POINTER(vp)]
+    lib.vrpb200_destroy.argtypes = [vp]
+    lib.vrpb200_last_error.argtypes = [vp]
+    lib.vrpb200_last_error.restype = C.c_char_p
+    lib.vrpb200_version.argtypes = []
+    lib.vrpb200_set_weights.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(i64)]
+    lib.vrpb200_rollout.argtypes = [vp, f32p, i64, i32, i32, f32p, f32p, u64, vp, f32p, f32p, vp, C.POINTER(Trace), vp]
+    lib.vrpb200_rollout_host.argtypes = [vp, f32p, i64, i32, i32, u64, vp, f32p]
+    lib.vrpb200_env_reset.argtypes = [vp, f32p, i64, i32, f32p, f32p, f32p, f32p, f32p, vp]
+    lib.vrpb200_env_step.argtypes = [vp, f32p, i64, i32, vp, vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    lib.vrpb200_embed.argtypes = [vp, f32p, i64, f32p, vp]
+    lib.vrpb200_attention.argtypes = [vp, i32, i64, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    lib.vrpb200_decode_step.argtypes = [vp, i64, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
+    lib.vrpb200_reward.argtypes = [vp, f32p, i64, i64, i32, f32p, vp]
+    lib.vrpb200_last_launch.argtypes = [vp, C.POINTER(C.c_int32)]
+    for name in EXPORTS:
+        if name != "vrpb200_last_error":
+            getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+class VrpB200Error(RuntimeError):
+    pass

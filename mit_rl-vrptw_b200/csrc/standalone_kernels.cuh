@@ -1,0 +1,283 @@
+// Stand-alone kernels behind the drop-in surface (Env.reset/step, LinearEmbedding, Attention*Actor.__call__,
+// RNNDecodeStep.step, reward_func).  They follow the reference op for op ("as written": un-collapsed
+// Conv1D chains, float masks) and are NOT the hot path - the fused rollout kernel is.  They exist so that a
+// caller can drive the reference's step-by-step protocol against device state, and so that the fused
+// kernel can be cross-checked on the GPU against an independent formulation.
+#pragma once
+#include "rollout_kernel.cuh"
+
+namespace vrpb200 {
+
+// ---- Env.reset (VRPTW/vrptw_utils.py:199-252, VRP/vrp_utils.py:159-196): one warp per row ----------
+__global__ void env_reset_kernel(const float* __restrict__ input, long long B, int W, int N, int D, float capacity,
+                                 float* demand, float* load, float* time, float* mask, float* prev_xy) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B * W) return;
+    const long long b = row % B;
+    const float* in = input + b * N * D;
+    for (int n = lane; n < N; n += 32) {
+        const float d = in[n * D + D - 1];
+        demand[row * N + n] = d;
+        mask[row * N + n] = (n == N - 1) ? 1.0f : (d == 0.0f ? 1.0f : 0.0f);
+    }
+    if (lane == 0) {
+        load[row] = capacity;
+        if (time) time[row] = 0.0f;
+        if (prev_xy) {
+            prev_xy[row * 2 + 0] = in[(N - 1) * D + 0];
+            prev_xy[row * 2 + 1] = in[(N - 1) * D + 1];
+        }
+    }
+}
+
+// ---- Env.step (VRPTW/vrptw_utils.py:254-358, VRP/vrp_utils.py:198-255): one warp per row -----------
+template <bool TW>
+__global__ void env_step_kernel(const float* __restrict__ input, long long B, int W, int N, int D, float capacity,
+                                const long long* __restrict__ idx, const long long* __restrict__ parent,
+                                const float* demand_in, const float* load_in, const float* time_in,
+                                const float* prev_in, float* demand, float* load, float* time, float* mask,
+                                float* prev_xy, float* d_sat_out) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B * W) return;
+    const long long b = row % B;
+    const long long src = parent ? b + B * parent[row] : row;   // beam gather, vrptw_utils.py:262-287
+    const float* in = input + b * N * D;
+    const int n_cust = N - 1;
+    const int id = (int)idx[row];
+    const float ld0 = load_in[src];
+    const float d_idx = demand_in[src * N + id];
+    const float d_sat = fminf(d_idx, ld0);
+    float nload = __fsub_rn(ld0, d_sat);
+    float px = 0.f, py = 0.f, ntime = 0.f;
+    const float sx = in[id * D + 0], sy = in[id * D + 1];
+    if (TW) {
+        px = prev_in[src * 2 + 0];
+        py = prev_in[src * 2 + 1];
+        const float ts = dist_rn(px, py, sx, sy);
+        ntime = fmaxf(__fadd_rn(time_in[src], ts), in[id * D + 2]);
+    }
+    const float dep = (id == n_cust) ? 1.0f : 0.0f;
+    nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, capacity));
+    if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
+    float dn[4], sumdem = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = lane + 32 * j;
+        dn[j] = 0.0f;
+        if (n < N) {
+            dn[j] = demand_in[src * N + n];
+            if (n == id) dn[j] = __fsub_rn(dn[j], d_sat);
+        }
+        sumdem += dn[j];
+    }
+    sumdem = warp_sum(sumdem);
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = lane + 32 * j;
+        if (n < N) {
+            demand[row * N + n] = dn[j];
+            float e_tw = 0.f;
+            if (TW) e_tw = in[n * D + 3];
+            mask[row * N + n] = (float)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, in[n * D + 0],
+                                                     in[n * D + 1], e_tw, dep, sumdem);
+        }
+    }
+    if (lane == 0) {
+        load[row] = nload;
+        if (TW) {
+            time[row] = ntime;
+            prev_xy[row * 2 + 0] = sx;
+            prev_xy[row * 2 + 1] = sy;
+        }
+        if (d_sat_out) d_sat_out[row] = d_sat;
+    }
+}
+
+// ---- LinearEmbedding.__call__ (shared/embeddings.py:40-46): Conv1D k=1 -----------------------------
+__global__ void embed_kernel(const float* __restrict__ x, long long M, int D1, int E, const float* __restrict__ Wk,
+                             const float* __restrict__ bias, float* out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M * E) return;
+    const long long m = i / E;
+    const int e = (int)(i - m * E);
+    float s = 0.0f;
+    for (int c = 0; c < D1; ++c) s = fmaf(x[m * D1 + c], Wk[c * E + e], s);
+    out[i] = s + bias[e];
+}
+
+// Raw (TF layout) attention weights of one module, device pointers.
+struct RawAtt {
+    const float *v, *emb_d_k, *emb_d_b, *emb_ld_k, *emb_ld_b, *emb_t_k, *emb_t_b;
+    const float *proj_d_k, *proj_d_b, *proj_ld_k, *proj_ld_b, *proj_t_k, *proj_t_b;
+    const float *proj_q_k, *proj_q_b, *proj_ref_k, *proj_ref_b;
+};
+
+// One row of Attention*Actor.__call__ as written (VRPTW/vrptw_attention.py:30-84, VRP/vrp_attention.py:27-76).
+// 128 threads (one per hidden unit).  query: smem [H]; ref: global [N,E]; logits: smem [N]; e_out: global [N,H] or null.
+// sh: >= 3*H floats of scratch.
+template <bool TW>
+__device__ void attention_row(const RawAtt& w, int N, int E, const float* query, const float* ref, const float* demand,
+                              float load, float time, int use_tanh, float C, float* e_out, float* logits, float* sh) {
+    const int h = threadIdx.x;
+    float* s_d = sh;            // emb_d of the current node
+    float* s_ld = sh + kH;      // emb_ld
+    float* s_red = sh + 2 * kH; // reduction scratch
+    float q = 0.0f;
+    for (int k = 0; k < kH; ++k) q = fmaf(query[k], w.proj_q_k[k * kH + h], q);
+    q += w.proj_q_b[h];
+    float tt = 0.0f;
+    if (TW) {   // t = proj_t(emb_time(time))  (vrptw_attention.py:62-65), one vector per row
+        __syncthreads();
+        s_d[h] = fmaf(time, w.emb_t_k[h], w.emb_t_b[h]);
+        __syncthreads();
+        for (int k = 0; k < kH; ++k) tt = fmaf(s_d[k], w.proj_t_k[k * kH + h], tt);
+        tt += w.proj_t_b[h];
+    }
+    for (int n = 0; n < N; ++n) {
+        __syncthreads();
+        s_d[h] = fmaf(demand[n], w.emb_d_k[h], w.emb_d_b[h]);
+        s_ld[h] = fmaf(load - demand[n], w.emb_ld_k[h], w.emb_ld_b[h]);
+        __syncthreads();
+        float d = 0.0f, ld = 0.0f, e = 0.0f;
+        for (int k = 0; k < kH; ++k) {
+            d = fmaf(s_d[k], w.proj_d_k[k * kH + h], d);
+            ld = fmaf(s_ld[k], w.proj_ld_k[k * kH + h], ld);
+        }
+        d += w.proj_d_b[h];
+        ld += w.proj_ld_b[h];
+        for (int k = 0; k < E; ++k) e = fmaf(ref[n * E + k], w.proj_ref_k[k * kH + h], e);
+        e += w.proj_ref_b[h];
+        if (e_out) e_out[n * kH + h] = e;
+        float arg = q + e + d + ld;
+        if (TW) arg += tt;
+        float p = w.v[h] * tanhf(arg);
+        p = warp_sum(p);
+        if ((h & 31) == 0) s_red[h >> 5] = p;
+        __syncthreads();
+        if (h == 0) {
+            const float u = (s_red[0] + s_red[1]) + (s_red[2] + s_red[3]);
+            logits[n] = use_tanh ? C * tanhf(u) : u;
+        }
+    }
+    __syncthreads();
+}
+
+template <bool TW>
+__global__ void attention_kernel(RawAtt w, int N, int E, const float* query, const float* ref, const float* demand,
+                                 const float* load, const float* time, int use_tanh, float C, float* e_out,
+                                 float* logits) {
+    __shared__ float s_q[kH], s_log[128], s_sh[3 * kH];
+    const long long r = blockIdx.x;
+    s_q[threadIdx.x] = query[r * kH + threadIdx.x];
+    __syncthreads();
+    attention_row<TW>(w, N, E, s_q, ref + r * N * E, demand + r * N, load[r], TW ? time[r] : 0.0f, use_tanh, C,
+                      e_out ? e_out + r * N * kH : nullptr, s_log, s_sh);
+    if (threadIdx.x < N) logits[r * N + threadIdx.x] = s_log[threadIdx.x];
+}
+
+struct RawModel {
+    const float *lstm_k, *lstm_b;   // [E+H, 4H], [4H]
+    RawAtt att[8];                  // glimpses 0..n_glimpses-1, then the pointer
+    int n_glimpses;
+};
+
+// softmax pieces for one row held in smem (N <= 128), 128 threads
+__device__ void row_log_softmax(const float* logit, int N, float* logprob, float* prob, float* red) {
+    const int h = threadIdx.x;
+    float v = (h < N) ? logit[h] : -INFINITY;
+    float m = warp_max(v);
+    if ((h & 31) == 0) red[h >> 5] = m;
+    __syncthreads();
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float ex = (h < N) ? expf(v - m) : 0.0f;
+    float s = warp_sum(ex);
+    if ((h & 31) == 0) red[h >> 5] = s;
+    __syncthreads();
+    s = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    if (h < N) {
+        const float lp = (v - m) - logf(s);
+        logprob[h] = lp;
+        prob[h] = expf(lp);
+    }
+    __syncthreads();
+}
+
+// ---- RNNDecodeStep.step (shared/decode_step.py:97-128, 182-234): one block of 128 threads per row -----
+template <bool TW>
+__global__ void decode_step_kernel(RawModel mdl, int N, int E, const float* dec_inp, const float* context,
+                                   const float* demand, const float* load, const float* time, const float* mask,
+                                   float* c_io, float* h_io, int use_tanh, float C, int mask_glimpses, int mask_pointer,
+                                   float forget_bias, float* logit_out, float* prob_out, float* logprob_out) {
+    __shared__ float s_x[kH + 128], s_hy[kH], s_log[128], s_lp[128], s_p[128], s_sh[3 * kH], s_red[4];
+    const long long r = blockIdx.x;
+    const int h = threadIdx.x;
+    if (h < E) s_x[h] = dec_inp[r * E + h];
+    s_x[E + h] = h_io[r * kH + h];
+    __syncthreads();
+    // BasicLSTMCell: [x, h] . W + b, gates i, j, f, o
+    float g[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < E + kH; ++k) {
+        const float xv = s_x[k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) g[q] = fmaf(xv, mdl.lstm_k[(size_t)k * 4 * kH + q * kH + h], g[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) g[q] += mdl.lstm_b[q * kH + h];
+    const float cn = __fadd_rn(__fmul_rn(c_io[r * kH + h], sigmoid_acc(g[2] + forget_bias)),
+                               __fmul_rn(sigmoid_acc(g[0]), tanh_acc(g[1])));
+    const float hn = __fmul_rn(tanh_acc(cn), sigmoid_acc(g[3]));
+    c_io[r * kH + h] = cn;
+    h_io[r * kH + h] = hn;
+    s_hy[h] = hn;
+    __syncthreads();
+    const float ld = load[r], tm = TW ? time[r] : 0.0f;
+    for (int gI = 0; gI < mdl.n_glimpses; ++gI) {   // decode_step.py:218-227
+        attention_row<TW>(mdl.att[gI], N, E, s_hy, context + r * N * E, demand + r * N, ld, tm, 0, C, nullptr, s_log, s_sh);
+        if (mask_glimpses && h < N) s_log[h] = __fsub_rn(s_log[h], __fmul_rn(kBig, mask[r * N + h]));
+        __syncthreads();
+        row_log_softmax(s_log, N, s_lp, s_p, s_red);
+        // hy = prob . e_g  (e_g recomputed: [N,E] x [E,H])
+        float acc = 0.0f;
+        for (int n = 0; n < N; ++n) {
+            float e = 0.0f;
+            for (int k = 0; k < E; ++k) e = fmaf(context[(r * N + n) * E + k], mdl.att[gI].proj_ref_k[k * kH + h], e);
+            e += mdl.att[gI].proj_ref_b[h];
+            acc = fmaf(s_p[n], e, acc);
+        }
+        __syncthreads();
+        s_hy[h] = acc;
+        __syncthreads();
+    }
+    attention_row<TW>(mdl.att[mdl.n_glimpses], N, E, s_hy, context + r * N * E, demand + r * N, ld, tm, use_tanh, C,
+                      nullptr, s_log, s_sh);
+    if (mask_pointer && h < N) s_log[h] = __fsub_rn(s_log[h], __fmul_rn(kBig, mask[r * N + h]));
+    __syncthreads();
+    row_log_softmax(s_log, N, s_lp, s_p, s_red);
+    if (h < N) {
+        logit_out[r * N + h] = s_log[h];
+        prob_out[r * N + h] = s_p[h];
+        logprob_out[r * N + h] = s_lp[h];
+    }
+}
+
+// ---- reward_func, depot=None branch (VRPTW/vrptw_utils.py:397-414, VRP/vrp_utils.py:293-307) ---------
+__global__ void reward_kernel(const float* __restrict__ actions, long long T, long long R, int A, float* cost) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float px = actions[((T - 1) * R + r) * A + 0], py = actions[((T - 1) * R + r) * A + 1];
+    float s = 0.0f;
+    for (long long t = 0; t < T; ++t) {
+        const float x = actions[(t * R + r) * A + 0], y = actions[(t * R + r) * A + 1];
+        s = __fadd_rn(s, dist_rn(px, py, x, y));
+        px = x;
+        py = y;
+    }
+    cost[r] = s;
+}
+
+}  // namespace vrpb200

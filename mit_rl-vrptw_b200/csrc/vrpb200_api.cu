@@ -1,0 +1,537 @@
+// C ABI of libvrpb200.so (include/vrpb200.h): handle, weight pre-processing, launchers.
+// No torch types, no CPU fallback: every compute entry point launches sm_100a kernels.
+#include "../../include/vrpb200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "rollout_kernel.cuh"
+#include "standalone_kernels.cuh"
+
+using namespace vrpb200;
+
+namespace {
+thread_local std::string g_create_error;
+}
+
+struct vrpb200_handle {
+    vrpb200_config cfg;
+    int device = 0;
+    bool tw = false;
+    int D1 = 0;   // input_dim - 1
+    std::string err;
+    bool have_weights = false;
+    float* d_blob = nullptr;          // processed + raw weights, one allocation
+    size_t blob_floats = 0;
+    // offsets (in floats) into the blob
+    const float* Wg = nullptr;
+    const float* bg = nullptr;
+    AttWeights att[8];
+    RawModel raw;
+    const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
+    // staging of the *_host call
+    float* pin_in = nullptr;  size_t pin_in_bytes = 0;
+    int32_t* pin_idx = nullptr; size_t pin_idx_bytes = 0;
+    float* pin_cost = nullptr; size_t pin_cost_bytes = 0;
+    float* dev_in = nullptr;  size_t dev_in_bytes = 0;
+    int32_t* dev_idx = nullptr; size_t dev_idx_bytes = 0;
+    float* dev_cost = nullptr; size_t dev_cost_bytes = 0;
+    cudaStream_t own_stream = nullptr;
+    int32_t last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int max_smem_optin = 0;
+    int num_sms = 0;
+};
+
+namespace {
+
+int fail(vrpb200_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(h, VRPB200_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct HostTensor { const float* p; int64_t n; };
+
+const char* kLstm = "Actor/Decoder/LSTM/rnn/multi_rnn_cell/cell_0/basic_lstm_cell";
+
+std::string att_prefix(const vrpb200_config& c, int a) {   // a in [0, n_glimpses]: glimpses then pointer
+    if (a < c.n_glimpses) return "Actor/Glimpse" + std::to_string(a);
+    return "Actor/Decoder/Attention";
+}
+
+template <class T>
+int ensure(vrpb200_handle* h, T** p, size_t* have, size_t need, bool pinned) {
+    if (*have >= need) return 0;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
+    if (pinned) CUDA_TRY(h, cudaMallocHost((void**)p, need));
+    else CUDA_TRY(h, cudaMalloc((void**)p, need));
+    *have = need;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vrpb200_version(void) { return 1; }
+
+const char* vrpb200_last_error(const vrpb200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) {
+    if (!cfg || !out) return fail(nullptr, VRPB200_E_ARG, "null argument");
+    *out = nullptr;
+    const vrpb200_config& c = *cfg;
+    if (c.task != VRPB200_TASK_VRP && c.task != VRPB200_TASK_VRPTW) return fail(nullptr, VRPB200_E_ARG, "task must be 0 (vrp) or 1 (vrptw)");
+    const int want_dim = c.task == VRPB200_TASK_VRPTW ? 5 : 3;
+    if (c.input_dim != want_dim) return fail(nullptr, VRPB200_E_ARG, "input_dim %d does not match task (want %d)", c.input_dim, want_dim);
+    if (c.n_nodes < 2 || c.n_nodes > 128) return fail(nullptr, VRPB200_E_ARG, "n_nodes %d outside [2,128]", c.n_nodes);
+    if (c.n_cust != c.n_nodes - 1) return fail(nullptr, VRPB200_E_ARG, "n_cust must be n_nodes-1 (depot is the last node)");
+    if (c.hidden_dim != kH) return fail(nullptr, VRPB200_E_ARG, "hidden_dim %d not supported by this build (128)", c.hidden_dim);
+    if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
+    if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
+    if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
+    if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
+        return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, VRPB200_E_CUDA, "no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, VRPB200_E_ARG, "device %d out of range (%d devices)", device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return fail(nullptr, VRPB200_E_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, VRPB200_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+    vrpb200_handle* h = new vrpb200_handle();
+    h->cfg = c;
+    h->device = device;
+    h->tw = c.task == VRPB200_TASK_VRPTW;
+    h->D1 = c.input_dim - 1;
+    h->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    h->num_sms = prop.multiProcessorCount;
+    *out = h;
+    return VRPB200_OK;
+}
+
+int vrpb200_destroy(vrpb200_handle* h) {
+    if (!h) return VRPB200_OK;
+    cudaSetDevice(h->device);
+    if (h->d_blob) cudaFree(h->d_blob);
+    if (h->pin_in) cudaFreeHost(h->pin_in);
+    if (h->pin_idx) cudaFreeHost(h->pin_idx);
+    if (h->pin_cost) cudaFreeHost(h->pin_cost);
+    if (h->dev_in) cudaFree(h->dev_in);
+    if (h->dev_idx) cudaFree(h->dev_idx);
+    if (h->dev_cost) cudaFree(h->dev_cost);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return VRPB200_OK;
+}
+
+int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, const float* const* h_data,
+                        const int64_t* n_elem) {
+    if (!h) return VRPB200_E_ARG;
+    const vrpb200_config& c = h->cfg;
+    const int E = c.embedding_dim, D1 = h->D1, H = kH;
+    std::map<std::string, HostTensor> m;
+    for (int i = 0; i < n; ++i) m[names[i]] = HostTensor{h_data[i], n_elem[i]};
+    std::string missing;
+    auto get = [&](const std::string& name, int64_t want) -> const float* {
+        auto it = m.find(name);
+        if (it == m.end()) { missing += " " + name; return nullptr; }
+        if (it->second.n != want) { missing += " " + name + "(size " + std::to_string(it->second.n) + " != " + std::to_string(want) + ")"; return nullptr; }
+        return it->second.p;
+    };
+    const float* emb_k = get("Actor/Embedding/conv1d/kernel", (int64_t)D1 * E);
+    const float* emb_b = get("Actor/Embedding/conv1d/bias", E);
+    const float* lstm_k = get(std::string(kLstm) + "/kernel", (int64_t)(E + H) * 4 * H);
+    const float* lstm_b = get(std::string(kLstm) + "/bias", 4 * H);
+    const int natt = c.n_glimpses + 1;
+    struct RawHost { const float *v, *ed_k, *ed_b, *eld_k, *eld_b, *et_k, *et_b, *pd_k, *pd_b, *pld_k, *pld_b, *pt_k, *pt_b, *pq_k, *pq_b, *pr_k, *pr_b; };
+    std::vector<RawHost> rh(natt);
+    for (int a = 0; a < natt; ++a) {
+        const std::string p = att_prefix(c, a);
+        RawHost& r = rh[a];
+        r.v = get(p + "/v", H);
+        r.ed_k = get(p + "/emb_d/kernel", H);   r.ed_b = get(p + "/emb_d/bias", H);
+        r.eld_k = get(p + "/emb_ld/kernel", H); r.eld_b = get(p + "/emb_ld/bias", H);
+        r.pd_k = get(p + "/proj_d/kernel", H * H);   r.pd_b = get(p + "/proj_d/bias", H);
+        r.pld_k = get(p + "/proj_ld/kernel", H * H); r.pld_b = get(p + "/proj_ld/bias", H);
+        r.pq_k = get(p + "/proj_q/kernel", H * H);   r.pq_b = get(p + "/proj_q/bias", H);
+        r.pr_k = get(p + "/proj_ref/kernel", (int64_t)E * H); r.pr_b = get(p + "/proj_ref/bias", H);
+        if (h->tw) {
+            r.et_k = get(p + "/emb_time/kernel", H); r.et_b = get(p + "/emb_time/bias", H);
+            r.pt_k = get(p + "/proj_t/kernel", H * H); r.pt_b = get(p + "/proj_t/bias", H);
+        } else {
+            r.et_k = r.et_b = r.pt_k = r.pt_b = nullptr;
+        }
+    }
+    if (!missing.empty()) return fail(h, VRPB200_E_WEIGHTS, "missing or mis-sized variables:%s", missing.c_str());
+
+    // ---- build the blob on the host --------------------------------------------------------------
+    std::vector<float> blob;
+    auto reserve = [&](size_t nfl) { size_t o = blob.size(); blob.resize(o + ((nfl + 31) / 32) * 32, 0.0f); return o; };   // 128 B aligned pieces
+    auto put = [&](const float* src, size_t nfl) { size_t o = reserve(nfl); memcpy(&blob[o], src, nfl * 4); return o; };
+
+    // phase A: gates kernel, rows 0..127 = W_lstm[E + k], rows 128..128+D1-1 = W_emb . W_lstm[:E], rest zero;
+    // layout [slab s][kk 8][uh 2][part 2][lane 32][gate 4], unit = uh*64 + 2*lane + part, k = 8 s + kk.
+    const size_t oWg = reserve((size_t)kGateSlabs * kSlabFloats);
+    const size_t obg = reserve(4 * H);
+    {
+        std::vector<double> Wx((size_t)D1 * 4 * H, 0.0), bx(4 * H, 0.0);
+        for (int col = 0; col < 4 * H; ++col) {
+            for (int cc = 0; cc < D1; ++cc) {
+                double s = 0;
+                for (int e2 = 0; e2 < E; ++e2) s += (double)emb_k[cc * E + e2] * lstm_k[(size_t)e2 * 4 * H + col];
+                Wx[(size_t)cc * 4 * H + col] = s;
+            }
+            double s = lstm_b[col];
+            for (int e2 = 0; e2 < E; ++e2) s += (double)emb_b[e2] * lstm_k[(size_t)e2 * 4 * H + col];
+            bx[col] = s;
+        }
+        for (int k = 0; k < kKG; ++k) {
+            const int s = k / 8, kk = k % 8;
+            for (int unit = 0; unit < H; ++unit) {
+                const int uh = unit / 64, lane = (unit % 64) / 2, part = unit % 2;
+                for (int g = 0; g < 4; ++g) {
+                    const int col = g * H + unit;
+                    float val = 0.0f;
+                    if (k < H) val = lstm_k[(size_t)(E + k) * 4 * H + col];
+                    else if (k - H < D1) val = (float)Wx[(size_t)(k - H) * 4 * H + col];
+                    blob[oWg + (size_t)s * kSlabFloats + ((size_t)((kk * 2 + uh) * 2 + part) * 32 + lane) * 4 + g] = val;
+                }
+            }
+        }
+        for (int unit = 0; unit < H; ++unit)
+            for (int g = 0; g < 4; ++g) blob[obg + unit * 4 + g] = (float)bx[g * H + unit];
+    }
+    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce; };
+    std::vector<AttOff> ao(natt);
+    for (int a = 0; a < natt; ++a) {
+        const RawHost& r = rh[a];
+        AttOff& o = ao[a];
+        o.Wq = put(r.pq_k, (size_t)H * H);   // [k][unit] row-major == 4 slabs of 32 k-rows
+        o.bq = reserve(H); o.A = reserve(4 * H); o.gd = reserve(H); o.gl = reserve(H); o.gt = reserve(H);
+        o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H);
+        for (int hh = 0; hh < H; ++hh) {
+            double gdv = 0, cd = r.pd_b[hh], gld = 0, cld = r.pld_b[hh], gtv = 0, ct = 0;
+            for (int k = 0; k < H; ++k) {
+                gdv += (double)r.ed_k[k] * r.pd_k[k * H + hh];  cd += (double)r.ed_b[k] * r.pd_k[k * H + hh];
+                gld += (double)r.eld_k[k] * r.pld_k[k * H + hh]; cld += (double)r.eld_b[k] * r.pld_k[k * H + hh];
+            }
+            if (h->tw) {
+                ct = r.pt_b[hh];
+                for (int k = 0; k < H; ++k) { gtv += (double)r.et_k[k] * r.pt_k[k * H + hh]; ct += (double)r.et_b[k] * r.pt_k[k * H + hh]; }
+            }
+            double ce = r.pr_b[hh];
+            for (int e2 = 0; e2 < E; ++e2) ce += (double)emb_b[e2] * r.pr_k[e2 * H + hh];
+            for (int cc = 0; cc < 4; ++cc) {
+                double s = 0;
+                if (cc < D1) for (int e2 = 0; e2 < E; ++e2) s += (double)emb_k[cc * E + e2] * r.pr_k[e2 * H + hh];
+                blob[o.Au + cc * H + hh] = (float)s;
+                blob[o.A + cc * H + hh] = (float)(s * (double)kTwoLog2e);
+            }
+            blob[o.ce + hh] = (float)ce;
+            blob[o.bq + hh] = (float)((double)r.pq_b[hh] + ce + cd + cld + ct);
+            blob[o.gd + hh] = (float)((gdv - gld) * (double)kTwoLog2e);
+            blob[o.gl + hh] = (float)gld;
+            blob[o.gt + hh] = (float)gtv;
+        }
+    }
+    // raw copies for the stand-alone (as-written) kernels
+    const size_t o_emb_k = put(emb_k, (size_t)D1 * E), o_emb_b = put(emb_b, E);
+    const size_t o_lstm_k = put(lstm_k, (size_t)(E + H) * 4 * H), o_lstm_b = put(lstm_b, 4 * H);
+    struct RawOff { size_t v, ed_k, ed_b, eld_k, eld_b, et_k, et_b, pd_k, pd_b, pld_k, pld_b, pt_k, pt_b, pq_k, pq_b, pr_k, pr_b; };
+    std::vector<RawOff> ro(natt);
+    for (int a = 0; a < natt; ++a) {
+        const RawHost& r = rh[a];
+        RawOff& o = ro[a];
+        o.v = put(r.v, H);
+        o.ed_k = put(r.ed_k, H); o.ed_b = put(r.ed_b, H); o.eld_k = put(r.eld_k, H); o.eld_b = put(r.eld_b, H);
+        o.pd_k = put(r.pd_k, H * H); o.pd_b = put(r.pd_b, H); o.pld_k = put(r.pld_k, H * H); o.pld_b = put(r.pld_b, H);
+        o.pq_k = put(r.pq_k, H * H); o.pq_b = put(r.pq_b, H); o.pr_k = put(r.pr_k, (size_t)E * H); o.pr_b = put(r.pr_b, H);
+        if (h->tw) { o.et_k = put(r.et_k, H); o.et_b = put(r.et_b, H); o.pt_k = put(r.pt_k, H * H); o.pt_b = put(r.pt_b, H); }
+        else { o.et_k = o.et_b = o.pt_k = o.pt_b = 0; }
+    }
+
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->d_blob && h->blob_floats < blob.size()) { cudaFree(h->d_blob); h->d_blob = nullptr; }
+    if (!h->d_blob) CUDA_TRY(h, cudaMalloc((void**)&h->d_blob, blob.size() * 4));
+    h->blob_floats = blob.size();
+    CUDA_TRY(h, cudaMemcpy(h->d_blob, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+    const float* d = h->d_blob;
+    h->Wg = d + oWg;
+    h->bg = d + obg;
+    for (int a = 0; a < natt; ++a) {
+        h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
+                               d + ao[a].v, d + ao[a].Au, d + ao[a].ce};
+        const RawOff& o = ro[a];
+        RawAtt& ra = h->raw.att[a];
+        ra.v = d + o.v;
+        ra.emb_d_k = d + o.ed_k; ra.emb_d_b = d + o.ed_b; ra.emb_ld_k = d + o.eld_k; ra.emb_ld_b = d + o.eld_b;
+        ra.emb_t_k = d + o.et_k; ra.emb_t_b = d + o.et_b;
+        ra.proj_d_k = d + o.pd_k; ra.proj_d_b = d + o.pd_b; ra.proj_ld_k = d + o.pld_k; ra.proj_ld_b = d + o.pld_b;
+        ra.proj_t_k = d + o.pt_k; ra.proj_t_b = d + o.pt_b;
+        ra.proj_q_k = d + o.pq_k; ra.proj_q_b = d + o.pq_b; ra.proj_ref_k = d + o.pr_k; ra.proj_ref_b = d + o.pr_b;
+    }
+    h->raw.lstm_k = d + o_lstm_k;
+    h->raw.lstm_b = d + o_lstm_b;
+    h->raw.n_glimpses = c.n_glimpses;
+    h->raw_emb_k = d + o_emb_k;
+    h->raw_emb_b = d + o_emb_b;
+    h->have_weights = true;
+    return VRPB200_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int RB, bool TW>
+int launch_rollout_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_kernel<RB, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout_kernel<RB, TW><<<grid, RB * 8, smem, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
+    const vrpb200_config& c = h->cfg;
+    const int FD = h->tw ? 4 : 2;
+    // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks,
+    // else the smallest (more, lighter CTAs for small batches)
+    const int cand[4] = {64, 48, 32, 16};
+    int RB = 0;
+    if (c.rows_per_cta) {
+        RB = c.rows_per_cta;
+    } else {
+        for (int i = 0; i < 4 && !RB; ++i) {
+            const int rb = cand[i];
+            if (make_layout(rb, rb, c.n_nodes, FD).total > h->max_smem_optin) continue;
+            if ((a.B + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
+        }
+    }
+    if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory");
+    a.IB = RB / a.W;
+    const SmemLayout L = make_layout(RB, a.IB, c.n_nodes, FD);
+    if (L.total > h->max_smem_optin)
+        return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, L.total, h->max_smem_optin);
+    const long long grid = (a.B + a.IB - 1) / a.IB;
+    if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
+    h->last_launch[0] = (int)grid; h->last_launch[1] = RB * 8; h->last_launch[2] = L.total; h->last_launch[3] = RB;
+    h->last_launch[4] = 1;
+    int rc = 0;
+#define DISPATCH(rb)                                                                     \
+    case rb:                                                                             \
+        rc = h->tw ? launch_rollout_t<rb, true>(h, a, (int)grid, L.total, st)            \
+                   : launch_rollout_t<rb, false>(h, a, (int)grid, L.total, st);          \
+        break;
+    switch (RB) {
+        DISPATCH(64) DISPATCH(48) DISPATCH(32) DISPATCH(16)
+        default: return fail(h, VRPB200_E_ARG, "bad rows_per_cta");
+    }
+#undef DISPATCH
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode, int beam_width,
+                    const float* d_uniforms, const float* d_uniforms_retry, uint64_t seed, int32_t* d_idx,
+                    float* d_cost, float* d_logprob, int32_t* d_beam_parent, const vrpb200_trace* trace,
+                    void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights) return fail(h, VRPB200_E_STATE, "rollout before set_weights");
+    if (!d_input || !d_cost || !d_idx) return fail(h, VRPB200_E_ARG, "d_input, d_idx and d_cost are required");
+    if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
+    if (mode != VRPB200_GREEDY && mode != VRPB200_STOCHASTIC && mode != VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "bad mode %d", mode);
+    if (mode == VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "beam search is not implemented by the fused kernel yet");
+    if (h->cfg.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "n_glimpses > 0 is not implemented by the fused kernel yet (use decode_step)");
+    (void)d_beam_parent; (void)beam_width;
+    if (mode == VRPB200_STOCHASTIC && ((d_uniforms == nullptr) != (d_uniforms_retry == nullptr)))
+        return fail(h, VRPB200_E_ARG, "pass both uniform buffers or neither");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const vrpb200_config& c = h->cfg;
+    RolloutArgs a;
+    memset(&a, 0, sizeof a);
+    a.input = d_input; a.Wg = h->Wg; a.bg = h->bg; a.att = h->att[c.n_glimpses];
+    a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
+    a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
+    if (trace) {
+        a.tr_logits = trace->d_logits; a.tr_probs = trace->d_probs; a.tr_masks = trace->d_masks;
+        a.fin_demand = trace->d_final_demand; a.fin_load = trace->d_final_load; a.fin_time = trace->d_final_time;
+        a.fin_mask = trace->d_final_mask; a.steps_out = trace->d_steps;
+    }
+    a.full = (a.tr_logits || a.tr_probs || a.tr_masks) ? 1 : 0;
+    a.seed = seed; a.B = B; a.W = 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
+    a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
+    a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
+    return launch_rollout(h, a, (cudaStream_t)stream);
+}
+
+int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int mode, int beam_width,
+                         uint64_t seed, int32_t* h_idx, float* h_cost) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h_input || !h_cost) return fail(h, VRPB200_E_ARG, "h_input and h_cost are required");
+    if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
+    const vrpb200_config& c = h->cfg;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (!h->own_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    const int W = 1;
+    const size_t in_b = (size_t)B * c.n_nodes * c.input_dim * 4, idx_b = (size_t)c.decode_len * B * W * 4, cost_b = (size_t)B * W * 4;
+    int rc;
+    if ((rc = ensure(h, &h->pin_in, &h->pin_in_bytes, in_b, true))) return rc;
+    if ((rc = ensure(h, &h->pin_cost, &h->pin_cost_bytes, cost_b, true))) return rc;
+    if ((rc = ensure(h, &h->dev_in, &h->dev_in_bytes, in_b, false))) return rc;
+    if ((rc = ensure(h, &h->dev_idx, &h->dev_idx_bytes, idx_b, false))) return rc;
+    if ((rc = ensure(h, &h->dev_cost, &h->dev_cost_bytes, cost_b, false))) return rc;
+    if (h_idx && (rc = ensure(h, &h->pin_idx, &h->pin_idx_bytes, idx_b, true))) return rc;
+    memcpy(h->pin_in, h_input, in_b);
+    CUDA_TRY(h, cudaMemcpyAsync(h->dev_in, h->pin_in, in_b, cudaMemcpyHostToDevice, h->own_stream));
+    rc = vrpb200_rollout(h, h->dev_in, B, mode, beam_width, nullptr, nullptr, seed, h->dev_idx, h->dev_cost, nullptr,
+                         nullptr, nullptr, h->own_stream);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->pin_cost, h->dev_cost, cost_b, cudaMemcpyDeviceToHost, h->own_stream));
+    if (h_idx) CUDA_TRY(h, cudaMemcpyAsync(h->pin_idx, h->dev_idx, idx_b, cudaMemcpyDeviceToHost, h->own_stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
+    memcpy(h_cost, h->pin_cost, cost_b);
+    if (h_idx) memcpy(h_idx, h->pin_idx, idx_b);
+    return VRPB200_OK;
+}
+
+int vrpb200_env_reset(vrpb200_handle* h, const float* d_input, int64_t B, int beam_width, float* d_demand,
+                      float* d_load, float* d_time, float* d_mask, float* d_prev_xy, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_input || !d_demand || !d_load || !d_mask || B < 1 || beam_width < 1) return fail(h, VRPB200_E_ARG, "env_reset: bad argument");
+    if (h->tw && (!d_time || !d_prev_xy)) return fail(h, VRPB200_E_ARG, "env_reset: VRPTW needs d_time and d_prev_xy");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long R = B * beam_width;
+    const int wpb = 8;
+    env_reset_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        d_input, B, beam_width, h->cfg.n_nodes, h->cfg.input_dim, h->cfg.capacity, d_demand, d_load, d_time, d_mask, d_prev_xy);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_env_step(vrpb200_handle* h, const float* d_input, int64_t B, int beam_width, const int64_t* d_idx,
+                     const int64_t* d_beam_parent, const float* d_demand_in, const float* d_load_in,
+                     const float* d_time_in, const float* d_prev_xy_in, float* d_demand, float* d_load, float* d_time,
+                     float* d_mask, float* d_prev_xy, float* d_sat, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_input || !d_idx || !d_demand_in || !d_load_in || !d_demand || !d_load || !d_mask || B < 1 || beam_width < 1)
+        return fail(h, VRPB200_E_ARG, "env_step: bad argument");
+    if (h->tw && (!d_time_in || !d_prev_xy_in || !d_time || !d_prev_xy)) return fail(h, VRPB200_E_ARG, "env_step: VRPTW needs time and prev_xy");
+    if (d_beam_parent && (d_demand_in == d_demand || d_load_in == d_load))
+        return fail(h, VRPB200_E_ARG, "env_step: with beam_parent the in and out state must not alias");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long R = B * beam_width;
+    const int wpb = 8;
+    const unsigned grid = (unsigned)((R + wpb - 1) / wpb);
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    if (h->tw)
+        env_step_kernel<true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+            d_input, B, beam_width, h->cfg.n_nodes, h->cfg.input_dim, h->cfg.capacity, (const long long*)d_idx,
+            (const long long*)d_beam_parent, d_demand_in, d_load_in, d_time_in, d_prev_xy_in, d_demand, d_load, d_time,
+            d_mask, d_prev_xy, d_sat);
+    else
+        env_step_kernel<false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
+            d_input, B, beam_width, h->cfg.n_nodes, h->cfg.input_dim, h->cfg.capacity, (const long long*)d_idx,
+            (const long long*)d_beam_parent, d_demand_in, d_load_in, d_time_in, d_prev_xy_in, d_demand, d_load, d_time,
+            d_mask, d_prev_xy, d_sat);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_embed(vrpb200_handle* h, const float* d_input_pnt, int64_t M, float* d_emb, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights) return fail(h, VRPB200_E_STATE, "embed before set_weights");
+    if (!d_input_pnt || !d_emb || M < 1) return fail(h, VRPB200_E_ARG, "embed: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long tot = M * h->cfg.embedding_dim;
+    embed_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_input_pnt, M, h->D1, h->cfg.embedding_dim,
+                                                                                 h->raw_emb_k, h->raw_emb_b, d_emb);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_attention(vrpb200_handle* h, int att, int64_t R, const float* d_query, const float* d_ref,
+                      const float* d_demand, const float* d_load, const float* d_time, float* d_e, float* d_logits,
+                      void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights) return fail(h, VRPB200_E_STATE, "attention before set_weights");
+    if (!d_query || !d_ref || !d_demand || !d_load || !d_logits || R < 1) return fail(h, VRPB200_E_ARG, "attention: bad argument");
+    if (h->tw && !d_time) return fail(h, VRPB200_E_ARG, "attention: VRPTW needs d_time");
+    if (att < -1 || att >= h->cfg.n_glimpses) return fail(h, VRPB200_E_ARG, "attention: module %d out of range", att);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const bool pointer = att < 0;
+    const RawAtt& w = h->raw.att[pointer ? h->cfg.n_glimpses : att];
+    const int use_tanh = pointer ? h->cfg.use_tanh : 0;   // glimpses are built with use_tanh=False, decode_step.py:41-46
+    if (h->tw)
+        attention_kernel<true><<<(unsigned)R, kH, 0, (cudaStream_t)stream>>>(w, h->cfg.n_nodes, h->cfg.embedding_dim, d_query, d_ref,
+                                                                             d_demand, d_load, d_time, use_tanh,
+                                                                             h->cfg.tanh_exploration, d_e, d_logits);
+    else
+        attention_kernel<false><<<(unsigned)R, kH, 0, (cudaStream_t)stream>>>(w, h->cfg.n_nodes, h->cfg.embedding_dim, d_query, d_ref,
+                                                                              d_demand, d_load, d_time, use_tanh,
+                                                                              h->cfg.tanh_exploration, d_e, d_logits);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp, const float* d_context,
+                        const float* d_demand, const float* d_load, const float* d_time, const float* d_mask,
+                        float* d_c, float* d_h, float* d_logit, float* d_prob, float* d_logprob, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights) return fail(h, VRPB200_E_STATE, "decode_step before set_weights");
+    if (!d_decoder_inp || !d_context || !d_demand || !d_load || !d_mask || !d_c || !d_h || !d_logit || !d_prob || !d_logprob || R < 1)
+        return fail(h, VRPB200_E_ARG, "decode_step: bad argument");
+    if (h->tw && !d_time) return fail(h, VRPB200_E_ARG, "decode_step: VRPTW needs d_time");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const vrpb200_config& c = h->cfg;
+    if (h->tw)
+        decode_step_kernel<true><<<(unsigned)R, kH, 0, (cudaStream_t)stream>>>(
+            h->raw, c.n_nodes, c.embedding_dim, d_decoder_inp, d_context, d_demand, d_load, d_time, d_mask, d_c, d_h,
+            c.use_tanh, c.tanh_exploration, c.mask_glimpses, c.mask_pointer, c.forget_bias, d_logit, d_prob, d_logprob);
+    else
+        decode_step_kernel<false><<<(unsigned)R, kH, 0, (cudaStream_t)stream>>>(
+            h->raw, c.n_nodes, c.embedding_dim, d_decoder_inp, d_context, d_demand, d_load, d_time, d_mask, d_c, d_h,
+            c.use_tanh, c.tanh_exploration, c.mask_glimpses, c.mask_pointer, c.forget_bias, d_logit, d_prob, d_logprob);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t R, int A, float* d_cost, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_actions || !d_cost || T < 1 || R < 1 || A < 2) return fail(h, VRPB200_E_ARG, "reward: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    reward_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, T, R, A, d_cost);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_last_launch(const vrpb200_handle* h, int32_t out[8]) {
+    if (!h || !out) return VRPB200_E_ARG;
+    memcpy(out, h->last_launch, sizeof h->last_launch);
+    return VRPB200_OK;
+}
+
+}  // extern "C"

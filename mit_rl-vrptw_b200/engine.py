@@ -1,0 +1,238 @@
+"""Thin host wrapper over the C ABI: one ``Engine`` = one ``vrpb200_handle`` on one device.
+
+torch is used for device memory and streams only (plumbing); every computation is a call into
+libvrpb200.so.  There is no fallback: constructing an Engine without the library or without a
+B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Config, Trace, VrpB200Error, DECODE_MODES
+
+
+def config_from_args(args: dict, rows_per_cta: int = 0) -> Config:
+    """args = the reference's merged flag/task dict (configs.py:28-111 + task_specific_params.py)."""
+    task_name = args.get("task_name") or ("vrptw" if args["input_dim"] == 5 else "vrp")
+    return Config(
+        task=_lib.TASK_VRPTW if task_name.startswith("vrptw") else _lib.TASK_VRP,
+        n_nodes=args["n_nodes"], n_cust=args["n_cust"], input_dim=args["input_dim"],
+        embedding_dim=args.get("embedding_dim", 30), hidden_dim=args.get("hidden_dim", 128),
+        decode_len=args["decode_len"], n_glimpses=args.get("n_glimpses", 0),
+        use_tanh=int(bool(args.get("use_tanh", False))), mask_glimpses=int(bool(args.get("mask_glimpses", True))),
+        mask_pointer=int(bool(args.get("mask_pointer", True))), rows_per_cta=rows_per_cta,
+        capacity=float(args["capacity"]), tanh_exploration=float(args.get("tanh_exploration", 10.0)),
+        forget_bias=float(args.get("forget_bias", 1.0)))
+
+
+@dataclass
+class RolloutOutput:
+    idxs: torch.Tensor                      # [T, R] int32
+    R: torch.Tensor                         # [R] fp32 tour length
+    logprobs: Optional[torch.Tensor] = None  # [T, R]
+    logits: Optional[torch.Tensor] = None    # [T, R, N]
+    probs: Optional[torch.Tensor] = None
+    masks: Optional[torch.Tensor] = None
+    final_demand: Optional[torch.Tensor] = None
+    final_load: Optional[torch.Tensor] = None
+    final_time: Optional[torch.Tensor] = None
+    final_mask: Optional[torch.Tensor] = None
+    steps: Optional[torch.Tensor] = None     # [grid] int32 decode steps executed per instance block
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise VrpB200Error("no CUDA device: the rollout path has no CPU implementation")
+        self.args = dict(args)
+        self.cfg = config_from_args(args, rows_per_cta)
+        self.device = torch.device("cuda", device)
+        self.handle = C.c_void_p()
+        rc = self.lib.vrpb200_create(C.byref(self.cfg), device, C.byref(self.handle))
+        if rc != 0:
+            raise VrpB200Error(f"vrpb200_create: {self.lib.vrpb200_last_error(None).decode()}")
+        self.tw = self.cfg.task == _lib.TASK_VRPTW
+        self.N, self.T, self.D = self.cfg.n_nodes, self.cfg.decode_len, self.cfg.input_dim
+        self.E, self.H = self.cfg.embedding_dim, self.cfg.hidden_dim
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise VrpB200Error(f"{what}: {self.lib.vrpb200_last_error(self.handle).decode()} (code {rc})")
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _f32(self, t, name):
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t, dtype=np.float32))
+        t = t.to(device=self.device, dtype=torch.float32)
+        return t.contiguous()
+
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.vrpb200_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- weights ---------------------------------------------------------------------------------
+    def set_weights(self, params: Dict[str, np.ndarray]):
+        """params: TF-1 variable name -> array (what tf.train.Saver holds, attention_agent.py:79-80)."""
+        names = sorted(params)
+        arrs = [np.ascontiguousarray(np.asarray(params[k], dtype=np.float32)) for k in names]
+        c_names = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        c_ptrs = (C.c_void_p * len(names))(*[a.ctypes.data for a in arrs])
+        c_sizes = (C.c_int64 * len(names))(*[a.size for a in arrs])
+        self._check(self.lib.vrpb200_set_weights(self.handle, len(names), c_names, c_ptrs, c_sizes), "set_weights")
+
+    # -- the hot path ----------------------------------------------------------------------------
+    def rollout(self, input_data, decode_type: str = "greedy", beam_width: int = 1, uniforms=None, uniforms_retry=None,
+                seed: int = 0, want_logprobs: bool = False, trace: bool = False, final_state: bool = False,
+                want_steps: bool = False) -> RolloutOutput:
+        x = self._f32(input_data, "input_data")
+        if x.dim() != 3 or x.shape[1] != self.N or x.shape[2] != self.D:
+            raise VrpB200Error(f"input_data must be [B,{self.N},{self.D}], got {tuple(x.shape)}")
+        B = x.shape[0]
+        mode = DECODE_MODES[decode_type]
+        W = beam_width if mode == _lib.BEAM else 1
+        R = B * W
+        dev = self.device
+        idx = torch.empty((self.T, R), dtype=torch.int32, device=dev)
+        cost = torch.empty((R,), dtype=torch.float32, device=dev)
+        out = RolloutOutput(idxs=idx, R=cost)
+        if want_logprobs:
+            out.logprobs = torch.empty((self.T, R), dtype=torch.float32, device=dev)
+        tr = Trace()
+        if trace:
+            out.logits = torch.empty((self.T, R, self.N), dtype=torch.float32, device=dev)
+            out.probs = torch.empty_like(out.logits)
+            out.masks = torch.empty_like(out.logits)
+            tr.d_logits, tr.d_probs, tr.d_masks = out.logits.data_ptr(), out.probs.data_ptr(), out.masks.data_ptr()
+        if final_state or trace:
+            out.final_demand = torch.empty((R, self.N), dtype=torch.float32, device=dev)
+            out.final_mask = torch.empty((R, self.N), dtype=torch.float32, device=dev)
+            out.final_load = torch.empty((R,), dtype=torch.float32, device=dev)
+            out.final_time = torch.zeros((R,), dtype=torch.float32, device=dev)
+            tr.d_final_demand, tr.d_final_mask = out.final_demand.data_ptr(), out.final_mask.data_ptr()
+            tr.d_final_load, tr.d_final_time = out.final_load.data_ptr(), out.final_time.data_ptr()
+        if want_steps:
+            out.steps = torch.zeros(((B + 15) // 16,), dtype=torch.int32, device=dev)   # upper bound on the grid
+            tr.d_steps = out.steps.data_ptr()
+        u1 = u2 = None
+        if uniforms is not None:
+            u1, u2 = self._f32(uniforms, "uniforms"), self._f32(uniforms_retry, "uniforms_retry")
+            if tuple(u1.shape) != (self.T, R) or tuple(u2.shape) != (self.T, R):
+                raise VrpB200Error(f"uniforms must be [{self.T},{R}]")
+        self._check(self.lib.vrpb200_rollout(
+            self.handle, _ptr(x), B, mode, W, _ptr(u1), _ptr(u2), C.c_uint64(seed), _ptr(idx), _ptr(cost),
+            _ptr(out.logprobs), None, C.byref(tr), self._stream()), "rollout")
+        if want_steps:
+            out.steps = out.steps[: self.last_launch()["grid"]]
+        return out
+
+    def rollout_host(self, input_np: np.ndarray, decode_type: str = "greedy", beam_width: int = 1, seed: int = 0,
+                     want_idx: bool = True):
+        """Host buffers in, host buffers out (H2D + rollout + D2H inside the call)."""
+        x = np.ascontiguousarray(input_np, dtype=np.float32)
+        B = x.shape[0]
+        mode = DECODE_MODES[decode_type]
+        W = beam_width if mode == _lib.BEAM else 1
+        cost = np.empty((B * W,), np.float32)
+        idx = np.empty((self.T, B * W), np.int32) if want_idx else None
+        self._check(self.lib.vrpb200_rollout_host(
+            self.handle, C.c_void_p(x.ctypes.data), B, mode, W, C.c_uint64(seed),
+            C.c_void_p(idx.ctypes.data) if want_idx else None, C.c_void_p(cost.ctypes.data)), "rollout_host")
+        return idx, cost
+
+    def last_launch(self) -> dict:
+        arr = (C.c_int32 * 8)()
+        self._check(self.lib.vrpb200_last_launch(self.handle, arr), "last_launch")
+        return dict(grid=arr[0], block=arr[1], smem=arr[2], rows_per_cta=arr[3], kernels=arr[4])
+
+    # -- Env -------------------------------------------------------------------------------------
+    def env_reset(self, input_data: torch.Tensor, beam_width: int = 1):
+        x = self._f32(input_data, "input_data")
+        B = x.shape[0]
+        R = B * beam_width
+        dev = self.device
+        st = dict(demand=torch.empty((R, self.N), device=dev), load=torch.empty((R,), device=dev),
+                  time=torch.zeros((R,), device=dev), mask=torch.empty((R, self.N), device=dev),
+                  prev_xy=torch.zeros((R, 2), device=dev))
+        self._check(self.lib.vrpb200_env_reset(self.handle, _ptr(x), B, beam_width, _ptr(st["demand"]), _ptr(st["load"]),
+                                               _ptr(st["time"]), _ptr(st["mask"]), _ptr(st["prev_xy"]), self._stream()),
+                    "env_reset")
+        return st
+
+    def env_step(self, input_data: torch.Tensor, beam_width: int, state: dict, idx: torch.Tensor,
+                 beam_parent: Optional[torch.Tensor] = None):
+        x = self._f32(input_data, "input_data")
+        B = x.shape[0]
+        R = B * beam_width
+        dev = self.device
+        idx = idx.to(device=dev, dtype=torch.int64).reshape(R).contiguous()
+        par = None if beam_parent is None else beam_parent.to(device=dev, dtype=torch.int64).reshape(R).contiguous()
+        new = dict(demand=torch.empty((R, self.N), device=dev), load=torch.empty((R,), device=dev),
+                   time=torch.zeros((R,), device=dev), mask=torch.empty((R, self.N), device=dev),
+                   prev_xy=torch.zeros((R, 2), device=dev))
+        d_sat = torch.empty((R,), device=dev)
+        self._check(self.lib.vrpb200_env_step(
+            self.handle, _ptr(x), B, beam_width, _ptr(idx), _ptr(par), _ptr(state["demand"]), _ptr(state["load"]),
+            _ptr(state["time"]), _ptr(state["prev_xy"]), _ptr(new["demand"]), _ptr(new["load"]), _ptr(new["time"]),
+            _ptr(new["mask"]), _ptr(new["prev_xy"]), _ptr(d_sat), self._stream()), "env_step")
+        return new, d_sat
+
+    # -- stand-alone model pieces ------------------------------------------------------------------
+    def embed(self, input_pnt: torch.Tensor) -> torch.Tensor:
+        x = self._f32(input_pnt, "input_pnt")
+        lead = x.shape[:-1]
+        M = int(np.prod(lead))
+        out = torch.empty((*lead, self.E), device=self.device)
+        self._check(self.lib.vrpb200_embed(self.handle, _ptr(x), M, _ptr(out), self._stream()), "embed")
+        return out
+
+    def attention(self, att: int, query, ref, demand, load, time=None):
+        q, r, d, l = self._f32(query, "q"), self._f32(ref, "ref"), self._f32(demand, "demand"), self._f32(load, "load")
+        t = None if time is None else self._f32(time, "time")
+        R = q.shape[0]
+        e = torch.empty((R, self.N, self.H), device=self.device)
+        logits = torch.empty((R, self.N), device=self.device)
+        self._check(self.lib.vrpb200_attention(self.handle, att, R, _ptr(q), _ptr(r), _ptr(d), _ptr(l), _ptr(t), _ptr(e),
+                                               _ptr(logits), self._stream()), "attention")
+        return e, logits
+
+    def decode_step(self, decoder_inp, context, demand, load, time, mask, c, h):
+        """c, h are updated in place; returns logit, prob, logprob [R, N]."""
+        x, ctx = self._f32(decoder_inp, "decoder_inp"), self._f32(context, "context")
+        R = ctx.shape[0]
+        x = x.reshape(R, self.E)
+        d, l, m = self._f32(demand, "demand"), self._f32(load, "load"), self._f32(mask, "mask")
+        t = None if time is None else self._f32(time, "time")
+        logit = torch.empty((R, self.N), device=self.device)
+        prob, logprob = torch.empty_like(logit), torch.empty_like(logit)
+        self._check(self.lib.vrpb200_decode_step(self.handle, R, _ptr(x), _ptr(ctx), _ptr(d), _ptr(l), _ptr(t), _ptr(m),
+                                                 _ptr(c), _ptr(h), _ptr(logit), _ptr(prob), _ptr(logprob), self._stream()),
+                    "decode_step")
+        return logit, prob, logprob
+
+    def reward(self, actions: torch.Tensor) -> torch.Tensor:
+        a = self._f32(actions, "actions")
+        T, R, A = a.shape
+        out = torch.empty((R,), device=self.device)
+        self._check(self.lib.vrpb200_reward(self.handle, _ptr(a), T, R, A, _ptr(out), self._stream()), "reward")
+        return out

@@ -19,3 +19,16 @@ def load_golden(name):
     args = O.default_args(meta["task"], **meta["over"])
     params = O.init_params(args, seed=int(fx["param_seed"]), bias_scale=float(fx["bias_scale"]))
     return fx, args, params
+
+
+def load_pkg():
+    """The product package (directory name has a hyphen)."""
+    import importlib
+    return importlib.import_module("mit_rl-vrptw_b200")
+
+
+def first_divergence(idx_a, idx_b):
+    """[T,R] index arrays -> per-row first step at which they differ (T if never)."""
+    T = idx_a.shape[0]
+    neq = idx_a != idx_b
+    return np.where(neq.any(0), neq.argmax(0), T)

@@ -1,0 +1,184 @@
+"""CUDA rollout (through the C ABI) against the golden fixtures produced by the reference's own code
+and against the numpy oracle on seeded instances.  Needs a B200: run with ``-m gpu``.
+
+Tolerances (BASELINE.json north_star): env state, masks and - given identical logits - chosen indices
+bit-exact; logits / tour lengths within 1e-4 relative (fp32).
+"""
+import numpy as np
+import pytest
+
+from oracle import restatement as O
+from tests.helpers import GOLDEN_INDEX, first_divergence, load_golden, load_pkg
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_RTOL = 1e-4      # north_star: "logits and tour lengths must agree within 1e-4 relative (fp32)"
+LOGIT_ATOL = 2e-5      # u passes through 0: floor of the relative test
+MASKED_ATOL = 0.02     # logit - 1e5*k: one fp32 ulp at 1e5 is 0.0078
+
+
+def _engine(args, params, **kw):
+    import torch
+    pkg = load_pkg()
+    eng = pkg.Engine(args, device=0, **kw)
+    eng.set_weights(params)
+    return eng, torch
+
+
+def _compare_trace(out, fx, args, decode_type):
+    idx = out.idxs.cpu().numpy().astype(np.int64)
+    T, R = idx.shape
+    ref_idx = fx["idxs"]
+    div = first_divergence(idx, ref_idx)
+    assert (div == T).all(), f"indices diverge from the reference at steps {div[div < T]}"
+    masks = out.masks.cpu().numpy()
+    np.testing.assert_array_equal(masks, fx["masks"])                                   # bit-exact
+    logits, ref_logits = out.logits.cpu().numpy(), fx["logits"]
+    unmasked = fx["masks"] == 0
+    np.testing.assert_allclose(logits[unmasked], ref_logits[unmasked], rtol=LOGIT_RTOL, atol=LOGIT_ATOL)
+    np.testing.assert_allclose(logits[~unmasked], ref_logits[~unmasked], rtol=0, atol=MASKED_ATOL)
+    np.testing.assert_allclose(out.probs.cpu().numpy(), fx["probs"], rtol=2e-4, atol=1e-6)
+    np.testing.assert_allclose(out.logprobs.cpu().numpy(), fx["logprobs"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(out.R.cpu().numpy(), fx["R"], rtol=1e-4)
+    np.testing.assert_array_equal(out.final_demand.cpu().numpy(), fx["final_demand"])   # bit-exact
+    np.testing.assert_array_equal(out.final_load.cpu().numpy(), fx["final_load"])
+    np.testing.assert_array_equal(out.final_mask.cpu().numpy(), fx["final_mask"])
+    if args["task_name"] == "vrptw":
+        np.testing.assert_array_equal(out.final_time.cpu().numpy(), fx["final_time"])
+
+
+FUSED_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
+               if m["decode_type"] in ("greedy", "stochastic") and not m["over"].get("n_glimpses")]
+
+
+@pytest.mark.parametrize("name", FUSED_CASES)
+@pytest.mark.parametrize("rows_per_cta", [0, 64])
+def test_rollout_matches_reference_fixture(name, rows_per_cta):
+    fx, args, params = load_golden(name)
+    meta = GOLDEN_INDEX[name]
+    eng, torch = _engine(args, params, rows_per_cta=rows_per_cta)
+    x = torch.from_numpy(fx["data"].astype(np.float32)).cuda()
+    out = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"),
+                      want_logprobs=True, trace=True)
+    torch.cuda.synchronize()
+    _compare_trace(out, fx, args, meta["decode_type"])
+
+
+@pytest.mark.parametrize("name", [n for n in FUSED_CASES if GOLDEN_INDEX[n]["decode_type"] == "greedy"])
+def test_fast_path_equals_trace_path(name):
+    """Skipping masked nodes + early exit must not change any output."""
+    fx, args, params = load_golden(name)
+    eng, torch = _engine(args, params)
+    x = torch.from_numpy(fx["data"].astype(np.float32)).cuda()
+    fast = eng.rollout(x, "greedy", want_logprobs=True, final_state=True, want_steps=True)
+    full = eng.rollout(x, "greedy", want_logprobs=True, trace=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fast.idxs, full.idxs)
+    assert torch.equal(fast.R, full.R)
+    assert torch.equal(fast.logprobs, full.logprobs)
+    assert torch.equal(fast.final_demand, full.final_demand)
+    assert torch.equal(fast.final_mask, full.final_mask)
+    assert torch.equal(fast.final_load, full.final_load)
+    assert int(fast.steps.max()) <= args["decode_len"]
+
+
+@pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
+                                         ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
+@pytest.mark.parametrize("bias", [0.0, 0.3])
+def test_greedy_vs_oracle_seeded(task, B, seed, bias):
+    """Ragged batch sizes, every task size; per-instance comparison up to the first near-tie."""
+    args = O.default_args(task)
+    params = O.init_params(args, seed=100 + seed, bias_scale=bias)
+    data = O.create_dataset(task, B, seed=seed)
+    eng, torch = _engine(args, params)
+    out = eng.rollout(torch.from_numpy(data.astype(np.float32)).cuda(), "greedy", want_logprobs=True, trace=True)
+    torch.cuda.synchronize()
+    ref = O.rollout(params, args, data, "greedy", keep_probs=True)
+    idx = out.idxs.cpu().numpy().astype(np.int64)
+    T = idx.shape[0]
+    div = first_divergence(idx, ref.idxs)
+    masks, logits = out.masks.cpu().numpy(), out.logits.cpu().numpy()
+    for r in range(B):
+        upto = min(div[r] + 1, T)     # the step of the divergence still sees identical state
+        np.testing.assert_array_equal(masks[:upto, r], ref.masks[:upto, r])
+        um = ref.masks[:upto, r] == 0
+        np.testing.assert_allclose(logits[:upto, r][um], ref.logits[:upto, r][um], rtol=LOGIT_RTOL, atol=LOGIT_ATOL)
+        if div[r] < T:   # a legitimate divergence is a near-tie of the two candidates in the reference's own probs
+            t = div[r]
+            p = ref.probs[t, r]
+            assert abs(p[idx[t, r]] - p[ref.idxs[t, r]]) <= 1e-5 * p.max(), (task, r, t)
+    agree = (div == T)
+    np.testing.assert_allclose(out.R.cpu().numpy()[agree], ref.R[agree], rtol=1e-4)
+    np.testing.assert_array_equal(out.final_demand.cpu().numpy()[agree], ref.final_state.demand[agree])
+    np.testing.assert_array_equal(out.final_load.cpu().numpy()[agree], ref.final_state.load[agree])
+    np.testing.assert_array_equal(out.final_mask.cpu().numpy()[agree], ref.final_state.mask[agree])
+    assert agree.mean() >= 0.98, f"{task}: only {agree.mean():.3%} identical greedy tours"
+
+
+def test_stochastic_given_uniforms_vs_oracle():
+    args = O.default_args("vrptw20")
+    params = O.init_params(args, seed=77, bias_scale=0.2)
+    B, T = 256, args["decode_len"]
+    data = O.create_dataset("vrptw20", B, seed=9)
+    rnd = np.random.RandomState(3)
+    u1 = rnd.uniform(size=(T, B)).astype(np.float32)
+    u2 = rnd.uniform(size=(T, B)).astype(np.float32)
+    eng, torch = _engine(args, params)
+    out = eng.rollout(torch.from_numpy(data.astype(np.float32)).cuda(), "stochastic", uniforms=u1, uniforms_retry=u2,
+                      want_logprobs=True, final_state=True)
+    torch.cuda.synchronize()
+    ref = O.rollout(params, args, data, "stochastic", uniforms=u1, uniforms_retry=u2, per_row_retry=True)
+    div = first_divergence(out.idxs.cpu().numpy().astype(np.int64), ref.idxs)
+    agree = div == T
+    assert agree.mean() >= 0.98
+    np.testing.assert_allclose(out.R.cpu().numpy()[agree], ref.R[agree], rtol=1e-4)
+    np.testing.assert_allclose(out.logprobs.cpu().numpy()[:, agree], ref.logprobs[:, agree], rtol=2e-4, atol=2e-5)
+
+
+def test_stochastic_in_kernel_stream_is_valid_and_reproducible():
+    args = O.default_args("vrptw20")
+    params = O.init_params(args, seed=78)
+    data = O.create_dataset("vrptw20", 300, seed=10)
+    eng, torch = _engine(args, params)
+    x = torch.from_numpy(data.astype(np.float32)).cuda()
+    a = eng.rollout(x, "stochastic", seed=1234, final_state=True)
+    b = eng.rollout(x, "stochastic", seed=1234)
+    c = eng.rollout(x, "stochastic", seed=99)
+    torch.cuda.synchronize()
+    assert torch.equal(a.idxs, b.idxs) and torch.equal(a.R, b.R)
+    assert not torch.equal(a.idxs, c.idxs)
+    # every sampled tour is feasible: replay it through the oracle env, chosen nodes are never masked
+    env = O.EnvOracle(args, data)
+    env.reset(1)
+    idx = a.idxs.cpu().numpy().astype(np.int64)
+    for t in range(idx.shape[0]):
+        assert (env.mask[np.arange(300), idx[t]] == 0).all(), f"masked node chosen at step {t}"
+        env.step(idx[t][:, None])
+    np.testing.assert_array_equal(a.final_demand.cpu().numpy(), env.demand)
+
+
+def test_host_entry_point_equals_device_entry_point():
+    args = O.default_args("vrptw20")
+    params = O.init_params(args, seed=5)
+    data = O.create_dataset("vrptw20", 1000, seed=11).astype(np.float32)
+    eng, torch = _engine(args, params)
+    idx_h, cost_h = eng.rollout_host(data, "greedy")
+    out = eng.rollout(torch.from_numpy(data).cuda(), "greedy")
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(idx_h, out.idxs.cpu().numpy())
+    np.testing.assert_array_equal(cost_h, out.R.cpu().numpy())
+
+
+def test_errors_are_reported_not_thrown():
+    pkg = load_pkg()
+    args = O.default_args("vrptw10")
+    with pytest.raises(pkg.VrpB200Error):
+        pkg.Engine(dict(args, hidden_dim=64))
+    eng = pkg.Engine(args)
+    import torch
+    with pytest.raises(pkg.VrpB200Error, match="set_weights"):
+        eng.rollout(torch.zeros(4, 11, 5).cuda())
+    p = O.init_params(args, seed=1)
+    p.pop("Actor/Decoder/Attention/v")
+    with pytest.raises(pkg.VrpB200Error, match="Attention/v"):
+        eng.set_weights(p)
