@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py - the headline benchmark: decoded instances/s of the batched greedy rollout on VRPTW-100.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU
+
+One "step" = one pass of the hot path (RLAgent.build_model('greedy') + evaluate_batch of the reference,
+model/attention_agent.py:84-240, 475-518) over one batch of synthetic instances.  Default workload =
+BASELINE.json configs[4]: UPS VRPTW, 100 customers, greedy, 1 M instances over 8 GPUs = 125 000 instances
+per GPU per step (weak scaling; instances are sharded, no collective on the decode path, one NCCL gather of
+the tour costs per step).  VRPTW-100 is an extrapolated task (the reference's table stops at vrptw50):
+n_nodes 101, capacity 50, decode_len 180.
+
+value   : whole-job instances/s, inputs resident in HBM, CUDA events, max over ranks.
+e2e     : the same through the host entry point of the C ABI (vrpb200_rollout_host): pinned host input,
+          chunked H2D / decode / D2H of costs and tours inside the timed region.
+roofline: the path is neither HBM- nor tensor-bound (2.7 KB of HBM traffic per instance against ~50 MFLOP and
+          ~2 M transcendentals): the binding unit is an SM pipe (FP32 FMA or MUFU).  Pipe peaks are measured
+          live with the library's register-only micro-benchmarks; the HBM line uses MEASURED_PEAKS.json.
+cpu_baseline / --impl reference: TensorFlow is not installable in this image and the reference is TF-1 graph
+          code, so the CPU arm is the numpy restatement of the reference graph (oracle/, checked against
+          fixtures produced by running the reference's own Python files) on all host cores, on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "decoded instances/sec (VRPTW-100 greedy)"
+WORKLOADS = {
+    # name: (task, ups distribution, default instances per GPU per step)
+    "ups_vrptw100_greedy": ("vrptw100", True, 125000),
+    "vrptw100_greedy": ("vrptw100", False, 125000),
+    "vrptw50_greedy": ("vrptw50", False, 131072),
+    "vrptw20_greedy": ("vrptw20", False, 4096),
+    "vrp10_greedy": ("vrp10", False, 128),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ups_vrptw100_greedy", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch-per-gpu", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="instances of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rows-per-cta", type=int, default=0)
+    return ap.parse_args()
+
+
+def make_args(pkg, task):
+    return pkg.task_specific_params.default_args(task)
+
+
+def make_instances(pkg, task, ups, n, seed):
+    a = make_args(pkg, task)
+    return pkg.data.create_dataset(a["task_name"], n, a["n_cust"], seed, ups=ups).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_rate(task, ups, pkg, sample, steps, warmup):
+    """The reference algorithm on the host cores: numpy restatement of the TF-1 graph (oracle/restatement.py)."""
+    from oracle import restatement as O   # the one place bench.py executes oracle/: the CPU arm
+    args = O.default_args(task)
+    params = pkg.data.glorot_params(args, seed=1234)
+    data = make_instances(pkg, task, ups, sample, seed=4242)
+    for _ in range(warmup):
+        O.rollout(params, args, data[: max(8, sample // 8)], "greedy")
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        O.rollout(params, args, data, "greedy")
+        times.append(time.perf_counter() - t0)
+    return sample / float(np.mean(times)), float(np.mean(times))
+
+
+def main():
+    a = parse()
+    pkg = importlib.import_module("mit_rl-vrptw_b200")
+    task, ups, default_b = WORKLOADS[a.workload]
+    Bg = a.batch_per_gpu or default_b
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if a.gpus > 1 and "RANK" not in os.environ:   # convenience: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    args = make_args(pkg, task)
+    T, N, D = args["decode_len"], args["n_nodes"], args["input_dim"]
+    cores = os.cpu_count()
+    config = {"workload": a.workload, "task": task, "n_nodes": N, "decode_len": T, "instances_per_gpu_per_step": Bg,
+              "instances_per_step": Bg * max(world, a.gpus if a.impl == "ours" else 1), "decode": "greedy", "embedding_dim": args["embedding_dim"],
+              "hidden_dim": args["hidden_dim"], "weights": "random-init (Glorot uniform, zero biases), seed 1234",
+              "instances": "UPS Gaussian-mixture generator" if ups else "uniform generator",
+              "task_note": "vrptw100 is extrapolated: the reference's task table stops at vrptw50" if task == "vrptw100" else "",
+              "parallelism": f"instances sharded over {world} GPU(s), no decode-path collective, one NCCL gather of costs per step",
+              "l2": f"input of one step is {Bg * N * D * 4 / 2**20:.0f} MiB per GPU (> 126 MB L2: no flush needed)" if Bg * N * D * 4 > 126e6
+                    else "input smaller than L2: a 256 MiB buffer is written between timed steps"}
+
+    # ---------------------------------------------------------------- reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return 0
+        sample = a.cpu_sample
+        rate, sec = cpu_reference_rate(task, ups, pkg, sample, a.steps, min(a.warmup, 1))
+        cb = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
+              "sample": f"{sample} instances of the workload per step, numpy restatement of the reference graph "
+                        f"(TensorFlow is not installable in this image), BLAS threads = all {cores} host cores"}
+        line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": "instances/s", "n_gpus": a.gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config, "cpu_baseline": cb,
+                "e2e": {"value": rate, "unit": "instances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0, "us_per_decode_step": sec * 1e6 / T}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------- our arm (CUDA)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device; this repo has no CPU path for the rollout"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = pkg.Engine(args, device=local_rank, rows_per_cta=a.rows_per_cta)
+    eng.set_weights(pkg.data.glorot_params(args, seed=1234))
+    x_host = torch.from_numpy(make_instances(pkg, task, ups, Bg, seed=1000 + rank)).pin_memory()
+    x_dev = x_host.cuda(non_blocking=False)
+    gathered = [torch.empty(Bg, device="cuda") for _ in range(world)] if (world > 1 and rank == 0) else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if Bg * N * D * 4 <= 126e6 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        out = eng.rollout(x_dev, "greedy")
+        if world > 1:   # the only collective of the path: tour costs to rank 0
+            dist.gather(out.R, gathered, dst=0)
+        return out
+
+    for _ in range(a.warmup):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    for k in range(a.steps):
+        if flush is not None:
+            flush.fill_(k)
+        evs[k][0].record()
+        out = step_device()
+        evs[k][1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    tt = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    mean_cost = float(out.R.mean().item())
+
+    # ---- end to end through the host entry point
+    idx_host = torch.empty((T, Bg), dtype=torch.int32).pin_memory()
+    cost_host = torch.empty((Bg,), dtype=torch.float32).pin_memory()
+    xh, ih, ch = x_host.numpy(), idx_host.numpy(), cost_host.numpy()
+    for _ in range(max(1, min(a.warmup, 2))):
+        eng.rollout_host(xh, "greedy", idx_out=ih, cost_out=ch)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        eng.rollout_host(xh, "greedy", idx_out=ih, cost_out=ch)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_launches = eng.last_launch()["kernels"]
+    t2 = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_s = float(t2.item())
+    assert np.array_equal(ch, out.R.cpu().numpy()), "host entry point and device entry point disagree"
+
+    # ---- work accounting for the roofline (one extra, untimed, counted pass; the rollout is deterministic)
+    st = eng.rollout(x_dev, "greedy", want_stats=True, want_steps=True)
+    torch.cuda.synchronize()
+    node_evals, live_rowsteps, gemm_rowsteps, blocks = [int(v) for v in st.stats.cpu().tolist()]
+    launch = eng.last_launch()
+    result = 0
+    if rank == 0:
+        H = args["hidden_dim"]
+        ms_step = ms_total / a.steps
+        sec_step = ms_step * 1e-3
+        mufu_ops = 2.0 * H * node_evals + 10.0 * H * gemm_rowsteps + 3.0 * node_evals   # tanh grid, LSTM gates, softmax exp
+        fp32_ops = 8.0 * H * node_evals + (136 * 512 + 128 * 128) * gemm_rowsteps       # FP32-pipe lane ops (FMA counted once)
+        hbm_bytes = Bg * (N * D * 4 + T * 4 + 4)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_path):
+            with open(peaks_path) as f:
+                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+        mufu_peak = eng.pipe_peak("mufu")
+        fma_peak = eng.pipe_peak("fma")
+        pipes = {
+            "mufu": {"achieved": mufu_ops / sec_step / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s"},
+            "fp32": {"achieved": fp32_ops / sec_step / 1e9, "peak": fma_peak / 1e9, "unit": "Gop/s (FMA = 1 op)"},
+            "hbm": {"achieved": hbm_bytes / sec_step / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src},
+            "tensor": {"achieved": 0.0, "peak": None, "unit": "TFLOP/s", "note": "phase A/B GEMMs run on the FP32 pipe in this round"},
+        }
+        for p in pipes.values():
+            p["frac"] = (p["achieved"] / p["peak"]) if p["peak"] else 0.0
+        bound = max(("mufu", "fp32", "hbm"), key=lambda k: pipes[k]["frac"])
+        roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
+                    "frac": pipes[bound]["frac"], "traffic": None,
+                    "peak_source": "pipe peaks measured live by vrpb200_pipe_peak (register-only micro-benchmark on all SMs); "
+                                   "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks and neither binds this path",
+                    "work_per_launch": {"node_evaluations": node_evals, "live_row_steps": live_rowsteps, "gemm_row_steps": gemm_rowsteps,
+                                        "blocks": blocks, "mean_steps_per_block": float(st.steps.float().mean().item()),
+                                        "mufu_ops": mufu_ops, "fp32_lane_ops": fp32_ops, "hbm_bytes": hbm_bytes},
+                    "pipes": pipes,
+                    "kernel": f"rollout_kernel<{launch['rows_per_cta']},TW> grid {launch['grid']} x {launch['block']} thr, {launch['smem']} B smem, "
+                              f"1 launch per step, {ms_step:.3f} ms per launch (CUDA events)"}
+        # profiles/ holds the ncu capture of the same kernel; dram bytes per launch from it if present
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path):
+            with open(tr_path) as f:
+                roofline["traffic"] = json.load(f).get(a.workload)
+        value = Bg * world * a.steps / (ms_total * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config, "us_per_decode_step": ms_step * 1e3 / T,
+                "ns_per_row_step": ms_step * 1e6 / max(1, live_rowsteps), "mean_tour_length": mean_cost,
+                "roofline": roofline, "clocks": clocks,
+                "e2e": {"value": Bg * world * a.steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": Bg * N * D * 4,
+                        "d2h_bytes_per_step": Bg * 4 + T * Bg * 4, "api": "vrpb200_rollout_host (pinned host buffers, chunked copy/decode overlap)",
+                        "kernel_launches_per_step": e2e_launches},
+                "gpu_launches": a.steps * 1}
+        if not a.no_cpu_baseline and world == 1:
+            rate, sec = cpu_reference_rate(task, ups, pkg, a.cpu_sample, 1, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",
+                                    "sample": f"{a.cpu_sample} instances of the workload, one pass ({sec:.1f} s), numpy restatement of the "
+                                              f"reference graph on all {cores} host cores (TensorFlow not installable here)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+if __name__ == "__main__":
+    sys.exit(main())

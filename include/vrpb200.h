@@ -76,6 +76,7 @@ typedef struct vrpb200_trace {
     float* d_final_time;    /* [R]  (VRPTW only) */
     float* d_final_mask;    /* [R, N] */
     int32_t* d_steps;       /* [gridDim] decode steps each instance block actually executed */
+    uint64_t* d_stats;      /* [4] += node evaluations, live row-steps, block-steps x rows-per-CTA, blocks (work accounting) */
 } vrpb200_trace;
 
 /* ---- life cycle ------------------------------------------------------------------------- */
@@ -106,11 +107,12 @@ int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode
                     int32_t* d_idx, float* d_cost, float* d_logprob, int32_t* d_beam_parent,
                     const vrpb200_trace* trace, void* stream);
 
-/* The same call with HOST buffers (what evaluate_batch's sess.run(feed_dict) is to a caller):
- * pinned staging, H2D of h_input, the rollout, D2H of h_cost (and h_idx when not NULL).
- * Synchronous; returns after the results are in host memory. */
+/* The same call with HOST buffers (what evaluate_batch's sess.run(feed_dict) is to a caller): the batch is
+ * cut into chunks that are copied H2D, decoded and copied back D2H on a few streams so that transfers
+ * overlap decoding.  Pass page-locked (pinned) buffers for full PCIe speed; pageable memory works, slower.
+ * h_stats (may be NULL): uint64[4] work counters as vrpb200_trace.d_stats.  Synchronous. */
 int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int mode, int beam_width,
-                         uint64_t seed, int32_t* h_idx, float* h_cost);
+                         uint64_t seed, int32_t* h_idx, float* h_cost, uint64_t* h_stats);
 
 /* ---- Env (VRPTW/vrptw_utils.py:161-358, VRP/vrp_utils.py:133-255) ------------------------- *
  * State arrays are the Env attributes of the same name, fp32, R rows:
@@ -150,6 +152,11 @@ int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp
  * (first two columns x, y) -> d_cost [R]. */
 int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t R, int A, float* d_cost,
                    void* stream);
+
+/* Measured throughput of one SM pipe on the handle's device, for the roofline denominators that
+ * MEASURED_PEAKS.json does not hold: kind 0 = MUFU (ex2/rcp, ops/s), 1 = FP32 FMA (FMA/s, 2 flop each).
+ * Runs a register-only micro-benchmark on every SM for ~`iters` x 4096 ops per thread.  Synchronous. */
+int vrpb200_pipe_peak(vrpb200_handle* h, int kind, int iters, double* ops_per_second);
 
 /* Launch statistics of the last rollout on this handle (for bench.py): grid size, block size,
  * dynamic shared memory bytes, rows per CTA, number of kernels launched. */

@@ -32,13 +32,13 @@ class Config(C.Structure):
 class Trace(C.Structure):
     """struct vrpb200_trace (device pointers)"""
     _fields_ = [(n, C.c_void_p) for n in (
-        "d_logits", "d_probs", "d_masks", "d_final_demand", "d_final_load", "d_final_time", "d_final_mask", "d_steps")]
+        "d_logits", "d_probs", "d_masks", "d_final_demand", "d_final_load", "d_final_time", "d_final_mask", "d_steps", "d_stats")]
 
 
 EXPORTS = (
     "vrpb200_create", "vrpb200_destroy", "vrpb200_last_error", "vrpb200_version", "vrpb200_set_weights",
     "vrpb200_rollout", "vrpb200_rollout_host", "vrpb200_env_reset", "vrpb200_env_step", "vrpb200_embed",
-    "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_last_launch",
+    "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_last_launch", "vrpb200_pipe_peak",
 )
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -81,7 +81,7 @@ def load() -> C.CDLL:
     lib.vrpb200_version.argtypes = []
     lib.vrpb200_set_weights.argtypes = [vp, i32, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(i64)]
     lib.vrpb200_rollout.argtypes = [vp, f32p, i64, i32, i32, f32p, f32p, u64, vp, f32p, f32p, vp, C.POINTER(Trace), vp]
-    lib.vrpb200_rollout_host.argtypes = [vp, f32p, i64, i32, i32, u64, vp, f32p]
+    lib.vrpb200_rollout_host.argtypes = [vp, f32p, i64, i32, i32, u64, vp, f32p, vp]
     lib.vrpb200_env_reset.argtypes = [vp, f32p, i64, i32, f32p, f32p, f32p, f32p, f32p, vp]
     lib.vrpb200_env_step.argtypes = [vp, f32p, i64, i32, vp, vp, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
     lib.vrpb200_embed.argtypes = [vp, f32p, i64, f32p, vp]
@@ -89,6 +89,7 @@ def load() -> C.CDLL:
     lib.vrpb200_decode_step.argtypes = [vp, i64, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, vp]
     lib.vrpb200_reward.argtypes = [vp, f32p, i64, i64, i32, f32p, vp]
     lib.vrpb200_last_launch.argtypes = [vp, C.POINTER(C.c_int32)]
+    lib.vrpb200_pipe_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]
     for name in EXPORTS:
         if name != "vrpb200_last_error":
             getattr(lib, name).restype = C.c_int

@@ -65,8 +65,10 @@ struct RolloutArgs {
     float* fin_time;
     float* fin_mask;
     int32_t* steps_out;      // [grid] or null
+    unsigned long long* stats; // [4] or null: node evaluations, live row-steps, block-steps*RB, blocks
     unsigned long long seed;
     long long B;             // instances
+    long long row_base;      // global index of instance 0 of this call (chunked host entry point), RNG only
     int W;                   // beams per instance (1 unless beam search)
     int IB;                  // instances per CTA
     int N, n_cust, D, T;
@@ -268,6 +270,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_kernel(const RolloutArgs a)
     for (int r = 0; r < 8; ++r) cst[r][0] = cst[r][1] = 0.0f;
 
     uint32_t slabcnt = 0;
+    unsigned n_eval = 0, n_rowsteps = 0;   // work counters of this warp (roofline accounting)
     int t = 0;
     for (; t < T; ++t) {
         // ================= phase A: gates = [h, feat(prev node)] . Wg ===================================
@@ -436,6 +439,8 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_kernel(const RolloutArgs a)
                 nact += __popc(actbits[j]);
             }
             const int npad = align_up(nact, 8);
+            n_eval += nact;
+            ++n_rowsteps;
             if (lane < npad - nact) list[nact + lane] = 0;   // padding entries: node 0, result ignored
             __syncwarp();
 
@@ -552,7 +557,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_kernel(const RolloutArgs a)
                     const long long o = (long long)t * R + row;
                     for (int draw = 0; draw < 2 && sel < 0; ++draw) {
                         const float* ub = draw ? a.uniforms_retry : a.uniforms;
-                        const float u = ub ? ub[o] : counter_uniform(a.seed, t, row, draw);
+                        const float u = ub ? ub[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
                         float cum = 0.0f;   // tf.cumsum: sequential fp32; skipped nodes have prob exactly 0
                         for (int k = 0; k < nact; ++k) {
                             const int n = list[k];
@@ -646,6 +651,14 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_kernel(const RolloutArgs a)
         }
     }
     if (tid == 0 && a.steps_out) a.steps_out[blockIdx.x] = t_end;
+    if (a.stats && lane == 0) {
+        atomicAdd(a.stats + 0, (unsigned long long)n_eval);
+        atomicAdd(a.stats + 1, (unsigned long long)n_rowsteps);
+        if (tid == 0) {
+            atomicAdd(a.stats + 2, (unsigned long long)t_end * RB);
+            atomicAdd(a.stats + 3, 1ull);
+        }
+    }
 }
 
 }  // namespace vrpb200

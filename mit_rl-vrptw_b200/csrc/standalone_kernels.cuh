@@ -280,4 +280,34 @@ __global__ void reward_kernel(const float* __restrict__ actions, long long T, lo
     cost[r] = s;
 }
 
+// ---- pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not hold -----------------
+// kind 0: MUFU (ex2 + rcp alternating, 8 independent chains per thread); kind 1: FP32 FMA (16 chains).
+__global__ void __launch_bounds__(512) pipe_peak_kernel(int kind, int iters, float* sink) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = 0.5f + 0.001f * (threadIdx.x + i);
+    if (kind == 0) {
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = rcp_approx(ex2_approx(x[i]));   // 2 MUFU per chain link
+            }
+        }
+    } else {
+        const float a = 1.0001f, b = 0.0001f;
+        for (int it = 0; it < iters; ++it) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) sink[0] = s;   // keep the chains alive
+}
+
 }  // namespace vrpb200

@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -36,14 +37,14 @@ struct vrpb200_handle {
     AttWeights att[8];
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
-    // staging of the *_host call
-    float* pin_in = nullptr;  size_t pin_in_bytes = 0;
-    int32_t* pin_idx = nullptr; size_t pin_idx_bytes = 0;
-    float* pin_cost = nullptr; size_t pin_cost_bytes = 0;
-    float* dev_in = nullptr;  size_t dev_in_bytes = 0;
-    int32_t* dev_idx = nullptr; size_t dev_idx_bytes = 0;
-    float* dev_cost = nullptr; size_t dev_cost_bytes = 0;
-    cudaStream_t own_stream = nullptr;
+    // staging of the *_host call: kChunks in-flight chunks, one stream each
+    static constexpr int kChunks = 3;
+    float* dev_in[kChunks] = {nullptr, nullptr, nullptr};
+    int32_t* dev_idx[kChunks] = {nullptr, nullptr, nullptr};
+    float* dev_cost[kChunks] = {nullptr, nullptr, nullptr};
+    size_t dev_in_bytes[kChunks] = {0, 0, 0}, dev_idx_bytes[kChunks] = {0, 0, 0}, dev_cost_bytes[kChunks] = {0, 0, 0};
+    cudaStream_t streams[kChunks] = {nullptr, nullptr, nullptr};
+    unsigned long long* dev_stats = nullptr;
     int32_t last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int max_smem_optin = 0;
     int num_sms = 0;
@@ -78,11 +79,10 @@ std::string att_prefix(const vrpb200_config& c, int a) {   // a in [0, n_glimpse
 }
 
 template <class T>
-int ensure(vrpb200_handle* h, T** p, size_t* have, size_t need, bool pinned) {
+int ensure(vrpb200_handle* h, T** p, size_t* have, size_t need) {
     if (*have >= need) return 0;
-    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *have = 0; }
-    if (pinned) CUDA_TRY(h, cudaMallocHost((void**)p, need));
-    else CUDA_TRY(h, cudaMalloc((void**)p, need));
+    if (*p) { cudaFree(*p); *p = nullptr; *have = 0; }
+    CUDA_TRY(h, cudaMalloc((void**)p, need));
     *have = need;
     return 0;
 }
@@ -134,13 +134,13 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (!h) return VRPB200_OK;
     cudaSetDevice(h->device);
     if (h->d_blob) cudaFree(h->d_blob);
-    if (h->pin_in) cudaFreeHost(h->pin_in);
-    if (h->pin_idx) cudaFreeHost(h->pin_idx);
-    if (h->pin_cost) cudaFreeHost(h->pin_cost);
-    if (h->dev_in) cudaFree(h->dev_in);
-    if (h->dev_idx) cudaFree(h->dev_idx);
-    if (h->dev_cost) cudaFree(h->dev_cost);
-    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
+        if (h->dev_in[i]) cudaFree(h->dev_in[i]);
+        if (h->dev_idx[i]) cudaFree(h->dev_idx[i]);
+        if (h->dev_cost[i]) cudaFree(h->dev_cost[i]);
+        if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
+    }
+    if (h->dev_stats) cudaFree(h->dev_stats);
     delete h;
     return VRPB200_OK;
 }
@@ -355,10 +355,10 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
 
 extern "C" {
 
-int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode, int beam_width,
-                    const float* d_uniforms, const float* d_uniforms_retry, uint64_t seed, int32_t* d_idx,
-                    float* d_cost, float* d_logprob, int32_t* d_beam_parent, const vrpb200_trace* trace,
-                    void* stream) {
+static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int mode, int beam_width,
+                        const float* d_uniforms, const float* d_uniforms_retry, uint64_t seed, int32_t* d_idx,
+                        float* d_cost, float* d_logprob, int32_t* d_beam_parent, const vrpb200_trace* trace,
+                        void* stream, long long row_base) {
     if (!h) return VRPB200_E_ARG;
     if (!h->have_weights) return fail(h, VRPB200_E_STATE, "rollout before set_weights");
     if (!d_input || !d_cost || !d_idx) return fail(h, VRPB200_E_ARG, "d_input, d_idx and d_cost are required");
@@ -380,41 +380,94 @@ int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode
         a.tr_logits = trace->d_logits; a.tr_probs = trace->d_probs; a.tr_masks = trace->d_masks;
         a.fin_demand = trace->d_final_demand; a.fin_load = trace->d_final_load; a.fin_time = trace->d_final_time;
         a.fin_mask = trace->d_final_mask; a.steps_out = trace->d_steps;
+        a.stats = (unsigned long long*)trace->d_stats;
     }
     a.full = (a.tr_logits || a.tr_probs || a.tr_masks) ? 1 : 0;
-    a.seed = seed; a.B = B; a.W = 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
+    a.seed = seed; a.B = B; a.row_base = row_base; a.W = 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
     a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
     return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
+int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode, int beam_width,
+                    const float* d_uniforms, const float* d_uniforms_retry, uint64_t seed, int32_t* d_idx,
+                    float* d_cost, float* d_logprob, int32_t* d_beam_parent, const vrpb200_trace* trace,
+                    void* stream) {
+    return rollout_impl(h, d_input, B, mode, beam_width, d_uniforms, d_uniforms_retry, seed, d_idx, d_cost, d_logprob,
+                        d_beam_parent, trace, stream, 0);
+}
+
 int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int mode, int beam_width,
-                         uint64_t seed, int32_t* h_idx, float* h_cost) {
+                         uint64_t seed, int32_t* h_idx, float* h_cost, uint64_t* h_stats) {
     if (!h) return VRPB200_E_ARG;
     if (!h_input || !h_cost) return fail(h, VRPB200_E_ARG, "h_input and h_cost are required");
     if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
+    if (mode == VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "rollout_host: beam search goes through vrpb200_rollout");
     const vrpb200_config& c = h->cfg;
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (!h->own_stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    const int W = 1;
-    const size_t in_b = (size_t)B * c.n_nodes * c.input_dim * 4, idx_b = (size_t)c.decode_len * B * W * 4, cost_b = (size_t)B * W * 4;
+    constexpr int NC = vrpb200_handle::kChunks;
+    for (int i = 0; i < NC; ++i)
+        if (!h->streams[i]) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+    if (!h->dev_stats) CUDA_TRY(h, cudaMalloc((void**)&h->dev_stats, 4 * sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemsetAsync(h->dev_stats, 0, 4 * sizeof(unsigned long long), h->streams[0]));
+    CUDA_TRY(h, cudaStreamSynchronize(h->streams[0]));
+    // chunk = 4 waves of 64-row blocks: large enough to amortise launch + tail, small enough that the first
+    // H2D and the last D2H (the only un-overlapped transfers) are short
+    const int64_t chunk = std::min<int64_t>(B, (int64_t)h->num_sms * 64 * 4);
+    const int T = c.decode_len;
+    const size_t inst_b = (size_t)c.n_nodes * c.input_dim * 4;
     int rc;
-    if ((rc = ensure(h, &h->pin_in, &h->pin_in_bytes, in_b, true))) return rc;
-    if ((rc = ensure(h, &h->pin_cost, &h->pin_cost_bytes, cost_b, true))) return rc;
-    if ((rc = ensure(h, &h->dev_in, &h->dev_in_bytes, in_b, false))) return rc;
-    if ((rc = ensure(h, &h->dev_idx, &h->dev_idx_bytes, idx_b, false))) return rc;
-    if ((rc = ensure(h, &h->dev_cost, &h->dev_cost_bytes, cost_b, false))) return rc;
-    if (h_idx && (rc = ensure(h, &h->pin_idx, &h->pin_idx_bytes, idx_b, true))) return rc;
-    memcpy(h->pin_in, h_input, in_b);
-    CUDA_TRY(h, cudaMemcpyAsync(h->dev_in, h->pin_in, in_b, cudaMemcpyHostToDevice, h->own_stream));
-    rc = vrpb200_rollout(h, h->dev_in, B, mode, beam_width, nullptr, nullptr, seed, h->dev_idx, h->dev_cost, nullptr,
-                         nullptr, nullptr, h->own_stream);
-    if (rc) return rc;
-    CUDA_TRY(h, cudaMemcpyAsync(h->pin_cost, h->dev_cost, cost_b, cudaMemcpyDeviceToHost, h->own_stream));
-    if (h_idx) CUDA_TRY(h, cudaMemcpyAsync(h->pin_idx, h->dev_idx, idx_b, cudaMemcpyDeviceToHost, h->own_stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->own_stream));
-    memcpy(h_cost, h->pin_cost, cost_b);
-    if (h_idx) memcpy(h_idx, h->pin_idx, idx_b);
+    vrpb200_trace tr;
+    memset(&tr, 0, sizeof tr);
+    tr.d_stats = (uint64_t*)h->dev_stats;
+    int launches = 0;
+    for (int64_t off = 0, k = 0; off < B; off += chunk, ++k) {
+        const int s = (int)(k % NC);
+        const int64_t nb = std::min<int64_t>(chunk, B - off);
+        if ((rc = ensure(h, &h->dev_in[s], &h->dev_in_bytes[s], (size_t)chunk * inst_b))) return rc;
+        if ((rc = ensure(h, &h->dev_idx[s], &h->dev_idx_bytes[s], (size_t)chunk * T * 4))) return rc;
+        if ((rc = ensure(h, &h->dev_cost[s], &h->dev_cost_bytes[s], (size_t)chunk * 4))) return rc;
+        cudaStream_t st = h->streams[s];   // stream order protects the staging buffers of slot s
+        CUDA_TRY(h, cudaMemcpyAsync(h->dev_in[s], (const char*)h_input + (size_t)off * inst_b, (size_t)nb * inst_b,
+                                    cudaMemcpyHostToDevice, st));
+        rc = rollout_impl(h, h->dev_in[s], nb, mode, beam_width, nullptr, nullptr, seed, h->dev_idx[s], h->dev_cost[s],
+                          nullptr, nullptr, &tr, st, off);
+        if (rc) return rc;
+        ++launches;
+        CUDA_TRY(h, cudaMemcpyAsync(h_cost + off, h->dev_cost[s], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (h_idx)   // [T, nb] device -> columns [off, off+nb) of the host's [T, B]
+            CUDA_TRY(h, cudaMemcpy2DAsync(h_idx + off, (size_t)B * 4, h->dev_idx[s], (size_t)nb * 4, (size_t)nb * 4, T,
+                                          cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < NC; ++i) CUDA_TRY(h, cudaStreamSynchronize(h->streams[i]));
+    if (h_stats) CUDA_TRY(h, cudaMemcpy(h_stats, h->dev_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    h->last_launch[4] = launches;
+    return VRPB200_OK;
+}
+
+int vrpb200_pipe_peak(vrpb200_handle* h, int kind, int iters, double* ops_per_second) {
+    if (!h || !ops_per_second || (kind != 0 && kind != 1) || iters < 1) return fail(h, VRPB200_E_ARG, "pipe_peak: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    float* sink = nullptr;
+    CUDA_TRY(h, cudaMalloc((void**)&sink, 4));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(h, cudaEventCreate(&e0));
+    CUDA_TRY(h, cudaEventCreate(&e1));
+    const int grid = h->num_sms * 4, block = 512;
+    pipe_peak_kernel<<<grid, block>>>(kind, 8, sink);   // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_TRY(h, cudaEventRecord(e0));
+        pipe_peak_kernel<<<grid, block>>>(kind, iters, sink);
+        CUDA_TRY(h, cudaEventRecord(e1));
+        CUDA_TRY(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, e0, e1));
+        best = std::min(best, ms);
+    }
+    const double per_thread = (double)iters * 32.0 * (kind == 0 ? 16.0 : 16.0);
+    *ops_per_second = per_thread * grid * block / (best * 1e-3);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
     return VRPB200_OK;
 }
 

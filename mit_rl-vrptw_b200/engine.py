@@ -44,6 +44,7 @@ class RolloutOutput:
     final_time: Optional[torch.Tensor] = None
     final_mask: Optional[torch.Tensor] = None
     steps: Optional[torch.Tensor] = None     # [grid] int32 decode steps executed per instance block
+    stats: Optional[torch.Tensor] = None     # [4] int64 work counters: node evals, live row-steps, block-steps*rows, blocks
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -104,7 +105,7 @@ class Engine:
     # -- the hot path ----------------------------------------------------------------------------
     def rollout(self, input_data, decode_type: str = "greedy", beam_width: int = 1, uniforms=None, uniforms_retry=None,
                 seed: int = 0, want_logprobs: bool = False, trace: bool = False, final_state: bool = False,
-                want_steps: bool = False) -> RolloutOutput:
+                want_steps: bool = False, want_stats: bool = False) -> RolloutOutput:
         x = self._f32(input_data, "input_data")
         if x.dim() != 3 or x.shape[1] != self.N or x.shape[2] != self.D:
             raise VrpB200Error(f"input_data must be [B,{self.N},{self.D}], got {tuple(x.shape)}")
@@ -134,6 +135,9 @@ class Engine:
         if want_steps:
             out.steps = torch.zeros(((B + 15) // 16,), dtype=torch.int32, device=dev)   # upper bound on the grid
             tr.d_steps = out.steps.data_ptr()
+        if want_stats:
+            out.stats = torch.zeros((4,), dtype=torch.int64, device=dev)
+            tr.d_stats = out.stats.data_ptr()
         u1 = u2 = None
         if uniforms is not None:
             u1, u2 = self._f32(uniforms, "uniforms"), self._f32(uniforms_retry, "uniforms_retry")
@@ -147,18 +151,29 @@ class Engine:
         return out
 
     def rollout_host(self, input_np: np.ndarray, decode_type: str = "greedy", beam_width: int = 1, seed: int = 0,
-                     want_idx: bool = True):
-        """Host buffers in, host buffers out (H2D + rollout + D2H inside the call)."""
-        x = np.ascontiguousarray(input_np, dtype=np.float32)
+                     idx_out: Optional[np.ndarray] = None, cost_out: Optional[np.ndarray] = None, want_idx: bool = True,
+                     want_stats: bool = False):
+        """Host buffers in, host buffers out (chunked H2D + rollout + D2H inside the call).
+        Pass pinned arrays (e.g. views of torch pinned tensors) for full PCIe speed."""
+        x = input_np if (isinstance(input_np, np.ndarray) and input_np.dtype == np.float32 and input_np.flags.c_contiguous) \
+            else np.ascontiguousarray(input_np, dtype=np.float32)
         B = x.shape[0]
         mode = DECODE_MODES[decode_type]
         W = beam_width if mode == _lib.BEAM else 1
-        cost = np.empty((B * W,), np.float32)
-        idx = np.empty((self.T, B * W), np.int32) if want_idx else None
+        cost = cost_out if cost_out is not None else np.empty((B * W,), np.float32)
+        idx = idx_out if idx_out is not None else (np.empty((self.T, B * W), np.int32) if want_idx else None)
+        stats = np.zeros((4,), np.uint64) if want_stats else None
         self._check(self.lib.vrpb200_rollout_host(
             self.handle, C.c_void_p(x.ctypes.data), B, mode, W, C.c_uint64(seed),
-            C.c_void_p(idx.ctypes.data) if want_idx else None, C.c_void_p(cost.ctypes.data)), "rollout_host")
-        return idx, cost
+            C.c_void_p(idx.ctypes.data) if idx is not None else None, C.c_void_p(cost.ctypes.data),
+            C.c_void_p(stats.ctypes.data) if want_stats else None), "rollout_host")
+        return (idx, cost, stats) if want_stats else (idx, cost)
+
+    def pipe_peak(self, kind: str, iters: int = 256) -> float:
+        """Measured throughput (ops/s) of the MUFU ('mufu') or FP32 FMA ('fma') pipe on this device."""
+        out = C.c_double()
+        self._check(self.lib.vrpb200_pipe_peak(self.handle, {"mufu": 0, "fma": 1}[kind], iters, C.byref(out)), "pipe_peak")
+        return out.value
 
     def last_launch(self) -> dict:
         arr = (C.c_int32 * 8)()
