@@ -1,0 +1,675 @@
+"""Host-side mirror of the reference's Python protocol for the rollout path (drop-in surface).
+
+Same class names, constructor arguments, attributes and return values as the reference, so that the
+code in main.py:17-53 / model/attention_agent.py that wires them together keeps working:
+
+    reference                                             here
+    ---------------------------------------------------   -------------------------------------------
+    shared/embeddings.py        LinearEmbedding           LinearEmbedding
+    VRP/vrp_attention.py        AttentionVRPActor         AttentionVRPActor
+    VRPTW/vrptw_attention.py    AttentionVRPTWActor       AttentionVRPTWActor
+    UPS/*_attention.py          Attention*_UPS_Actor      AttentionVRP_UPS_Actor, AttentionVRPTW_UPS_Actor
+    shared/decode_step.py       RNNDecodeStep             RNNDecodeStep
+    VRP|VRPTW|UPS/*_utils.py    Env, State, reward_func,  VRPEnv / VRPTWEnv (``Env`` via the loader), State*,
+                                DataGenerator             reward_func, DataGenerator
+    model/attention_agent.py    RLAgent                   RLAgent (build_model, evaluate_batch, inference, ...)
+    main.py                     load_task_specific_components  load_task_specific_components
+
+TensorFlow placeholders + feed_dict become eager CUDA tensors: assign ``env.input_data = tensor``.
+TF variables become entries of a ``VariableStore`` keyed by the TF-1 variable names (what
+tf.train.Saver writes), so a converted checkpoint loads by name.  All arithmetic is done by
+libvrpb200.so through ``Engine``; torch provides device memory, indexing and the beam bookkeeping of the
+step-wise path.  Nothing here computes the model on the CPU.
+"""
+from __future__ import annotations
+
+import collections
+import os
+import time
+import warnings
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import data as _data
+from .task_specific_params import task_lst  # noqa: F401  (re-export, reference: task_specific_params.py)
+
+# --------------------------------------------------------------------------------------------------
+# variables
+# --------------------------------------------------------------------------------------------------
+
+
+class VariableStore:
+    """name -> float32 array; the stand-in for TF's global variable collection."""
+
+    def __init__(self, seed: int = 1234):
+        self.vars: Dict[str, np.ndarray] = collections.OrderedDict()
+        self.rnd = np.random.RandomState(seed)
+        self.version = 0
+
+    def get(self, name, shape, init="glorot", fans=None):
+        """tf.get_variable / tf.layers semantics: create on first request (Glorot-uniform kernels, zero biases)."""
+        if name in self.vars:
+            if tuple(self.vars[name].shape) != tuple(shape):
+                raise ValueError(f"variable {name}: shape {self.vars[name].shape} != requested {tuple(shape)}")
+            return self.vars[name]
+        if init == "zeros":
+            v = np.zeros(shape, np.float32)
+        else:
+            fi, fo = fans
+            lim = np.sqrt(6.0 / (fi + fo))
+            v = self.rnd.uniform(-lim, lim, size=shape).astype(np.float32)
+        self.vars[name] = v
+        self.version += 1
+        return v
+
+    def assign(self, params: Dict[str, np.ndarray], strict: bool = True):
+        """saver.restore: overwrite by name; unknown names are an error when strict."""
+        for k, v in params.items():
+            v = np.asarray(v, np.float32)
+            if k in self.vars and self.vars[k].shape != v.shape:
+                raise ValueError(f"variable {k}: checkpoint shape {v.shape} != {self.vars[k].shape}")
+            if k not in self.vars and strict:
+                raise KeyError(f"checkpoint variable {k} is not part of the model")
+            self.vars[k] = v.copy()
+        self.version += 1
+
+    def save(self, path):
+        np.savez(path, **self.vars)
+
+    def load(self, path, strict=True):
+        with np.load(path) as z:
+            self.assign({k: z[k] for k in z.files}, strict=strict)
+
+
+_default_store = VariableStore()
+
+
+def default_store() -> VariableStore:
+    return _default_store
+
+
+def reset_default_store(seed: int = 1234) -> VariableStore:
+    """tf.reset_default_graph() for the variable collection."""
+    global _default_store
+    _default_store = VariableStore(seed)
+    return _default_store
+
+
+# --------------------------------------------------------------------------------------------------
+# engines: one C-ABI handle per (configuration, weights version)
+# --------------------------------------------------------------------------------------------------
+_engine_cache: Dict[tuple, object] = {}
+
+
+def _get_engine(args: dict, params: Dict[str, np.ndarray], version_key, device: int = 0):
+    from .engine import Engine
+    key = (tuple(sorted((k, str(v)) for k, v in args.items() if k in (
+        "task_name", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
+        "use_tanh", "mask_glimpses", "mask_pointer", "capacity", "tanh_exploration", "forget_bias"))), version_key, device)
+    eng = _engine_cache.get(key)
+    if eng is None:
+        if len(_engine_cache) > 8:
+            _engine_cache.clear()
+        eng = Engine(args, device=device)
+        eng.set_weights(params)
+        _engine_cache[key] = eng
+    return eng
+
+
+def _dummy_model_params(args: dict) -> Dict[str, np.ndarray]:
+    """Zero tensors for every variable the C ABI insists on; callers overwrite the ones they own."""
+    p = _data.glorot_params(args, seed=0)
+    return {k: np.zeros_like(v) for k, v in p.items()}
+
+
+# --------------------------------------------------------------------------------------------------
+# model pieces
+# --------------------------------------------------------------------------------------------------
+class Embedding(object):
+    """shared/embeddings.py:9-22"""
+
+    def __init__(self, emb_type, embedding_dim):
+        self.emb_type = emb_type
+        self.embedding_dim = embedding_dim
+        self.total_time = 0
+
+    def __call__(self, input_pnt):
+        pass
+
+
+class LinearEmbedding(Embedding):
+    """shared/embeddings.py:25-46: Conv1D(embedding_dim, 1) under scope ``_scope + 'Embedding/conv1d'``."""
+
+    def __init__(self, embedding_dim, _scope='', store: Optional[VariableStore] = None):
+        super(LinearEmbedding, self).__init__('linear', embedding_dim)
+        self.store = store or default_store()
+        self.scope = _scope + 'Embedding/conv1d'
+        self._built = None
+
+    def _build(self, d1):
+        if self._built != d1:
+            self.store.get(self.scope + '/kernel', [1, d1, self.embedding_dim], fans=(d1, self.embedding_dim))
+            self.store.get(self.scope + '/bias', [self.embedding_dim], init="zeros")
+            self._built = d1
+
+    def __call__(self, input_pnt):
+        import torch
+        t0 = time.time()
+        x = input_pnt if isinstance(input_pnt, torch.Tensor) else torch.as_tensor(np.asarray(input_pnt, np.float32))
+        d1 = x.shape[-1]
+        self._build(d1)
+        task_name = "vrptw" if d1 == 4 else "vrp"
+        args = dict(task_name=task_name, n_nodes=x.shape[-2], n_cust=x.shape[-2] - 1, input_dim=d1 + 1,
+                    embedding_dim=self.embedding_dim, hidden_dim=128, decode_len=1, capacity=1.0)
+        params = _dummy_model_params(args)
+        params['Actor/Embedding/conv1d/kernel'] = self.store.vars[self.scope + '/kernel']
+        params['Actor/Embedding/conv1d/bias'] = self.store.vars[self.scope + '/bias']
+        eng = _get_engine(args, params, ("emb", id(self.store), self.store.version, self.scope))
+        out = eng.embed(x)
+        self.total_time += time.time() - t0
+        return out
+
+
+class _AttentionActorBase(object):
+    """Attention*Actor of VRP/vrp_attention.py:3-76 and VRPTW/vrptw_attention.py:4-84 (and the UPS twins)."""
+    TW = False
+
+    def __init__(self, dim, use_tanh=False, C=10, _name='Attention', _scope='', store: Optional[VariableStore] = None):
+        self.use_tanh = use_tanh
+        self._scope = _scope
+        self._name = _name
+        self.dim = dim
+        self.C = C
+        self.store = store or default_store()
+        self.prefix = _scope + _name
+        st, p, H = self.store, self.prefix, dim
+        st.get(p + '/v', [1, H], fans=(1, H))
+        for blk in ['emb_d', 'emb_ld'] + (['emb_time'] if self.TW else []):
+            st.get(f'{p}/{blk}/kernel', [1, 1, H], fans=(1, H))
+            st.get(f'{p}/{blk}/bias', [H], init="zeros")
+        for blk in ['proj_d', 'proj_ld'] + (['proj_t'] if self.TW else []):
+            st.get(f'{p}/{blk}/kernel', [1, H, H], fans=(H, H))
+            st.get(f'{p}/{blk}/bias', [H], init="zeros")
+        st.get(p + '/proj_q/kernel', [H, H], fans=(H, H))
+        st.get(p + '/proj_q/bias', [H], init="zeros")
+        self._ref_built = None
+
+    def _build_ref(self, E):
+        if self._ref_built != E:
+            self.store.get(self.prefix + '/proj_ref/kernel', [1, E, self.dim], fans=(E, self.dim))
+            self.store.get(self.prefix + '/proj_ref/bias', [self.dim], init="zeros")
+            self._ref_built = E
+
+    def variable_names(self):
+        return [k for k in self.store.vars if k.startswith(self.prefix + '/')]
+
+    def __call__(self, query, ref, env):
+        """query [R, dim], ref [R, N, E], env with .demand/.load(/.time) -> (e [R, N, dim], logits [R, N])."""
+        E, N = ref.shape[-1], ref.shape[-2]
+        self._build_ref(E)
+        args = dict(task_name="vrptw" if self.TW else "vrp", n_nodes=N, n_cust=N - 1, input_dim=5 if self.TW else 3,
+                    embedding_dim=E, hidden_dim=self.dim, decode_len=1, capacity=1.0, use_tanh=self.use_tanh,
+                    tanh_exploration=float(self.C))
+        params = _dummy_model_params(args)
+        for k in self.variable_names():
+            params['Actor/Decoder/Attention' + k[len(self.prefix):]] = self.store.vars[k]
+        eng = _get_engine(args, params, ("att", id(self.store), self.store.version, self.prefix))
+        return eng.attention(-1, query, ref, env.demand, env.load, env.time if self.TW else None)
+
+
+class AttentionVRPActor(_AttentionActorBase):
+    TW = False
+
+
+class AttentionVRPTWActor(_AttentionActorBase):
+    TW = True
+
+
+class AttentionVRP_UPS_Actor(AttentionVRPActor):      # UPS/vrp_ups_attention.py: identical arithmetic
+    pass
+
+
+class AttentionVRPTW_UPS_Actor(AttentionVRPTWActor):  # UPS/vrptw_ups_attention.py: identical arithmetic
+    pass
+
+
+class _CriticNotOnPath(object):
+    """Attention*Critic is only used by the REINFORCE training step (model/attention_agent.py:243-322),
+    which is outside the rollout path."""
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("the critic belongs to the training step, which this library does not implement")
+
+
+AttentionVRPCritic = AttentionVRPTWCritic = AttentionVRP_UPS_Critic = AttentionVRPTW_UPS_Critic = _CriticNotOnPath
+
+
+class DecodeStep(object):
+    """shared/decode_step.py:3-128 (base class: owns the glimpse and pointer attention modules)."""
+
+    def __init__(self, ClAttention, hidden_dim, use_tanh=False, tanh_exploration=10., n_glimpses=0,
+                 mask_glimpses=True, mask_pointer=True, _scope='', store=None):
+        self.hidden_dim = hidden_dim
+        self.use_tanh = use_tanh
+        self.tanh_exploration = tanh_exploration
+        self.n_glimpses = n_glimpses
+        self.mask_glimpses = mask_glimpses
+        self.mask_pointer = mask_pointer
+        self._scope = _scope
+        self.BIGNUMBER = 100000.
+        self.store = store or default_store()
+        self.glimpses = [None for _ in range(self.n_glimpses)]
+        for i in range(self.n_glimpses):
+            self.glimpses[i] = ClAttention(hidden_dim, use_tanh=False, _scope=self._scope, _name="Glimpse" + str(i), store=self.store)
+        self.pointer = ClAttention(hidden_dim, use_tanh=use_tanh, C=tanh_exploration, _scope=self._scope,
+                                   _name="Decoder/Attention", store=self.store)
+
+
+class RNNDecodeStep(DecodeStep):
+    """shared/decode_step.py:131-234: one BasicLSTMCell layer + glimpses + pointer."""
+    LSTM = 'Decoder/LSTM/rnn/multi_rnn_cell/cell_0/basic_lstm_cell'
+
+    def __init__(self, ClAttention, hidden_dim, use_tanh=False, tanh_exploration=10., n_glimpses=0, mask_glimpses=True,
+                 mask_pointer=True, forget_bias=1.0, rnn_layers=1, _scope='', store=None):
+        super(RNNDecodeStep, self).__init__(ClAttention, hidden_dim, use_tanh=use_tanh, tanh_exploration=tanh_exploration,
+                                            n_glimpses=n_glimpses, mask_glimpses=mask_glimpses, mask_pointer=mask_pointer,
+                                            _scope=_scope, store=store)
+        if rnn_layers != 1:
+            raise ValueError("rnn_layers must be 1 (the reference shares one cell across layers, decode_step.py:180)")
+        self.forget_bias = forget_bias
+        self.rnn_layers = rnn_layers
+        self.dropout = 0.0     # the reference's placeholder; the rollout path always feeds 0.0 (attention_agent.py:495)
+        self._lstm_built = None
+
+    def _build_lstm(self, E):
+        if self._lstm_built != E:
+            H = self.hidden_dim
+            self.store.get(self._scope + self.LSTM + '/kernel', [E + H, 4 * H], fans=(E + H, 4 * H))
+            self.store.get(self._scope + self.LSTM + '/bias', [4 * H], init="zeros")
+            self.pointer._build_ref(E)
+            for g in self.glimpses:
+                g._build_ref(E)
+            self._lstm_built = E
+
+    def model_params(self, embedder: Optional[LinearEmbedding] = None, args=None) -> Dict[str, np.ndarray]:
+        """The store entries under the C ABI's canonical names (scope 'Actor/')."""
+        out = {}
+        sc = self._scope
+        for k, v in self.store.vars.items():
+            if k.startswith(sc) and (k.startswith(sc + 'Decoder/') or k.startswith(sc + 'Glimpse')):
+                out['Actor/' + k[len(sc):]] = v
+        if embedder is not None:
+            out['Actor/Embedding/conv1d/kernel'] = self.store.vars[embedder.scope + '/kernel']
+            out['Actor/Embedding/conv1d/bias'] = self.store.vars[embedder.scope + '/bias']
+        elif args is not None:
+            d1 = args['input_dim'] - 1
+            out['Actor/Embedding/conv1d/kernel'] = np.zeros([1, d1, args['embedding_dim']], np.float32)
+            out['Actor/Embedding/conv1d/bias'] = np.zeros([args['embedding_dim']], np.float32)
+        return out
+
+    def _engine(self, Env, E, N):
+        self._build_lstm(E)
+        tw = self.pointer.TW
+        args = dict(task_name="vrptw" if tw else "vrp", n_nodes=N, n_cust=N - 1, input_dim=5 if tw else 3, embedding_dim=E,
+                    hidden_dim=self.hidden_dim, decode_len=1, capacity=float(getattr(Env, "capacity", 1.0)),
+                    n_glimpses=self.n_glimpses, use_tanh=self.use_tanh, tanh_exploration=float(self.tanh_exploration),
+                    mask_glimpses=self.mask_glimpses, mask_pointer=self.mask_pointer, forget_bias=float(self.forget_bias))
+        return _get_engine(args, self.model_params(args=args), ("dec", id(self.store), self.store.version, self._scope))
+
+    def step(self, decoder_inp, context, Env, decoder_state=None, *args, **kwargs):
+        """decoder_inp [R,1,E], context [R,N,E], decoder_state = (c, h) each [R,H] (LSTMStateTuple order)
+        -> logit, prob, logprob [R,N], decoder_state."""
+        if self.dropout not in (0, 0.0):
+            raise NotImplementedError("dropout > 0 is the training step's setting; the rollout path uses 0.0")
+        import torch
+        E, N = context.shape[-1], context.shape[-2]
+        eng = self._engine(Env, E, N)
+        c, h = decoder_state
+        c, h = c.clone().contiguous(), h.clone().contiguous()
+        logit, prob, logprob = eng.decode_step(decoder_inp, context, Env.demand, Env.load,
+                                               Env.time if self.pointer.TW else None, Env.mask, c, h)
+        return logit, prob, logprob, (c, h)
+
+
+# --------------------------------------------------------------------------------------------------
+# environment
+# --------------------------------------------------------------------------------------------------
+StateVRP = collections.namedtuple("State", ("load", "demand", "d_sat", "mask"))            # VRP/vrp_utils.py:126-131
+StateVRPTW = collections.namedtuple("State", ("load", "time", "demand", "d_sat", "mask"))  # VRPTW/vrptw_utils.py:153-159
+
+
+class _EnvBase(object):
+    TW = False
+
+    def __init__(self, args):
+        self.args = args
+        self.capacity = args['capacity']
+        self.n_nodes = args['n_nodes']
+        self.n_cust = args['n_cust']
+        self.input_dim = args['input_dim']
+        self._input = None
+        self.time = self.load = self.mask = self.demand = None
+        self.beam_width = 1
+        eargs = dict(task_name="vrptw" if self.TW else "vrp", n_nodes=self.n_nodes, n_cust=self.n_cust,
+                     input_dim=self.input_dim, embedding_dim=args.get('embedding_dim', 30), hidden_dim=128, decode_len=1,
+                     capacity=float(self.capacity))
+        self._eargs = eargs
+
+    # placeholder semantics: assign the batch, everything derived follows
+    @property
+    def input_data(self):
+        return self._input
+
+    @input_data.setter
+    def input_data(self, value):
+        import torch
+        x = value if isinstance(value, torch.Tensor) else torch.as_tensor(np.asarray(value, np.float32))
+        self._input = x.to(device="cuda", dtype=torch.float32).contiguous()
+        x = self._input
+        self.input_pnt = x[:, :, :self.input_dim - 1]
+        self.demand = x[:, :, -1]
+        self.batch_size = x.shape[0]
+        if self.TW:
+            self.all_x, self.all_y, self.all_b_tw, self.all_e_tw = x[:, :, 0], x[:, :, 1], x[:, :, 2], x[:, :, 3]
+            self.previous_x, self.previous_y = x[:, self.n_nodes - 1, 0:1], x[:, self.n_nodes - 1, 1:2]
+
+    def _eng(self):
+        return _get_engine(self._eargs, _dummy_model_params(self._eargs), ("env",))
+
+    def _publish(self, st, d_sat):
+        import torch
+        self._state = st
+        self.demand, self.load, self.mask = st["demand"], st["load"], st["mask"]
+        W = self.beam_width
+        if self.TW:
+            self.time = st["time"]
+            self.previous_x, self.previous_y = st["prev_xy"][:, 0:1], st["prev_xy"][:, 1:2]
+            x = self._input
+            self.all_x, self.all_y = x[:, :, 0].repeat(W, 1), x[:, :, 1].repeat(W, 1)
+            self.all_b_tw, self.all_e_tw = x[:, :, 2].repeat(W, 1), x[:, :, 3].repeat(W, 1)
+            return StateVRPTW(load=self.load, time=self.time, demand=self.demand, d_sat=d_sat, mask=self.mask)
+        return StateVRP(load=self.load, demand=self.demand, d_sat=d_sat, mask=self.mask)
+
+    def reset(self, beam_width=1):
+        """Env.reset (VRPTW/vrptw_utils.py:199-252, VRP/vrp_utils.py:159-196)."""
+        import torch
+        if self._input is None:
+            raise RuntimeError("assign env.input_data before reset()")
+        self.beam_width = beam_width
+        self.batch_beam = self.batch_size * beam_width
+        st = self._eng().env_reset(self._input, beam_width)
+        return self._publish(st, torch.zeros((self.batch_beam, self.n_nodes), device=self._input.device))
+
+    def step(self, idx, beam_parent=None):
+        """Env.step (VRPTW/vrptw_utils.py:254-358, VRP/vrp_utils.py:198-255): idx, beam_parent [R,1] int64."""
+        st, d_sat = self._eng().env_step(self._input, self.beam_width, self._state, idx, beam_parent)
+        return self._publish(st, d_sat)
+
+
+class VRPEnv(_EnvBase):
+    TW = False
+
+
+class VRPTWEnv(_EnvBase):
+    TW = True
+
+
+def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
+    """Tour length of a decoded solution, depot=None branch (VRPTW/vrptw_utils.py:397-414, VRP/vrp_utils.py:293-307).
+    sample_solution: list of T tensors [R, >=2] or a tensor [T, R, >=2].  The min_trucks branches are out of scope."""
+    import torch
+    if depot is not None:
+        raise NotImplementedError("min_trucks reward (depot != None) is outside the rollout path (SURVEY section 8f, N2)")
+    sol = sample_solution if isinstance(sample_solution, torch.Tensor) else torch.stack(list(sample_solution), 0)
+    sol = sol.to(device="cuda", dtype=torch.float32).contiguous()
+    args = dict(task_name="vrp", n_nodes=2, n_cust=1, input_dim=3, embedding_dim=1, hidden_dim=128, decode_len=1, capacity=1.0)
+    return _get_engine(args, _dummy_model_params(args), ("reward",)).reward(sol)
+
+
+class DataGenerator(object):
+    """DataGenerator of VRP/vrp_utils.py:55-123, VRPTW/vrptw_utils.py:70-150 and the UPS twins: host-side numpy."""
+
+    def __init__(self, args):
+        self.args = args
+        self.rnd = np.random.RandomState(seed=args['random_seed'])
+        self.n_problems = args['test_size']
+        self.test_data = _data.create_dataset(args['task_name'], self.n_problems, args['n_cust'], args['random_seed'] + 1,
+                                              ups=bool(args.get('ups', False)))
+        self.reset()
+
+    def reset(self):
+        self.count = 0
+
+    def get_train_next(self):
+        a = self.args
+        seed = int(self.rnd.randint(0, 2**31 - 1))
+        return _data.create_dataset(a['task_name'], a['batch_size'], a['n_cust'], seed, ups=bool(a.get('ups', False)))
+
+    def get_test_next(self):
+        if self.count >= self.args['test_size']:
+            warnings.warn("The test iterator reset.")
+            self.count = 0
+        out = self.test_data[self.count:self.count + 1]
+        self.count += 1
+        return out
+
+    def get_test_all(self):
+        return self.test_data
+
+
+def load_task_specific_components(task, ups=False):
+    """main.py:17-53 -> (DataGenerator, Env, reward_func, AttentionActor, AttentionCritic)."""
+    if task == 'vrp':
+        return (DataGenerator, VRPEnv, reward_func, AttentionVRP_UPS_Actor if ups else AttentionVRPActor, AttentionVRPCritic)
+    if task == 'vrptw':
+        return (DataGenerator, VRPTWEnv, reward_func, AttentionVRPTW_UPS_Actor if ups else AttentionVRPTWActor, AttentionVRPTWCritic)
+    raise Exception('Task is not implemented')
+
+
+# --------------------------------------------------------------------------------------------------
+# the agent
+# --------------------------------------------------------------------------------------------------
+class _Printer:
+    def print_out(self, s, *a, **k):
+        print(s)
+
+
+class RLAgent(object):
+    """model/attention_agent.py:11-556, inference side.  ``build_model(decode_type)`` EXECUTES the rollout on
+    ``env.input_data`` (the reference builds a graph that sess.run executes later) and returns the same tuple
+    ``(R, v, logprobs, actions, idxs, input_pnt, probs)``."""
+
+    def __init__(self, args, prt, env, dataGen, reward_func, clAttentionActor, clAttentionCritic, is_train=False, _scope='',
+                 store: Optional[VariableStore] = None, device: int = 0):
+        if is_train:
+            raise NotImplementedError("the REINFORCE training step is outside the rollout path (SURVEY section 8f, N1)")
+        if args.get('embedding_graph', 0) != 0:
+            raise NotImplementedError("only embedding_graph=0 (LinearEmbedding) is on the rollout path")
+        self.args = args
+        self.prt = prt or _Printer()
+        self.env = env
+        self.dataGen = dataGen
+        self.reward_func = reward_func
+        self.clAttentionCritic = clAttentionCritic
+        self.store = store or default_store()
+        self.device = device
+        self.embedder_model = LinearEmbedding(args['embedding_dim'], _scope=_scope + 'Actor/', store=self.store)
+        self.decodeStep = RNNDecodeStep(clAttentionActor, args['hidden_dim'], use_tanh=args['use_tanh'],
+                                        tanh_exploration=args['tanh_exploration'], n_glimpses=args['n_glimpses'],
+                                        mask_glimpses=args['mask_glimpses'], mask_pointer=args['mask_pointer'],
+                                        forget_bias=args['forget_bias'], rnn_layers=args['rnn_layers'], _scope=_scope + 'Actor/',
+                                        store=self.store)
+        # created, saved, never used by the reference (attention_agent.py:65-66, shadowed at :133)
+        self.store.get(_scope + 'decoder_input', [1, 1, args['embedding_dim']], fans=(args['embedding_dim'], args['embedding_dim']))
+        self.embedder_model._build(args['input_dim'] - 1)
+        self.decodeStep._build_lstm(args['embedding_dim'])
+        self.sess = None
+        self.last_time = None
+
+    # -- checkpoint ------------------------------------------------------------------------------
+    def Initialize(self, sess=None):
+        self.sess = sess
+        self.load_model()
+
+    def load_model(self):
+        """args['load_path']: directory holding model.npz, or an .npz file, keyed by TF variable name."""
+        path = self.args.get('load_path') or ''
+        if os.path.isdir(path):
+            path = os.path.join(path, 'model.npz')
+        if path and os.path.exists(path):
+            self.store.load(path, strict=False)
+            print("have load model")
+
+    def model_params(self):
+        return self.decodeStep.model_params(self.embedder_model)
+
+    def engine(self):
+        eargs = dict(self.args)
+        eargs.setdefault('task_name', 'vrptw' if self.env.TW else 'vrp')
+        return _get_engine(eargs, self.model_params(), ("agent", id(self.store), self.store.version), self.device)
+
+    # -- the rollout -----------------------------------------------------------------------------
+    def build_model(self, decode_type="greedy", uniforms=None, uniforms_retry=None, seed=0, want_probs=False,
+                    backend="auto"):
+        """attention_agent.py:84-272.  backend 'fused' = the persistent rollout kernel, 'stepwise' = the reference's
+        loop over RNNDecodeStep.step / Env.step on device state (beam search and glimpses take this route in this
+        round), 'auto' picks."""
+        import torch
+        fused_ok = decode_type in ("greedy", "stochastic") and self.args['n_glimpses'] == 0 and not want_probs
+        if backend == "auto":
+            backend = "fused" if fused_ok else "stepwise"
+        if backend == "fused":
+            if not fused_ok:
+                raise NotImplementedError("fused kernel: greedy/stochastic without glimpses")
+            out = self.engine().rollout(self.env.input_data, decode_type, uniforms=uniforms, uniforms_retry=uniforms_retry,
+                                        seed=seed, want_logprobs=True)
+            idx = out.idxs.long()                                      # [T, R]
+            T, R = idx.shape
+            pnt = self.env.input_pnt                                    # [B, N, D-1]
+            actions = pnt[torch.arange(R, device=idx.device)[None, :].expand(T, R), idx]   # [T, R, D-1]
+            v = torch.zeros((), device=idx.device)
+            return (out.R, v, list(out.logprobs), list(actions), [i[:, None] for i in idx], pnt, None)
+        return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs)
+
+    def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs):
+        """The reference loop, line for line, on device tensors (attention_agent.py:89-240)."""
+        import torch
+        args, env = self.args, self.env
+        input_pnt = env.input_pnt
+        batch_size = input_pnt.shape[0]
+        dev = input_pnt.device
+        encoder_emb_inp = self.embedder_model(input_pnt.contiguous())                     # :96
+        beam_width = args['beam_width'] if decode_type == 'beam_search' else 1             # :98-102
+        self.beam_width = beam_width
+        env.reset(beam_width)                                                              # :110
+        R_ = batch_size * beam_width
+        BatchSequence = torch.arange(R_, device=dev)[:, None]                              # :112-114
+        actions_tmp, logprobs, probs, idxs = [], [], [], []
+        H = args['hidden_dim']
+        decoder_state = (torch.zeros(R_, H, device=dev), torch.zeros(R_, H, device=dev))   # :126-129
+        decoder_input = encoder_emb_inp[:, env.n_nodes - 1:env.n_nodes].repeat(beam_width, 1, 1)   # :133-134
+        context = encoder_emb_inp.repeat(beam_width, 1, 1)                                 # :137
+        BatchBeamSeq = torch.arange(batch_size, device=dev).repeat(beam_width)[:, None]
+        beam_path, log_beam_probs = [], []
+        pnt_t = input_pnt.repeat(beam_width, 1, 1)
+        for i in range(args['decode_len']):
+            logit, prob, logprob, decoder_state = self.decodeStep.step(decoder_input, context, env, decoder_state)   # :140
+            beam_parent = None
+            if decode_type == 'greedy':
+                idx = torch.argmax(prob, 1, keepdim=True)                                  # :147
+            elif decode_type == 'stochastic':                                             # :148-167
+                def my_multinomial(u):
+                    cum = torch.cumsum(prob, 1)
+                    rand = u[:, None].to(dev).expand(-1, env.n_nodes)
+                    sorted_ind = torch.arange(env.n_nodes, device=dev)[None, :].expand(R_, -1)
+                    tmp = (cum > rand).long() * sorted_ind + 10000 * (rand >= cum).long()
+                    return tmp, torch.argmin(tmp, 1, keepdim=True)
+                u1 = torch.as_tensor(uniforms[i]) if uniforms is not None else torch.rand(R_)
+                tmp, idx = my_multinomial(u1)
+                if bool((tmp.sum(1) > 10000 * env.n_nodes - 1).any()):
+                    u2 = torch.as_tensor(uniforms_retry[i]) if uniforms_retry is not None else torch.rand(R_)
+                    tmp, idx = my_multinomial(u2)
+            elif decode_type == 'beam_search':                                            # :169-205
+                if i == 0:
+                    log_beam_prob = torch.log(prob[:batch_size])
+                else:
+                    log_beam_prob = torch.log(prob) + log_beam_probs[-1]
+                    log_beam_prob = torch.cat(torch.split(log_beam_prob, batch_size, 0), 1)
+                # tf.nn.top_k orders ties by lower index: stable descending sort
+                order = torch.sort(log_beam_prob, dim=1, descending=True, stable=True)[1][:, :beam_width]
+                topk_logprob_val = torch.gather(log_beam_prob, 1, order)
+                topk_logprob_val = topk_logprob_val.t().reshape(-1, 1)
+                topk_logprob_ind = order.t().reshape(-1, 1)
+                idx = topk_logprob_ind % env.n_nodes
+                beam_parent = topk_logprob_ind // env.n_nodes
+                batchedBeamIdx = BatchBeamSeq + batch_size * beam_parent
+                prob = prob[batchedBeamIdx[:, 0]]
+                beam_path.append(beam_parent)
+                log_beam_probs.append(topk_logprob_val)
+            else:
+                raise ValueError(decode_type)
+            env.step(idx, beam_parent)                                                     # :207
+            batched_idx = idx[:, 0]
+            decoder_input = context[BatchSequence[:, 0], batched_idx][:, None, :]          # :211-212
+            logprobs.append(torch.log(prob[BatchSequence[:, 0], batched_idx]))             # :214
+            probs.append(prob)
+            idxs.append(idx)
+            actions_tmp.append(pnt_t[BatchSequence[:, 0], batched_idx])                    # :219
+        if decode_type == 'beam_search':                                                   # :222-231
+            tmplst = []
+            tmpind = [BatchSequence]
+            for k in reversed(range(len(actions_tmp))):
+                tmplst = [actions_tmp[k][tmpind[-1][:, 0]]] + tmplst
+                tmpind += [(BatchBeamSeq + batch_size * beam_path[k])[tmpind[-1][:, 0]]]
+            actions = tmplst
+        else:
+            actions = actions_tmp
+        self.last_beam_path = beam_path
+        R = self.reward_func(actions)                                                      # :236-240
+        v = torch.zeros((), device=dev)
+        return (R, v, logprobs, actions, idxs, input_pnt, probs if want_probs else None)
+
+    # -- evaluation ------------------------------------------------------------------------------
+    def evaluate_batch(self, eval_type='greedy', backend="auto"):
+        """attention_agent.py:475-518: decode dataGen.get_test_all(); min over beams; print mean/std/time."""
+        import torch
+        beam_width = self.args['beam_width'] if eval_type == 'beam_search' else 1
+        data = self.dataGen.get_test_all()
+        self.env.input_data = torch.as_tensor(np.asarray(data, np.float32))
+        torch.cuda.synchronize()
+        start_time = time.time()
+        R, v, logprobs, actions, idxs, batch, _ = self.build_model(eval_type, backend=backend)
+        R = R.cpu().numpy()
+        R = np.concatenate(np.split(np.expand_dims(R, 1), beam_width, axis=0), 1)
+        R = np.amin(R, 1, keepdims=False)
+        end_time = time.time() - start_time
+        self.last_time = end_time
+        self.prt.print_out('Average of {} in batch-mode: {} -- std {} -- time {} s'.format(
+            eval_type, np.mean(R), np.sqrt(np.var(R)), end_time))
+        return R
+
+    def evaluate_single(self, eval_type='greedy'):
+        """attention_agent.py:336-413 (B=1 latency mode): one problem at a time through the same path."""
+        import torch
+        beam_width = self.args['beam_width'] if eval_type == 'beam_search' else 1
+        self.dataGen.reset()
+        rewards = []
+        start_time = time.time()
+        for _ in range(self.dataGen.n_problems):
+            self.env.input_data = torch.as_tensor(np.asarray(self.dataGen.get_test_next(), np.float32))
+            R = self.build_model(eval_type)[0].cpu().numpy()
+            rewards.append(float(np.amin(R.reshape(beam_width, -1), 0)[0]))
+        end_time = time.time() - start_time
+        self.prt.print_out('Average of {} in single-mode: {} -- std {} -- time {} s'.format(
+            eval_type, np.mean(rewards), np.sqrt(np.var(rewards)), end_time))
+        return np.asarray(rewards)
+
+    def inference(self, infer_type='batch'):
+        if infer_type == 'batch':
+            self.evaluate_batch('greedy')
+            self.evaluate_batch('beam_search')
+        elif infer_type == 'single':
+            self.evaluate_single('greedy')
+            self.evaluate_single('beam_search')
+        self.prt.print_out("##################################################################")

@@ -1,0 +1,132 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol of include/vrpb200.h, the host
+mirror creates exactly the reference's variable names, generators match the oracle's, sharding logic (gloo, 2 ranks)."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import restatement as O
+from tests.helpers import load_pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    pkg = load_pkg()
+    pkg.build_library()
+    hdr = open(os.path.join(ROOT, "include", "vrpb200.h")).read()
+    declared = set(re.findall(r"\b(vrpb200_[a-z_]+)\s*\(", hdr))
+    assert len(declared) >= 14
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/vrpb200.h but not exported"
+    assert set(pkg._lib.EXPORTS) == declared
+    assert pkg._lib.load().vrpb200_version() == 1
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    pkg = load_pkg()
+    with pytest.raises(pkg.VrpB200Error):
+        pkg.Engine(O.default_args("vrptw10"))
+    lib = pkg._lib.load()
+    cfg = pkg.config_from_args(O.default_args("vrptw10"))
+    h = ctypes.c_void_p()
+    assert lib.vrpb200_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -2      # VRPB200_E_CUDA
+    assert b"no CUDA device" in lib.vrpb200_last_error(None)
+
+
+def test_create_rejects_bad_configs_before_touching_cuda():
+    pkg = load_pkg()
+    lib = pkg._lib.load()
+    for over in (dict(hidden_dim=64), dict(n_nodes=300, n_cust=299), dict(input_dim=4), dict(n_cust=3), dict(decode_len=0)):
+        cfg = pkg.config_from_args(dict(O.default_args("vrptw10"), **over))
+        h = ctypes.c_void_p()
+        assert lib.vrpb200_create(ctypes.byref(cfg), 0, ctypes.byref(h)) == -1, over   # VRPB200_E_ARG
+        assert lib.vrpb200_last_error(None)
+
+
+@pytest.mark.parametrize("task,ng", [("vrptw10", 0), ("vrp10", 0), ("vrptw20", 2)])
+def test_host_mirror_creates_the_reference_variable_names(task, ng):
+    pkg = load_pkg()
+    H = pkg.host
+    args = pkg.task_specific_params.default_args(task, n_glimpses=ng)
+    store = H.VariableStore(seed=1)
+    _, Env, reward_func, Actor, Critic = H.load_task_specific_components(args["task_name"], False)
+    agent = H.RLAgent(args, None, Env(args), None, reward_func, Actor, Critic, is_train=False, store=store)
+    want = O.init_params(O.default_args(task, n_glimpses=ng))
+    got = {k: v.shape for k, v in store.vars.items() if k != "decoder_input"}
+    assert got == {k: v.shape for k, v in want.items()}
+    assert set(agent.model_params()) == set(want)
+    # assigning a checkpoint by name replaces the values; an unknown name is rejected
+    store.assign(want)
+    np.testing.assert_array_equal(agent.model_params()["Actor/Decoder/Attention/v"], want["Actor/Decoder/Attention/v"])
+    with pytest.raises(KeyError):
+        store.assign({"Actor/Nope": np.zeros(3)})
+
+
+def test_generators_match_the_reference_restatement():
+    pkg = load_pkg()
+    for task in ("vrp10", "vrptw20", "vrp100"):
+        t = O.TASKS[task]
+        np.testing.assert_array_equal(pkg.data.create_dataset(t.task_name, 50, t.n_cust, 7), O.create_dataset(task, 50, 7))
+    d = pkg.data.create_vrptw_ups_dataset(200, 100, 3)
+    assert d.shape == (200, 101, 5)
+    np.testing.assert_allclose(d[:, -1], np.tile([0, 0, 0, 1000 * 0.1567, 0], [200, 1]), rtol=0, atol=0); assert True                      # depot row, UPS/vrptw_ups_utils.py:52
+    assert (d[:, :-1, 4] >= 1).all() and (d[:, :-1, 4] == np.round(d[:, :-1, 4])).all()
+    assert (d[:, :-1, 2] >= 0).all() and (d[:, :-1, 3] <= 950 * 0.1567 + 1e-9).all() and (d[:, :-1, 2] < d[:, :-1, 3]).all()
+    np.testing.assert_array_equal(d, pkg.data.create_vrptw_ups_dataset(200, 100, 3))
+
+
+def test_glorot_params_have_reference_names_and_bounds():
+    pkg = load_pkg()
+    args = pkg.task_specific_params.default_args("vrptw50")
+    p = pkg.data.glorot_params(args, seed=5)
+    want = O.init_params(O.default_args("vrptw50"))
+    assert {k: v.shape for k, v in p.items()} == {k: v.shape for k, v in want.items()}
+    k = p["Actor/Decoder/Attention/proj_q/kernel"]
+    assert np.abs(k).max() <= np.sqrt(6.0 / 256) and all(np.all(v == 0) for n, v in p.items() if n.endswith("bias"))
+
+
+def test_task_table_matches_reference_sizes():
+    pkg = load_pkg()
+    for name, t in O.TASKS.items():
+        assert tuple(pkg.task_specific_params.task_lst[name]) == tuple(t)
+
+
+def _worker(rank, world, port, n, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    pkg = load_pkg()
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    lo, hi = pkg.distributed.shard_range(n, rank, world)
+    local = torch.arange(lo, hi, dtype=torch.float32) * 2.0          # stand-in for the shard's tour costs
+    out = pkg.distributed.gather_costs(local, n, dst=0)
+    if rank == 0:
+        q.put(out.tolist())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 11])
+def test_sharding_and_cost_gather_two_ranks_gloo(n):
+    import torch.multiprocessing as mp
+    pkg = load_pkg()
+    assert [pkg.distributed.shard_range(11, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 11)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + n
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert got == [2.0 * i for i in range(n)]
