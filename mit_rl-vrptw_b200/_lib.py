@@ -25,7 +25,7 @@ class Config(C.Structure):
     """struct vrpb200_config"""
     _fields_ = [(n, C.c_int32) for n in (
         "task", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
-        "use_tanh", "mask_glimpses", "mask_pointer", "rows_per_cta")] + [
+        "use_tanh", "mask_glimpses", "mask_pointer", "rows_per_cta", "gemm_path")] + [
         ("capacity", C.c_float), ("tanh_exploration", C.c_float), ("forget_bias", C.c_float)]
 
 

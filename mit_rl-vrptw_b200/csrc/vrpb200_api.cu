@@ -34,6 +34,8 @@ struct vrpb200_handle {
     // offsets (in floats) into the blob
     const float* Wg = nullptr;
     const float* bg = nullptr;
+    const float* WgTc = nullptr;
+    const float* WqTc[8] = {nullptr};
     AttWeights att[8];
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
@@ -70,6 +72,16 @@ int fail(vrpb200_handle* h, int code, const char* fmt, ...) {
     } while (0)
 
 struct HostTensor { const float* p; int64_t n; };
+
+float tf32_round(float x) {   // round-to-nearest-even onto TF32's 10 explicit mantissa bits
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u += 0xFFFu + ((u >> 13) & 1u);
+    u &= 0xFFFFE000u;
+    float y;
+    memcpy(&y, &u, 4);
+    return y;
+}
 
 const char* kLstm = "Actor/Decoder/LSTM/rnn/multi_rnn_cell/cell_0/basic_lstm_cell";
 
@@ -108,6 +120,7 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
+    if (c.gemm_path != 0 && c.gemm_path != 1) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (tcgen05) or 1 (ffma)");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -194,6 +207,7 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     // layout [slab s][kk 8][uh 2][part 2][lane 32][gate 4], unit = uh*64 + 2*lane + part, k = 8 s + kk.
     const size_t oWg = reserve((size_t)kGateSlabs * kSlabFloats);
     const size_t obg = reserve(4 * H);
+    const size_t oWgTc = reserve((size_t)kTcUsesA * kSlabFloats);
     {
         std::vector<double> Wx((size_t)D1 * 4 * H, 0.0), bx(4 * H, 0.0);
         for (int col = 0; col < 4 * H; ++col) {
@@ -221,8 +235,24 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         }
         for (int unit = 0; unit < H; ++unit)
             for (int g = 0; g < 4; ++g) blob[obg + unit * 4 + g] = (float)bx[g * H + unit];
+        // tcgen05 path: per (k-chunk, N-half) stage a hi tile and a lo tile, [N=256][K=8] canonical K-major no-swizzle
+        // ([n/8][k/4][n%8][k%4]); n = 4*unit_local + gate, unit = 64*half + unit_local
+        for (int u = 0; u < kTcUsesA; ++u) {
+            const int kc = u >> 1, half = u & 1;
+            for (int n = 0; n < 256; ++n)
+                for (int kl = 0; kl < 8; ++kl) {
+                    const int unit = half * 64 + n / 4, g = n % 4, k = kc * 8 + kl, col = g * H + unit;
+                    float val = 0.0f;
+                    if (k < H) val = lstm_k[(size_t)(E + k) * 4 * H + col];
+                    else if (k - H < D1) val = (float)Wx[(size_t)(k - H) * 4 * H + col];
+                    const float hi = tf32_round(val), lo = tf32_round(val - hi);
+                    const size_t o = (size_t)(n / 8) * 64 + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
+                    blob[oWgTc + (size_t)u * kSlabFloats + o] = hi;
+                    blob[oWgTc + (size_t)u * kSlabFloats + 2048 + o] = lo;
+                }
+        }
     }
-    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce; };
+    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc; };
     std::vector<AttOff> ao(natt);
     for (int a = 0; a < natt; ++a) {
         const RawHost& r = rh[a];
@@ -230,6 +260,18 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         o.Wq = put(r.pq_k, (size_t)H * H);   // [k][unit] row-major == 4 slabs of 32 k-rows
         o.bq = reserve(H); o.A = reserve(4 * H); o.gd = reserve(H); o.gl = reserve(H); o.gt = reserve(H);
         o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H);
+        o.WqTc = reserve((size_t)kTcUsesB * kSlabFloats);
+        for (int u = 0; u < kTcUsesB; ++u)
+            for (int kk = 0; kk < 2; ++kk)
+                for (int n = 0; n < H; ++n)
+                    for (int kl = 0; kl < 8; ++kl) {
+                        const int k = (2 * u + kk) * 8 + kl;
+                        const float val = r.pq_k[(size_t)k * H + n];
+                        const float hi = tf32_round(val), lo = tf32_round(val - hi);
+                        const size_t oo = (size_t)(n / 8) * 64 + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
+                        blob[o.WqTc + (size_t)u * kSlabFloats + kk * 2048 + oo] = hi;
+                        blob[o.WqTc + (size_t)u * kSlabFloats + kk * 2048 + 1024 + oo] = lo;
+                    }
         for (int hh = 0; hh < H; ++hh) {
             double gdv = 0, cd = r.pd_b[hh], gld = 0, cld = r.pld_b[hh], gtv = 0, ct = 0;
             for (int k = 0; k < H; ++k) {
@@ -279,9 +321,11 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     const float* d = h->d_blob;
     h->Wg = d + oWg;
     h->bg = d + obg;
+    h->WgTc = d + oWgTc;
     for (int a = 0; a < natt; ++a) {
         h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
                                d + ao[a].v, d + ao[a].Au, d + ao[a].ce};
+        h->WqTc[a] = d + ao[a].WqTc;
         const RawOff& o = ro[a];
         RawAtt& ra = h->raw.att[a];
         ra.v = d + o.v;
@@ -304,10 +348,10 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
 
 namespace {
 
-template <int RB, bool TW>
+template <int RB, bool TW, bool TC>
 int launch_rollout_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout_kernel<RB, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout_kernel<RB, TW><<<grid, RB * 8, smem, st>>>(a);
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout_kernel<RB, TW, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout_kernel<RB, TW, TC><<<grid, TC ? 512 : RB * 8, smem, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -315,6 +359,7 @@ int launch_rollout_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
+    const bool tc = c.gemm_path == 0;
     // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks,
     // else the smallest (more, lighter CTAs for small batches)
     const int cand[4] = {64, 48, 32, 16};
@@ -324,24 +369,26 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     } else {
         for (int i = 0; i < 4 && !RB; ++i) {
             const int rb = cand[i];
-            if (make_layout(rb, rb, c.n_nodes, FD).total > h->max_smem_optin) continue;
+            if (make_layout(rb, rb, c.n_nodes, FD, tc).total > h->max_smem_optin) continue;
             if ((a.B + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
         }
     }
     if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory");
     a.IB = RB / a.W;
-    const SmemLayout L = make_layout(RB, a.IB, c.n_nodes, FD);
+    const SmemLayout L = make_layout(RB, a.IB, c.n_nodes, FD, tc);
     if (L.total > h->max_smem_optin)
         return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, L.total, h->max_smem_optin);
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
-    h->last_launch[0] = (int)grid; h->last_launch[1] = RB * 8; h->last_launch[2] = L.total; h->last_launch[3] = RB;
-    h->last_launch[4] = 1;
+    h->last_launch[0] = (int)grid; h->last_launch[1] = tc ? 512 : RB * 8; h->last_launch[2] = L.total; h->last_launch[3] = RB;
+    h->last_launch[4] = 1; h->last_launch[5] = tc ? 1 : 0;
     int rc = 0;
-#define DISPATCH(rb)                                                                     \
-    case rb:                                                                             \
-        rc = h->tw ? launch_rollout_t<rb, true>(h, a, (int)grid, L.total, st)            \
-                   : launch_rollout_t<rb, false>(h, a, (int)grid, L.total, st);          \
+#define DISPATCH(rb)                                                                                   \
+    case rb:                                                                                           \
+        if (tc) rc = h->tw ? launch_rollout_t<rb, true, true>(h, a, (int)grid, L.total, st)            \
+                           : launch_rollout_t<rb, false, true>(h, a, (int)grid, L.total, st);          \
+        else    rc = h->tw ? launch_rollout_t<rb, true, false>(h, a, (int)grid, L.total, st)           \
+                           : launch_rollout_t<rb, false, false>(h, a, (int)grid, L.total, st);         \
         break;
     switch (RB) {
         DISPATCH(64) DISPATCH(48) DISPATCH(32) DISPATCH(16)
@@ -374,6 +421,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     RolloutArgs a;
     memset(&a, 0, sizeof a);
     a.input = d_input; a.Wg = h->Wg; a.bg = h->bg; a.att = h->att[c.n_glimpses];
+    a.WgTc = h->WgTc; a.WqTc = h->WqTc[c.n_glimpses];
     a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
     a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
     if (trace) {

@@ -17,7 +17,7 @@ from . import _lib
 from ._lib import Config, Trace, VrpB200Error, DECODE_MODES
 
 
-def config_from_args(args: dict, rows_per_cta: int = 0) -> Config:
+def config_from_args(args: dict, rows_per_cta: int = 0, gemm_path: int = 0) -> Config:
     """args = the reference's merged flag/task dict (configs.py:28-111 + task_specific_params.py)."""
     task_name = args.get("task_name") or ("vrptw" if args["input_dim"] == 5 else "vrp")
     return Config(
@@ -26,7 +26,7 @@ def config_from_args(args: dict, rows_per_cta: int = 0) -> Config:
         embedding_dim=args.get("embedding_dim", 30), hidden_dim=args.get("hidden_dim", 128),
         decode_len=args["decode_len"], n_glimpses=args.get("n_glimpses", 0),
         use_tanh=int(bool(args.get("use_tanh", False))), mask_glimpses=int(bool(args.get("mask_glimpses", True))),
-        mask_pointer=int(bool(args.get("mask_pointer", True))), rows_per_cta=rows_per_cta,
+        mask_pointer=int(bool(args.get("mask_pointer", True))), rows_per_cta=rows_per_cta, gemm_path=gemm_path,
         capacity=float(args["capacity"]), tanh_exploration=float(args.get("tanh_exploration", 10.0)),
         forget_bias=float(args.get("forget_bias", 1.0)))
 
@@ -52,12 +52,12 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class Engine:
-    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0):
+    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0, gemm: str = "tc"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise VrpB200Error("no CUDA device: the rollout path has no CPU implementation")
         self.args = dict(args)
-        self.cfg = config_from_args(args, rows_per_cta)
+        self.cfg = config_from_args(args, rows_per_cta, {"tc": 0, "ffma": 1}[gemm])
         self.device = torch.device("cuda", device)
         self.handle = C.c_void_p()
         rc = self.lib.vrpb200_create(C.byref(self.cfg), device, C.byref(self.handle))

@@ -42,7 +42,10 @@ from .task_specific_params import task_lst  # noqa: F401  (re-export, reference:
 class VariableStore:
     """name -> float32 array; the stand-in for TF's global variable collection."""
 
+    _uids = iter(range(1, 1 << 62))
+
     def __init__(self, seed: int = 1234):
+        self.uid = next(VariableStore._uids)    # id() values are recycled after garbage collection; this is not
         self.vars: Dict[str, np.ndarray] = collections.OrderedDict()
         self.rnd = np.random.RandomState(seed)
         self.version = 0
@@ -165,7 +168,7 @@ class LinearEmbedding(Embedding):
         params = _dummy_model_params(args)
         params['Actor/Embedding/conv1d/kernel'] = self.store.vars[self.scope + '/kernel']
         params['Actor/Embedding/conv1d/bias'] = self.store.vars[self.scope + '/bias']
-        eng = _get_engine(args, params, ("emb", id(self.store), self.store.version, self.scope))
+        eng = _get_engine(args, params, ("emb", self.store.uid, self.store.version, self.scope))
         out = eng.embed(x)
         self.total_time += time.time() - t0
         return out
@@ -214,7 +217,7 @@ class _AttentionActorBase(object):
         params = _dummy_model_params(args)
         for k in self.variable_names():
             params['Actor/Decoder/Attention' + k[len(self.prefix):]] = self.store.vars[k]
-        eng = _get_engine(args, params, ("att", id(self.store), self.store.version, self.prefix))
+        eng = _get_engine(args, params, ("att", self.store.uid, self.store.version, self.prefix))
         return eng.attention(-1, query, ref, env.demand, env.load, env.time if self.TW else None)
 
 
@@ -315,7 +318,7 @@ class RNNDecodeStep(DecodeStep):
                     hidden_dim=self.hidden_dim, decode_len=1, capacity=float(getattr(Env, "capacity", 1.0)),
                     n_glimpses=self.n_glimpses, use_tanh=self.use_tanh, tanh_exploration=float(self.tanh_exploration),
                     mask_glimpses=self.mask_glimpses, mask_pointer=self.mask_pointer, forget_bias=float(self.forget_bias))
-        return _get_engine(args, self.model_params(args=args), ("dec", id(self.store), self.store.version, self._scope))
+        return _get_engine(args, self.model_params(args=args), ("dec", self.store.uid, self.store.version, self._scope))
 
     def step(self, decoder_inp, context, Env, decoder_state=None, *args, **kwargs):
         """decoder_inp [R,1,E], context [R,N,E], decoder_state = (c, h) each [R,H] (LSTMStateTuple order)
@@ -527,7 +530,7 @@ class RLAgent(object):
     def engine(self):
         eargs = dict(self.args)
         eargs.setdefault('task_name', 'vrptw' if self.env.TW else 'vrp')
-        return _get_engine(eargs, self.model_params(), ("agent", id(self.store), self.store.version), self.device)
+        return _get_engine(eargs, self.model_params(), ("agent", self.store.uid, self.store.version), self.device)
 
     # -- the rollout -----------------------------------------------------------------------------
     def build_model(self, decode_type="greedy", uniforms=None, uniforms_retry=None, seed=0, want_probs=False,

@@ -53,10 +53,11 @@ FUSED_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
 
 @pytest.mark.parametrize("name", FUSED_CASES)
 @pytest.mark.parametrize("rows_per_cta", [0, 64])
-def test_rollout_matches_reference_fixture(name, rows_per_cta):
+@pytest.mark.parametrize("gemm", ["tc", "ffma"])
+def test_rollout_matches_reference_fixture(name, rows_per_cta, gemm):
     fx, args, params = load_golden(name)
     meta = GOLDEN_INDEX[name]
-    eng, torch = _engine(args, params, rows_per_cta=rows_per_cta)
+    eng, torch = _engine(args, params, rows_per_cta=rows_per_cta, gemm=gemm)
     x = torch.from_numpy(fx["data"].astype(np.float32)).cuda()
     out = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"),
                       want_logprobs=True, trace=True)
@@ -85,12 +86,13 @@ def test_fast_path_equals_trace_path(name):
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
-def test_greedy_vs_oracle_seeded(task, B, seed, bias):
+@pytest.mark.parametrize("gemm", ["tc", "ffma"])
+def test_greedy_vs_oracle_seeded(task, B, seed, bias, gemm):
     """Ragged batch sizes, every task size; per-instance comparison up to the first near-tie."""
     args = O.default_args(task)
     params = O.init_params(args, seed=100 + seed, bias_scale=bias)
     data = O.create_dataset(task, B, seed=seed)
-    eng, torch = _engine(args, params)
+    eng, torch = _engine(args, params, gemm=gemm)
     out = eng.rollout(torch.from_numpy(data.astype(np.float32)).cuda(), "greedy", want_logprobs=True, trace=True)
     torch.cuda.synchronize()
     ref = O.rollout(params, args, data, "greedy", keep_probs=True)
@@ -167,6 +169,29 @@ def test_host_entry_point_equals_device_entry_point():
     torch.cuda.synchronize()
     np.testing.assert_array_equal(idx_h, out.idxs.cpu().numpy())
     np.testing.assert_array_equal(cost_h, out.R.cpu().numpy())
+
+
+def test_tensor_core_path_equals_fp32_path_up_to_near_ties():
+    """The tcgen05 (3xTF32 split) GEMMs against the FP32-pipe GEMMs of the same kernel: logits within 2e-6,
+    identical tours except at near-ties, every rows_per_cta."""
+    args = O.default_args("vrptw50")
+    params = O.init_params(args, seed=41, bias_scale=0.2)
+    data = O.create_dataset("vrptw50", 700, seed=12).astype(np.float32)
+    import torch
+    x = torch.from_numpy(data).cuda()
+    ref_eng, _ = _engine(args, params, gemm="ffma")
+    ref = ref_eng.rollout(x, "greedy", trace=True)
+    for rb in (16, 32, 48, 64):
+        eng, _ = _engine(args, params, gemm="tc", rows_per_cta=rb)
+        out = eng.rollout(x, "greedy", trace=True)
+        torch.cuda.synchronize()
+        same = (out.idxs == ref.idxs).all(0)
+        assert same.float().mean().item() >= 0.97, rb
+        um = (ref.masks == 0)[:, same]
+        d = (out.logits[:, same] - ref.logits[:, same]).abs()[um]
+        assert d.max().item() < 5e-6, (rb, d.max().item())
+        assert torch.equal(out.masks[:, same], ref.masks[:, same])
+        np.testing.assert_allclose(out.R[same].cpu().numpy(), ref.R[same].cpu().numpy(), rtol=1e-6)
 
 
 def test_errors_are_reported_not_thrown():

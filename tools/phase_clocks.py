@@ -1,0 +1,32 @@
+"""Scratch profiling: build a -DVRPB200_PHASE_CLOCKS variant of the library and print SM cycles per phase
+(read by warp 2 lane 0 of every CTA with clock64, summed over CTAs)."""
+import ctypes as C, importlib, os, subprocess, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = importlib.import_module("mit_rl-vrptw_b200")
+L = pkg._lib
+so = os.path.join(ROOT, "gpurun_out", "libvrpb200_clk.so")
+os.makedirs(os.path.dirname(so), exist_ok=True)
+subprocess.run(["/usr/local/cuda/bin/nvcc"] + L.NVCC_FLAGS + ["-DVRPB200_PHASE_CLOCKS", "-o", so, os.path.join(L.CSRC, "vrpb200_api.cu")], check=True)
+L.LIB_PATH = so
+L._lib = None
+task, B, gemm, rb = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0
+args = pkg.task_specific_params.default_args(task)
+eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
+eng.set_weights(pkg.data.glorot_params(args, 1))
+x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2).astype(np.float32)).cuda()
+eng.rollout(x)
+stats = torch.zeros(16, dtype=torch.int64, device="cuda")
+tr = L.Trace(); tr.d_stats = stats.data_ptr()
+idx = torch.empty((eng.T, B), dtype=torch.int32, device="cuda"); cost = torch.empty(B, device="cuda")
+rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 0, 1, None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
+                             C.c_void_p(cost.data_ptr()), None, None, C.byref(tr), None)
+torch.cuda.synchronize()
+s = stats.cpu().numpy()
+blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
+names = ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"]
+print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
+for n, v in zip(names, s[4:10]):
+    print(f"  {n:30s} {v / blocksteps:10.0f} clk/step")
+print(f"  total {s[4:10].sum() / blocksteps:.0f} clk/step")

@@ -18,6 +18,7 @@ ap.add_argument("--cases", default="vrptw20:4096,vrptw100:18944,vrptw100:131072"
 ap.add_argument("--rb", type=int, default=0)
 ap.add_argument("--mode", default="greedy")
 ap.add_argument("--full", type=int, default=0)
+ap.add_argument("--gemm", default="tc")
 a = ap.parse_args()
 for case in a.cases.split(","):
     task, B = case.split(":")
@@ -28,7 +29,7 @@ for case in a.cases.split(","):
     data = np.tile(base, [(B + len(base) - 1) // len(base), 1, 1])[:B]
     # de-duplicate tiled instances a little so rows are not identical
     x = torch.from_numpy(data).cuda()
-    eng = pkg.Engine(args, rows_per_cta=a.rb)
+    eng = pkg.Engine(args, rows_per_cta=a.rb, gemm=a.gemm)
     eng.set_weights(params)
     for _ in range(2):
         out = eng.rollout(x, a.mode, trace=False, want_steps=True)
