@@ -58,7 +58,9 @@ typedef struct vrpb200_config {
     int32_t mask_glimpses;   /* shared/decode_step.py:222-223 */
     int32_t mask_pointer;    /* shared/decode_step.py:231-232 */
     int32_t rows_per_cta;    /* 0 = choose; else 16/32/48/64 (tuning knob, no effect on results) */
-    int32_t gemm_path;       /* LSTM/query GEMMs of the fused kernel: 0 = tcgen05 (3xTF32 split, TMEM), 1 = FP32 FFMA */
+    int32_t gemm_path;       /* fused kernel variant: 0 = rollout2 (LSTM, query AND pointer scores on tcgen05, 3xTF32 split,
+                                TMEM accumulators), 1 = rollout v1 with FP32-pipe GEMMs, 2 = rollout v1 with tcgen05 LSTM/query
+                                GEMMs.  All three produce the same results up to fp32 rounding. */
     float capacity;
     float tanh_exploration;  /* C */
     float forget_bias;       /* BasicLSTMCell forget_bias, shared/decode_step.py:175 */

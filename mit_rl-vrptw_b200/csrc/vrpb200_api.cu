@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "rollout_kernel.cuh"
+#include "rollout2_kernel.cuh"
 #include "standalone_kernels.cuh"
 
 using namespace vrpb200;
@@ -120,7 +121,7 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path != 0 && c.gemm_path != 1) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (tcgen05) or 1 (ffma)");
+    if (c.gemm_path < 0 || c.gemm_path > 2) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (rollout2), 1 (v1 ffma) or 2 (v1 tcgen05)");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -356,10 +357,22 @@ int launch_rollout_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem
     return 0;
 }
 
+template <int RB, bool TW>
+int launch_rollout2_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout2_kernel<RB, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout2_kernel<RB, TW><<<grid, 512, smem, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
-    const bool tc = c.gemm_path == 0;
+    const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
+    auto smem_of = [&](int rb) {
+        if (v2) return layout2_fits_U(rb, c.n_nodes) ? make_layout2(rb, rb, c.n_nodes, FD).total : (1 << 30);
+        return make_layout(rb, rb, c.n_nodes, FD, tc).total;
+    };
     // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks,
     // else the smallest (more, lighter CTAs for small batches)
     const int cand[4] = {64, 48, 32, 16};
@@ -369,26 +382,28 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     } else {
         for (int i = 0; i < 4 && !RB; ++i) {
             const int rb = cand[i];
-            if (make_layout(rb, rb, c.n_nodes, FD, tc).total > h->max_smem_optin) continue;
+            if (smem_of(rb) > h->max_smem_optin) continue;
             if ((a.B + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
         }
     }
     if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory");
     a.IB = RB / a.W;
-    const SmemLayout L = make_layout(RB, a.IB, c.n_nodes, FD, tc);
-    if (L.total > h->max_smem_optin)
-        return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, L.total, h->max_smem_optin);
+    const int total = smem_of(RB);
+    if (total > h->max_smem_optin)
+        return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, total, h->max_smem_optin);
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
-    h->last_launch[0] = (int)grid; h->last_launch[1] = tc ? 512 : RB * 8; h->last_launch[2] = L.total; h->last_launch[3] = RB;
-    h->last_launch[4] = 1; h->last_launch[5] = tc ? 1 : 0;
+    h->last_launch[0] = (int)grid; h->last_launch[1] = tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
+    h->last_launch[4] = 1; h->last_launch[5] = c.gemm_path;
     int rc = 0;
 #define DISPATCH(rb)                                                                                   \
     case rb:                                                                                           \
-        if (tc) rc = h->tw ? launch_rollout_t<rb, true, true>(h, a, (int)grid, L.total, st)            \
-                           : launch_rollout_t<rb, false, true>(h, a, (int)grid, L.total, st);          \
-        else    rc = h->tw ? launch_rollout_t<rb, true, false>(h, a, (int)grid, L.total, st)           \
-                           : launch_rollout_t<rb, false, false>(h, a, (int)grid, L.total, st);         \
+        if (v2) rc = h->tw ? launch_rollout2_t<rb, true>(h, a, (int)grid, total, st)                   \
+                           : launch_rollout2_t<rb, false>(h, a, (int)grid, total, st);                 \
+        else if (tc) rc = h->tw ? launch_rollout_t<rb, true, true>(h, a, (int)grid, total, st)         \
+                                : launch_rollout_t<rb, false, true>(h, a, (int)grid, total, st);       \
+        else    rc = h->tw ? launch_rollout_t<rb, true, false>(h, a, (int)grid, total, st)             \
+                           : launch_rollout_t<rb, false, false>(h, a, (int)grid, total, st);           \
         break;
     switch (RB) {
         DISPATCH(64) DISPATCH(48) DISPATCH(32) DISPATCH(16)

@@ -11,19 +11,22 @@ params = O.init_params(args, seed=3, bias_scale=0.2)
 data = O.create_dataset(task, B, seed=5)
 x = torch.from_numpy(data.astype(np.float32)).cuda()
 outs = {}
-for gemm in ("ffma", "tc"):
+for gemm in ("ffma", "tc", "tc2"):
     eng = pkg.Engine(args, gemm=gemm)
     eng.set_weights(params)
     o = eng.rollout(x, "greedy", want_logprobs=True, trace=True)
     torch.cuda.synchronize()
     outs[gemm] = o
     print(gemm, "launch", eng.last_launch(), "mean cost", o.R.mean().item(), flush=True)
-a, b = outs["ffma"], outs["tc"]
-same = (a.idxs == b.idxs).all(0)
-print("tc vs ffma identical tours:", same.float().mean().item())
-um = a.masks == 0
-d = (a.logits - b.logits).abs()[um & (b.masks == 0)]
-print("logit diff tc-ffma (unmasked): max", d.max().item(), "mean", d.mean().item())
+a = outs["ffma"]
+for nm in ("tc", "tc2"):
+    b = outs[nm]
+    same = (a.idxs == b.idxs).all(0)
+    print(nm, "vs ffma identical tours:", same.float().mean().item())
+    um = (a.masks == 0) & (b.masks == 0)
+    um[:, ~same] = False
+    d = (a.logits - b.logits).abs()[um]
+    print("  logit diff (unmasked, agreeing rows): max", d.max().item(), "mean", d.mean().item())
 if B <= 512:
     ref = O.rollout(params, args, data, "greedy", keep_probs=True)
     for k, o in outs.items():
