@@ -64,6 +64,9 @@ struct RolloutArgs {
     const float* Wg;         // [17 slabs][8][2][2][32][4]  permuted LSTM kernel (+ folded embedding rows)
     const float* WgTc;       // tcgen05 path: [34 uses][hi 8 KB | lo 8 KB], tiles [N=256][K=8] canonical K-major
     const float* WqTc;       // tcgen05 path: [8 uses][2 k-chunks][hi 4 KB | lo 4 KB], tiles [N=128][K=8]
+    const float* WgT3;       // rollout3: [32 uses][2 gate types][hi 4 KB | lo 4 KB], tiles [128 units][K=8] of W_h^T
+    const float* WxT;        // rollout3: [4 features][4 gate types][128 units]  W_emb . W_lstm[:E]
+    const float* bgT;        // rollout3: [4 gate types][128 units]  b_lstm + b_emb . W_lstm[:E]
     const float* bg;         // [128][4]  gate bias per unit: i, j, f, o (b_lstm + b_emb . W_x)
     AttWeights att;          // pointer attention
     const float* uniforms;   // [T, R] or null

@@ -15,6 +15,7 @@
 
 #include "rollout_kernel.cuh"
 #include "rollout2_kernel.cuh"
+#include "rollout3_kernel.cuh"
 #include "standalone_kernels.cuh"
 
 using namespace vrpb200;
@@ -36,6 +37,7 @@ struct vrpb200_handle {
     const float* Wg = nullptr;
     const float* bg = nullptr;
     const float* WgTc = nullptr;
+    const float *WgT3 = nullptr, *WxT = nullptr, *bgT = nullptr;
     const float* WqTc[8] = {nullptr};
     AttWeights att[8];
     RawModel raw;
@@ -121,7 +123,7 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path < 0 || c.gemm_path > 2) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (rollout2), 1 (v1 ffma) or 2 (v1 tcgen05)");
+    if (c.gemm_path < 0 || c.gemm_path > 3) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..3");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -209,6 +211,7 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     const size_t oWg = reserve((size_t)kGateSlabs * kSlabFloats);
     const size_t obg = reserve(4 * H);
     const size_t oWgTc = reserve((size_t)kTcUsesA * kSlabFloats);
+    const size_t oWgT3 = reserve((size_t)kV3UsesG * kSlabFloats), oWxT = reserve(16 * H), obgT = reserve(4 * H);
     {
         std::vector<double> Wx((size_t)D1 * 4 * H, 0.0), bx(4 * H, 0.0);
         for (int col = 0; col < 4 * H; ++col) {
@@ -236,6 +239,27 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         }
         for (int unit = 0; unit < H; ++unit)
             for (int g = 0; g < 4; ++g) blob[obg + unit * 4 + g] = (float)bx[g * H + unit];
+        // rollout3: transposed tiles of the h part, per (k-chunk, pair of gate types): [128 units][K=8] K-major; plus the
+        // fp32 input part W_x^T [feature][gate type][unit] and bias [gate type][unit]
+        for (int u = 0; u < kV3UsesG; ++u) {
+            const int kc = u >> 1, mp = u & 1;
+            for (int mi = 0; mi < 2; ++mi)
+                for (int unit = 0; unit < H; ++unit)
+                    for (int kl = 0; kl < 8; ++kl) {
+                        const int m = 2 * mp + mi, k = kc * 8 + kl;
+                        const float val = lstm_k[(size_t)(E + k) * 4 * H + m * H + unit];
+                        const float hi = tf32_round(val), lo = tf32_round(val - hi);
+                        const size_t o = (size_t)(unit / 8) * 64 + (kl / 4) * 32 + (unit % 8) * 4 + (kl % 4);
+                        blob[oWgT3 + (size_t)u * kSlabFloats + mi * 2048 + o] = hi;
+                        blob[oWgT3 + (size_t)u * kSlabFloats + mi * 2048 + 1024 + o] = lo;
+                    }
+        }
+        for (int m = 0; m < 4; ++m)
+            for (int unit = 0; unit < H; ++unit) {
+                blob[obgT + m * H + unit] = (float)bx[m * H + unit];
+                for (int cc = 0; cc < 4; ++cc)
+                    blob[oWxT + (cc * 4 + m) * H + unit] = cc < D1 ? (float)Wx[(size_t)cc * 4 * H + m * H + unit] : 0.0f;
+            }
         // tcgen05 path: per (k-chunk, N-half) stage a hi tile and a lo tile, [N=256][K=8] canonical K-major no-swizzle
         // ([n/8][k/4][n%8][k%4]); n = 4*unit_local + gate, unit = 64*half + unit_local
         for (int u = 0; u < kTcUsesA; ++u) {
@@ -323,6 +347,7 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     h->Wg = d + oWg;
     h->bg = d + obg;
     h->WgTc = d + oWgTc;
+    h->WgT3 = d + oWgT3; h->WxT = d + oWxT; h->bgT = d + obgT;
     for (int a = 0; a < natt; ++a) {
         h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
                                d + ao[a].v, d + ao[a].Au, d + ao[a].ce};
@@ -365,11 +390,25 @@ int launch_rollout2_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int sme
     return 0;
 }
 
+template <int RB, bool TW, int STAGES>
+int launch_rollout3_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout3_kernel<RB, TW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout3_kernel<RB, TW, STAGES><<<grid, kV3Threads, smem, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
+    const bool v3 = c.gemm_path == 3;
     const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
+    int stages3 = 2;
     auto smem_of = [&](int rb) {
+        if (v3) {
+            stages3 = make_layout3(rb, rb, c.n_nodes, FD, 3).total <= h->max_smem_optin ? 3 : 2;
+            return make_layout3(rb, rb, c.n_nodes, FD, stages3).total;
+        }
         if (v2) return layout2_fits_U(rb, c.n_nodes) ? make_layout2(rb, rb, c.n_nodes, FD).total : (1 << 30);
         return make_layout(rb, rb, c.n_nodes, FD, tc).total;
     };
@@ -393,12 +432,16 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
         return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, total, h->max_smem_optin);
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
-    h->last_launch[0] = (int)grid; h->last_launch[1] = tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
+    h->last_launch[0] = (int)grid; h->last_launch[1] = v3 ? kV3Threads : tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
     h->last_launch[4] = 1; h->last_launch[5] = c.gemm_path;
     int rc = 0;
 #define DISPATCH(rb)                                                                                   \
     case rb:                                                                                           \
-        if (v2) rc = h->tw ? launch_rollout2_t<rb, true>(h, a, (int)grid, total, st)                   \
+        if (v3) { if (stages3 == 3) rc = h->tw ? launch_rollout3_t<rb, true, 3>(h, a, (int)grid, total, st)    \
+                                               : launch_rollout3_t<rb, false, 3>(h, a, (int)grid, total, st);  \
+                  else rc = h->tw ? launch_rollout3_t<rb, true, 2>(h, a, (int)grid, total, st)                 \
+                                  : launch_rollout3_t<rb, false, 2>(h, a, (int)grid, total, st); }             \
+        else if (v2) rc = h->tw ? launch_rollout2_t<rb, true>(h, a, (int)grid, total, st)                   \
                            : launch_rollout2_t<rb, false>(h, a, (int)grid, total, st);                 \
         else if (tc) rc = h->tw ? launch_rollout_t<rb, true, true>(h, a, (int)grid, total, st)         \
                                 : launch_rollout_t<rb, false, true>(h, a, (int)grid, total, st);       \
@@ -437,6 +480,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     memset(&a, 0, sizeof a);
     a.input = d_input; a.Wg = h->Wg; a.bg = h->bg; a.att = h->att[c.n_glimpses];
     a.WgTc = h->WgTc; a.WqTc = h->WqTc[c.n_glimpses];
+    a.WgT3 = h->WgT3; a.WxT = h->WxT; a.bgT = h->bgT;
     a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
     a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
     if (trace) {

@@ -8,10 +8,12 @@ pkg = importlib.import_module("mit_rl-vrptw_b200")
 L = pkg._lib
 so = os.path.join(ROOT, "gpurun_out", "libvrpb200_clk.so")
 os.makedirs(os.path.dirname(so), exist_ok=True)
-subprocess.run(["/usr/local/cuda/bin/nvcc"] + L.NVCC_FLAGS + ["-DVRPB200_PHASE_CLOCKS", "-o", so, os.path.join(L.CSRC, "vrpb200_api.cu")], check=True)
+subprocess.run(["/usr/local/cuda/bin/nvcc"] + L.NVCC_FLAGS + ["-DVRPB200_PHASE_CLOCKS"] + sys.argv[5:] + ["-o", so, os.path.join(L.CSRC, "vrpb200_api.cu")], check=True)
 L.LIB_PATH = so
 L._lib = None
+_ = 0
 task, B, gemm, rb = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0
+extra = sys.argv[5:]
 args = pkg.task_specific_params.default_args(task)
 eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))

@@ -18,7 +18,7 @@ ap.add_argument("--cases", default="vrptw20:4096,vrptw100:18944,vrptw100:131072"
 ap.add_argument("--rb", type=int, default=0)
 ap.add_argument("--mode", default="greedy")
 ap.add_argument("--full", type=int, default=0)
-ap.add_argument("--gemm", default="tc2")
+ap.add_argument("--gemm", default="tc3")
 a = ap.parse_args()
 for case in a.cases.split(","):
     task, B = case.split(":")

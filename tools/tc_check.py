@@ -11,7 +11,7 @@ params = O.init_params(args, seed=3, bias_scale=0.2)
 data = O.create_dataset(task, B, seed=5)
 x = torch.from_numpy(data.astype(np.float32)).cuda()
 outs = {}
-for gemm in ("ffma", "tc", "tc2"):
+for gemm in ("ffma", "tc2", "tc3"):
     eng = pkg.Engine(args, gemm=gemm)
     eng.set_weights(params)
     o = eng.rollout(x, "greedy", want_logprobs=True, trace=True)
@@ -19,7 +19,7 @@ for gemm in ("ffma", "tc", "tc2"):
     outs[gemm] = o
     print(gemm, "launch", eng.last_launch(), "mean cost", o.R.mean().item(), flush=True)
 a = outs["ffma"]
-for nm in ("tc", "tc2"):
+for nm in ("tc2", "tc3"):
     b = outs[nm]
     same = (a.idxs == b.idxs).all(0)
     print(nm, "vs ffma identical tours:", same.float().mean().item())
