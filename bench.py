@@ -15,7 +15,7 @@ value   : whole-job instances/s, inputs resident in HBM, CUDA events, max over r
 e2e     : the same through the host entry point of the C ABI (vrpb200_rollout_host): pinned host input,
           chunked H2D / decode / D2H of costs and tours inside the timed region.
 roofline: the path is neither HBM- nor tensor-bound (2.7 KB of HBM traffic per instance against ~50 MFLOP and
-          ~2 M transcendentals): the binding unit is an SM pipe (FP32 FMA or MUFU).  Pipe peaks are measured
+          ~2 M transcendentals): the binding unit is an SM pipe (MUFU for the tanh grid; FP32 for the FFMA variant).  Pipe peaks are measured
           live with the library's register-only micro-benchmarks; the HBM line uses MEASURED_PEAKS.json.
 cpu_baseline / --impl reference: TensorFlow is not installable in this image and the reference is TF-1 graph
           code, so the CPU arm is the numpy restatement of the reference graph (oracle/, checked against
@@ -58,6 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-cta", type=int, default=0)
+    ap.add_argument("--kernel", default="tc3", choices=["tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout3)")
     return ap.parse_args()
 
 
@@ -189,7 +190,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    eng = pkg.Engine(args, device=local_rank, rows_per_cta=a.rows_per_cta)
+    eng = pkg.Engine(args, device=local_rank, rows_per_cta=a.rows_per_cta, gemm=a.kernel)
     eng.set_weights(pkg.data.glorot_params(args, seed=1234))
     x_host = torch.from_numpy(make_instances(pkg, task, ups, Bg, seed=1000 + rank)).pin_memory()
     x_dev = x_host.cuda(non_blocking=False)
@@ -259,34 +260,49 @@ def main():
         H = args["hidden_dim"]
         ms_step = ms_total / a.steps
         sec_step = ms_step * 1e-3
+        # executed work of one launch, from the kernel's own counters:
+        #   node_evals     (row, node) pairs whose 128 tanh terms were evaluated
+        #   gemm_rowsteps  rows x executed steps that went through the LSTM + query GEMMs
         mufu_ops = 2.0 * H * node_evals + 10.0 * H * gemm_rowsteps + 3.0 * node_evals   # tanh grid, LSTM gates, softmax exp
-        fp32_ops = 8.0 * H * node_evals + (136 * 512 + 128 * 128) * gemm_rowsteps       # FP32-pipe lane ops (FMA counted once)
+        gemm_macs = (128 * 512 + 128 * 128 + 4 * 512) * gemm_rowsteps                    # h.W_h, h'.W_q, x.W_x
+        score_macs = 5.0 * H * node_evals                                                # feat.A + demand.g  (K = 5)
+        if a.kernel == "ffma":
+            fp32_ops = 8.0 * H * node_evals + gemm_macs                                  # everything on the FP32 pipe
+            tensor_flops = 0.0
+        elif a.kernel == "tc":
+            fp32_ops = 8.0 * H * node_evals + 30.0 * H * gemm_rowsteps
+            tensor_flops = 3 * 2.0 * gemm_macs                                           # 3xTF32 split
+        else:
+            fp32_ops = 4.0 * H * node_evals + 46.0 * H * gemm_rowsteps                   # tanh/dot epilogue; LSTM epilogue + x part
+            tensor_flops = 3 * 2.0 * (gemm_macs + score_macs * 8.0 / 5.0)                # K padded to 8 for the scores
         hbm_bytes = Bg * (N * D * 4 + T * 4 + 4)
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        hbm_peak, hbm_src, tc_peak = 6650.0, "fallback (B200_PROFILING.md)", 1590.0
         if os.path.exists(peaks_path):
             with open(peaks_path) as f:
-                hbm_peak, hbm_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json"
+                mp = json.load(f)
+                hbm_peak, hbm_src, tc_peak = float(mp["hbm_gbs"]), "MEASURED_PEAKS.json", float(mp.get("bf16_tflops", 1590.0))
         mufu_peak = eng.pipe_peak("mufu")
         fma_peak = eng.pipe_peak("fma")
         pipes = {
             "mufu": {"achieved": mufu_ops / sec_step / 1e9, "peak": mufu_peak / 1e9, "unit": "Gop/s"},
             "fp32": {"achieved": fp32_ops / sec_step / 1e9, "peak": fma_peak / 1e9, "unit": "Gop/s (FMA = 1 op)"},
             "hbm": {"achieved": hbm_bytes / sec_step / 1e9, "peak": hbm_peak, "unit": "GB/s", "peak_source": hbm_src},
-            "tensor": {"achieved": 0.0, "peak": None, "unit": "TFLOP/s", "note": "phase A/B GEMMs run on the FP32 pipe in this round"},
+            "tensor": {"achieved": tensor_flops / sec_step / 1e12, "peak": tc_peak / 2.0, "unit": "TFLOP/s",
+                       "note": "kind::tf32 issued flops incl. the 3x split; peak = half the measured bf16 peak (TF32 runs at half the bf16 rate)"},
         }
         for p in pipes.values():
             p["frac"] = (p["achieved"] / p["peak"]) if p["peak"] else 0.0
-        bound = max(("mufu", "fp32", "hbm"), key=lambda k: pipes[k]["frac"])
+        bound = max(("mufu", "fp32", "hbm", "tensor"), key=lambda k: pipes[k]["frac"])
         roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
                     "frac": pipes[bound]["frac"], "traffic": None,
                     "peak_source": "pipe peaks measured live by vrpb200_pipe_peak (register-only micro-benchmark on all SMs); "
                                    "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks and neither binds this path",
                     "work_per_launch": {"node_evaluations": node_evals, "live_row_steps": live_rowsteps, "gemm_row_steps": gemm_rowsteps,
                                         "blocks": blocks, "mean_steps_per_block": float(st.steps.float().mean().item()),
-                                        "mufu_ops": mufu_ops, "fp32_lane_ops": fp32_ops, "hbm_bytes": hbm_bytes},
+                                        "mufu_ops": mufu_ops, "fp32_lane_ops": fp32_ops, "tensor_flops": tensor_flops, "hbm_bytes": hbm_bytes},
                     "pipes": pipes,
-                    "kernel": f"rollout_kernel<{launch['rows_per_cta']},TW> grid {launch['grid']} x {launch['block']} thr, {launch['smem']} B smem, "
+                    "kernel": f"{ {'tc3': 'rollout3_kernel', 'tc2': 'rollout2_kernel'}.get(a.kernel, 'rollout_kernel') }<{launch['rows_per_cta']},TW> ({a.kernel}) grid {launch['grid']} x {launch['block']} thr, {launch['smem']} B smem, "
                               f"1 launch per step, {ms_step:.3f} ms per launch (CUDA events)"}
         # profiles/ holds the ncu capture of the same kernel; dram bytes per launch from it if present
         tr_path = os.path.join(ROOT, "profiles", "traffic.json")

@@ -678,7 +678,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     if (tid == 0 && a.steps_out) a.steps_out[blockIdx.x] = t_end;
     if (a.stats) {
         atomicAdd(a.stats + 0, n_eval);
-        if (lane == 0) atomicAdd(a.stats + 1, n_rowsteps);
+        if (n_rowsteps) atomicAdd(a.stats + 1, n_rowsteps);   // counted by the first lane of every row
         if (tid == 0) {
             atomicAdd(a.stats + 2, (unsigned long long)t_end * RB);
             atomicAdd(a.stats + 3, 1ull);
