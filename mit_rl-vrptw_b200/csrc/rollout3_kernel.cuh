@@ -45,7 +45,7 @@ __host__ __device__ inline Smem3 make_layout3(int RB, int IB, int N, int FD, int
     L.dem = off;    off += RB * NP * 4;
     L.mask = off;   off += align_up(RB * NP, 16);
     L.rs = off;     off += RB * kRowState * 4;
-    L.meta = off;   off += align_up((2 * RB + 32) * 4, 16);
+    L.meta = off;   off += align_up((6 * RB + 32) * 4, 16);   // nact, flags, beam: sel_idx, sel_par, sel_lp, prevlog; done[16], stop
     L.bar = off;    off += 192;
     L.total = off;
     return L;
@@ -111,7 +111,11 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     float* rowst = reinterpret_cast<float*>(smem + L.rs);
     int* nact_s = reinterpret_cast<int*>(smem + L.meta);
     int* flag_s = nact_s + RB;
-    int* done_s = flag_s + RB;                                // [16] per-warp "all my rows are finished"
+    int* sel_idx_s = flag_s + RB;                             // beam search: choice of every new beam row
+    int* sel_par_s = sel_idx_s + RB;
+    float* sel_lp_s = reinterpret_cast<float*>(sel_par_s + RB);
+    float* prevlog_s = sel_lp_s + RB;                         // log-probability of the beam so far
+    int* done_s = reinterpret_cast<int*>(prevlog_s + RB);     // [16] per-warp "all my rows are finished"
     volatile int* stop_s = done_s + 16;
     const uint32_t bar0 = smem_u32(smem + L.bar);            // full[0..3] at +0, empty[0..3] at +32
     const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, bar_grp = bar0 + 88,
@@ -492,7 +496,179 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
         // This part is a long dependent chain per row (reductions, exp/log, sqrt): LPR lanes per row (8, 16 or 32 - every compute warp busy),
         // every row of the block in flight at once; lane sl owns nodes sl, sl+LPR, ...
         int warp_done;
-        {
+        if (a.mode == 2) {
+            // ---------- beam search (model/attention_agent.py:169-205): rows of one instance compete ----------
+            const int sub = lane / LPR, sl = lane % LPR;
+            const int lr = warp * (32 / LPR) + sub;
+            const int wb = lr / IB, lb = lr - wb * IB;
+            const bool rvalid = lr < RB && wb < W && lb < IBv;
+            const int lrs = rvalid ? lr : 0, lbs = rvalid ? lb : 0;
+            float* rs = rowst + lrs * kRowState;
+            const long long row = (long long)wb * a.B + b0 + lb;
+            const bool was_done = rvalid && reinterpret_cast<int*>(rs)[8] != 0;
+            const bool live = rvalid && !was_done;
+            if (live && sl == 0) ++n_rowsteps;
+            float* ulog = logits + lrs * NP;
+            const float* frow = feat + (size_t)lbs * N * FD;
+            {   // (a) every row: log(prob[n]) for all nodes, in place of the logits (finished rows: depot with prob 1)
+                unsigned char* mk = maskb + lrs * NP;
+                const int fl = flag_s[lrs];
+                float lg[NPL];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const int n = sl + LPR * j;
+                    float u = -INFINITY;
+                    if (n < N && live) {
+                        const int m = mk[n];
+                        if (fl || m == 0) {
+                            u = ulog[n];
+                            if (a.use_tanh) u = a.tanh_C * tanhf(u);
+                            if (a.mask_pointer) u = __fsub_rn(u, __fmul_rn(kBig, (float)m));
+                        }
+                    }
+                    if (n == n_cust && was_done) u = 0.0f;
+                    lg[j] = u;
+                    mx = fmaxf(mx, u);
+                }
+#pragma unroll
+                for (int o = LPR / 2; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+                float se = 0.0f;
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) se += (lg[j] == -INFINITY) ? 0.0f : expf(lg[j] - mx);
+#pragma unroll
+                for (int o = LPR / 2; o; o >>= 1) se += __shfl_xor_sync(kFull, se, o);
+                const float lse = logf(se);
+                const bool tracing = a.tr_logits || a.tr_probs || a.tr_masks;
+                const long long tro = ((long long)t * R + row) * N;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const int n = sl + LPR * j;
+                    const float p = (lg[j] == -INFINITY) ? 0.0f : expf((lg[j] - mx) - lse);
+                    if (n < N && rvalid) {
+                        ulog[n] = logf(p);      // tf.log(prob): -inf for masked nodes
+                        if (tracing && live) {
+                            if (a.tr_logits) a.tr_logits[tro + n] = lg[j];
+                            if (a.tr_probs) a.tr_probs[tro + n] = p;
+                            if (a.tr_masks) a.tr_masks[tro + n] = (float)mk[n];
+                        }
+                    }
+                }
+            }
+            named_bar(5, NT);
+            // (b) per instance (one warp): W times the best (log-prob so far + log prob) over W x N candidates;
+            //     ties -> lower flat index (tf.nn.top_k); chosen entries are struck out with NaN
+            for (int ib = warp; ib < IBv; ib += 16) {
+                const int wc = (t == 0) ? 1 : W;       // step 0: every beam is a copy of beam 0 (attention_agent.py:171)
+                const int ncand = wc * N;
+                for (int k = 0; k < W; ++k) {
+                    float bv = -INFINITY;
+                    int bc = 0x7fffffff;
+                    for (int c = lane; c < ncand; c += 32) {
+                        const int w = c / N, n = c - w * N;
+                        float v = logits[(w * IB + ib) * NP + n];
+                        if (t > 0) v = __fadd_rn(v, prevlog_s[w * IB + ib]);
+                        if (v > bv || (v == bv && c < bc)) { bv = v; bc = c; }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, bv, o);
+                        const int oc = __shfl_xor_sync(kFull, bc, o);
+                        if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+                    }
+                    if (bc == 0x7fffffff) bc = 0;      // cannot happen (candidates are never all NaN), keeps indices in range
+                    const int w = bc / N, n = bc - w * N;
+                    if (lane == 0) {
+                        const int nr = k * IB + ib;
+                        float* cell = logits + (w * IB + ib) * NP + n;
+                        sel_idx_s[nr] = n;
+                        sel_par_s[nr] = w;
+                        sel_lp_s[nr] = *cell;
+                        *reinterpret_cast<volatile float*>(cell) = __int_as_float(0x7fc00000);
+                        reinterpret_cast<float*>(ftile)[nr] = bv; // new log-probability of beam nr, staged
+                    }
+                    __syncwarp();
+                }
+            }
+            named_bar(5, NT);
+            // (c) gather the parent's environment state into scratch (the F tiles are idle now)
+            const int SS = NP * 4 + align_up(NP, 4) + kRowState * 4;
+            unsigned char* scratch = ftile + 1024 + lrs * SS;
+            float* sdem = reinterpret_cast<float*>(scratch);
+            unsigned char* smk = scratch + NP * 4;
+            float* srs = reinterpret_cast<float*>(scratch + NP * 4 + align_up(NP, 4));
+            const int idx = rvalid ? sel_idx_s[lrs] : 0;
+            const int par = rvalid ? sel_par_s[lrs] : 0;
+            if (rvalid) {   // (rows without an instance alias row 0 for addressing only and must not write)
+                const int pr = par * IB + lbs;
+                for (int n = sl; n < N; n += LPR) {
+                    sdem[n] = dem[pr * NP + n];
+                    smk[n] = maskb[pr * NP + n];
+                }
+                if (sl < kRowState) srs[sl] = rowst[pr * kRowState + sl];
+                if (LPR < kRowState && sl + LPR < kRowState) srs[sl + LPR] = rowst[pr * kRowState + sl + LPR];
+            }
+            named_bar(5, NT);
+            // (d) Env.step on the gathered state (vrptw_utils.py:262-348); LSTM state stays with the slot
+            {
+                const bool p_done = reinterpret_cast<const int*>(srs)[8] != 0;
+                const float load = srs[0], time = TW ? srs[1] : 0.0f;
+                const float* fsel = frow + idx * FD;
+                const float sx = fsel[0], sy = fsel[1];
+                const float px = srs[2], py = srs[3];
+                const float d_idx = sdem[idx];
+                const float d_sat = fminf(d_idx, load);
+                float nload = __fsub_rn(load, d_sat);
+                const float ts = dist_rn(px, py, sx, sy);
+                float ntime = 0.0f;
+                if (TW) ntime = fmaxf(__fadd_rn(time, ts), fsel[2]);
+                const float dep = (idx == n_cust) ? 1.0f : 0.0f;
+                nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
+                if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
+                float sumdem = 0.0f;
+                float dn[NPL];
+#pragma unroll
+                for (int j = 0; j < NPL; ++j) {
+                    const int n = sl + LPR * j;
+                    dn[j] = (n < N) ? sdem[n] : 0.0f;
+                    if (n == idx) dn[j] = __fsub_rn(dn[j], d_sat);
+                    sumdem += dn[j];
+                }
+#pragma unroll
+                for (int o = LPR / 2; o; o >>= 1) sumdem += __shfl_xor_sync(kFull, sumdem, o);
+                if (rvalid) {
+#pragma unroll
+                    for (int j = 0; j < NPL; ++j) {
+                        const int n = sl + LPR * j;
+                        if (n < N) {
+                            float nx = 0.f, ny = 0.f, ne = 0.f;
+                            if (TW) {
+                                const float4 f4 = *reinterpret_cast<const float4*>(frow + n * 4);
+                                nx = f4.x; ny = f4.y; ne = f4.w;
+                            }
+                            dem[lr * NP + n] = dn[j];
+                            maskb[lr * NP + n] =
+                                (unsigned char)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem);
+                        }
+                    }
+                }
+                const int done_now = (!a.full && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
+                if (rvalid && sl == 0) {
+                    rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
+                    if (t == 0) { rs[4] = 0.0f; rs[5] = sx; rs[6] = sy; }
+                    else { rs[4] = __fadd_rn(srs[4], ts); rs[5] = srs[5]; rs[6] = srs[6]; }
+                    reinterpret_cast<int*>(rs)[8] = done_now;
+                    rs[9] = sx; rs[10] = sy; rs[11] = TW ? fsel[2] : 0.0f; rs[12] = TW ? fsel[FD - 1] : 0.0f;
+                    prevlog_s[lr] = reinterpret_cast<float*>(ftile)[lr];
+                    a.idx_out[(long long)t * R + row] = idx;
+                    if (a.parent_out) a.parent_out[(long long)t * R + row] = par;
+                    if (a.logprob_out) a.logprob_out[(long long)t * R + row] = sel_lp_s[lr];
+                }
+                (void)p_done;
+                warp_done = __all_sync(kFull, !rvalid || done_now);
+            }
+        } else {
             const int sub = lane / LPR, sl = lane % LPR;
             const int lr = warp * (32 / LPR) + sub;
             const int wb = lr / IB, lb = lr - wb * IB;
@@ -663,6 +839,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
         for (int tt = t_end + lane; tt < T; tt += 32) {
             a.idx_out[(long long)tt * R + row] = n_cust;
             if (a.logprob_out) a.logprob_out[(long long)tt * R + row] = 0.0f;
+            if (a.parent_out) a.parent_out[(long long)tt * R + row] = wb;   // finished beams keep their order
         }
         const float* rs = rowst + lr * kRowState;
         if (lane == 0) a.cost_out[row] = __fadd_rn(rs[4], dist_rn(rs[2], rs[3], rs[5], rs[6]));

@@ -74,6 +74,7 @@ struct RolloutArgs {
     int32_t* idx_out;        // [T, R]
     float* cost_out;         // [R]
     float* logprob_out;      // [T, R] or null
+    int32_t* parent_out;     // [T, R] or null (beam search)
     float* tr_logits;        // traces, any may be null
     float* tr_probs;
     float* tr_masks;
@@ -89,7 +90,7 @@ struct RolloutArgs {
     int W;                   // beams per instance (1 unless beam search)
     int IB;                  // instances per CTA
     int N, n_cust, D, T;
-    int mode;                // 0 greedy, 1 stochastic
+    int mode;                // 0 greedy, 1 stochastic, 2 beam search (rollout3 only)
     int full;                // evaluate every node every step, never exit early (trace mode)
     int use_tanh, mask_pointer;
     float capacity, tanh_C, forget_bias;

@@ -406,8 +406,11 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     int stages3 = 2;
     auto smem_of = [&](int rb) {
         if (v3) {
-            stages3 = make_layout3(rb, rb, c.n_nodes, FD, 3).total <= h->max_smem_optin ? 3 : 2;
-            return make_layout3(rb, rb, c.n_nodes, FD, stages3).total;
+            if (rb < a.W) return 1 << 30;                       // every beam of an instance lives in one CTA
+            const int ib = rb / a.W, np = (c.n_nodes + 3) / 4 * 4;
+            if (a.W > 1 && 1024 + rb * (np * 4 + np + kRowState * 4) > 8 * kC1TileBytes) return 1 << 30;   // beam gather scratch
+            stages3 = make_layout3(rb, ib, c.n_nodes, FD, 3).total <= h->max_smem_optin ? 3 : 2;
+            return make_layout3(rb, ib, c.n_nodes, FD, stages3).total;
         }
         if (v2) return layout2_fits_U(rb, c.n_nodes) ? make_layout2(rb, rb, c.n_nodes, FD).total : (1 << 30);
         return make_layout(rb, rb, c.n_nodes, FD, tc).total;
@@ -422,7 +425,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
         for (int i = 0; i < 4 && !RB; ++i) {
             const int rb = cand[i];
             if (smem_of(rb) > h->max_smem_optin) continue;
-            if ((a.B + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
+            if ((a.B * a.W + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
         }
     }
     if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory");
@@ -469,9 +472,10 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     if (!d_input || !d_cost || !d_idx) return fail(h, VRPB200_E_ARG, "d_input, d_idx and d_cost are required");
     if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
     if (mode != VRPB200_GREEDY && mode != VRPB200_STOCHASTIC && mode != VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "bad mode %d", mode);
-    if (mode == VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "beam search is not implemented by the fused kernel yet");
+    if (mode == VRPB200_BEAM && h->cfg.gemm_path != 3) return fail(h, VRPB200_E_ARG, "beam search needs the rollout3 kernel (gemm_path 3)");
+    if (mode == VRPB200_BEAM && (beam_width < 1 || beam_width > 64)) return fail(h, VRPB200_E_ARG, "beam_width outside [1,64]");
+    if (mode == VRPB200_BEAM && trace && (trace->d_logits || trace->d_probs || trace->d_masks) && false) return VRPB200_E_ARG;
     if (h->cfg.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "n_glimpses > 0 is not implemented by the fused kernel yet (use decode_step)");
-    (void)d_beam_parent; (void)beam_width;
     if (mode == VRPB200_STOCHASTIC && ((d_uniforms == nullptr) != (d_uniforms_retry == nullptr)))
         return fail(h, VRPB200_E_ARG, "pass both uniform buffers or neither");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -483,6 +487,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.WgT3 = h->WgT3; a.WxT = h->WxT; a.bgT = h->bgT;
     a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
     a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
+    a.parent_out = mode == VRPB200_BEAM ? d_beam_parent : nullptr;
     if (trace) {
         a.tr_logits = trace->d_logits; a.tr_probs = trace->d_probs; a.tr_masks = trace->d_masks;
         a.fin_demand = trace->d_final_demand; a.fin_load = trace->d_final_load; a.fin_time = trace->d_final_time;
@@ -490,7 +495,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
         a.stats = (unsigned long long*)trace->d_stats;
     }
     a.full = (a.tr_logits || a.tr_probs || a.tr_masks) ? 1 : 0;
-    a.seed = seed; a.B = B; a.row_base = row_base; a.W = 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
+    a.seed = seed; a.B = B; a.row_base = row_base; a.W = mode == VRPB200_BEAM ? beam_width : 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
     a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
     return launch_rollout(h, a, (cudaStream_t)stream);

@@ -44,6 +44,7 @@ class RolloutOutput:
     final_time: Optional[torch.Tensor] = None
     final_mask: Optional[torch.Tensor] = None
     steps: Optional[torch.Tensor] = None     # [grid] int32 decode steps executed per instance block
+    beam_parents: Optional[torch.Tensor] = None   # [T, R] int32 (beam search)
     stats: Optional[torch.Tensor] = None     # [4] int64 work counters: node evals, live row-steps, block-steps*rows, blocks
 
 
@@ -133,7 +134,7 @@ class Engine:
             tr.d_final_demand, tr.d_final_mask = out.final_demand.data_ptr(), out.final_mask.data_ptr()
             tr.d_final_load, tr.d_final_time = out.final_load.data_ptr(), out.final_time.data_ptr()
         if want_steps:
-            out.steps = torch.zeros(((B + 15) // 16,), dtype=torch.int32, device=dev)   # upper bound on the grid
+            out.steps = torch.zeros((B + 1,), dtype=torch.int32, device=dev)   # upper bound on the grid
             tr.d_steps = out.steps.data_ptr()
         if want_stats:
             out.stats = torch.zeros((4,), dtype=torch.int64, device=dev)
@@ -143,9 +144,11 @@ class Engine:
             u1, u2 = self._f32(uniforms, "uniforms"), self._f32(uniforms_retry, "uniforms_retry")
             if tuple(u1.shape) != (self.T, R) or tuple(u2.shape) != (self.T, R):
                 raise VrpB200Error(f"uniforms must be [{self.T},{R}]")
+        if mode == _lib.BEAM:
+            out.beam_parents = torch.empty((self.T, R), dtype=torch.int32, device=dev)
         self._check(self.lib.vrpb200_rollout(
             self.handle, _ptr(x), B, mode, W, _ptr(u1), _ptr(u2), C.c_uint64(seed), _ptr(idx), _ptr(cost),
-            _ptr(out.logprobs), None, C.byref(tr), self._stream()), "rollout")
+            _ptr(out.logprobs), _ptr(out.beam_parents), C.byref(tr), self._stream()), "rollout")
         if want_steps:
             out.steps = out.steps[: self.last_launch()["grid"]]
         return out

@@ -539,18 +539,31 @@ class RLAgent(object):
         loop over RNNDecodeStep.step / Env.step on device state (beam search and glimpses take this route in this
         round), 'auto' picks."""
         import torch
-        fused_ok = decode_type in ("greedy", "stochastic") and self.args['n_glimpses'] == 0 and not want_probs
+        fused_ok = decode_type in ("greedy", "stochastic", "beam_search") and self.args['n_glimpses'] == 0 and not want_probs
         if backend == "auto":
             backend = "fused" if fused_ok else "stepwise"
         if backend == "fused":
             if not fused_ok:
-                raise NotImplementedError("fused kernel: greedy/stochastic without glimpses")
-            out = self.engine().rollout(self.env.input_data, decode_type, uniforms=uniforms, uniforms_retry=uniforms_retry,
-                                        seed=seed, want_logprobs=True)
+                raise NotImplementedError("fused kernel: greedy / stochastic / beam search without glimpses")
+            W = self.args['beam_width'] if decode_type == 'beam_search' else 1
+            self.beam_width = W
+            out = self.engine().rollout(self.env.input_data, decode_type, beam_width=W, uniforms=uniforms,
+                                        uniforms_retry=uniforms_retry, seed=seed, want_logprobs=True)
             idx = out.idxs.long()                                      # [T, R]
             T, R = idx.shape
             pnt = self.env.input_pnt                                    # [B, N, D-1]
-            actions = pnt[torch.arange(R, device=idx.device)[None, :].expand(T, R), idx]   # [T, R, D-1]
+            B = pnt.shape[0]
+            inst = torch.arange(R, device=idx.device) % B               # instance of beam-major row w*B + b
+            actions = pnt[inst[None, :].expand(T, R), idx]              # [T, R, D-1]
+            if decode_type == 'beam_search':                            # back-tracking, attention_agent.py:222-231
+                par = out.beam_parents.long()
+                self.last_beam_path = [p[:, None] for p in par]
+                ind = torch.arange(R, device=idx.device)
+                bt = [None] * T
+                for k in reversed(range(T)):
+                    bt[k] = actions[k][ind]
+                    ind = (inst + B * par[k])[ind]
+                actions = torch.stack(bt)
             v = torch.zeros((), device=idx.device)
             return (out.R, v, list(out.logprobs), list(actions), [i[:, None] for i in idx], pnt, None)
         return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs)
