@@ -41,7 +41,8 @@ __host__ __device__ inline Smem3 make_layout3(int RB, int IB, int N, int FD, int
     L.items = off;  off += align_up(RB * NP * 2, 16);
     L.bc = off;     off += 2 * 4096;
     L.vsm = off;    off += 512;
-    L.feat = off;   off += align_up(IB * N * FD * 4, 16);
+    L.feat = off;   // node features stay in global memory (L2-resident, read-only): the space buys more rows per CTA
+    (void)IB; (void)FD;
     L.dem = off;    off += RB * NP * 4;
     L.mask = off;   off += align_up(RB * NP, 16);
     L.rs = off;     off += RB * kRowState * 4;
@@ -90,6 +91,32 @@ VRP_DEVINL void transpose4(float (&a)[4], int lane) {
     }
 }
 
+// sum_n exp(logit[n] - max) of one row held by LPR lanes (lane sl owns nodes sl + LPR j), added in ONE fixed order
+// whatever LPR is - the order a full warp would use (node n -> lane n % 32, slots n / 32 in sequence, then the xor
+// butterfly 16, 8, 4, 2, 1) - so that the choice of rows per CTA can never move a near-tie.
+template <int LPR>
+VRP_DEVINL float softmax_denominator(const float (&lg)[128 / LPR], float mx) {
+    constexpr int NQ = 32 / LPR;
+    float P[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        float acc = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float u = lg[q + NQ * k];
+            acc = __fadd_rn(acc, (u == -INFINITY) ? 0.0f : expf(u - mx));
+        }
+        P[q] = acc;
+    }
+    float se;
+    if (NQ == 4) se = __fadd_rn(__fadd_rn(P[0], P[2 % NQ]), __fadd_rn(P[1 % NQ], P[3 % NQ]));
+    else if (NQ == 2) se = __fadd_rn(P[0], P[1 % NQ]);
+    else se = P[0];
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
+    return se;
+}
+
 template <int RB, bool TW, int STAGES>
 __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutArgs a) {
     constexpr int NT = 512, RPW = RB / 16, RPT = RB / 4, FD = TW ? 4 : 2;
@@ -105,7 +132,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     float* logits = reinterpret_cast<float*>(smem + L.logits);
     unsigned short* items = reinterpret_cast<unsigned short*>(smem + L.items);
     float* vsm = reinterpret_cast<float*>(smem + L.vsm);
-    float* feat = reinterpret_cast<float*>(smem + L.feat);
     float* dem = reinterpret_cast<float*>(smem + L.dem);
     unsigned char* maskb = smem + L.mask;
     float* rowst = reinterpret_cast<float*>(smem + L.rs);
@@ -128,6 +154,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     const long long b0 = (long long)blockIdx.x * IB;
     const int IBv = (int)min((long long)IB, a.B - b0);
     const long long R = a.B * W;
+    const int D = a.D;
+    const float* gfeat = a.input + b0 * (long long)N * D;      // [instance of this block][node][x, y, (b_tw, e_tw,) demand]
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -153,8 +181,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     for (int i = tid; i < IBv * N; i += kV3Threads) {
         const int lb = i / N, n = i - lb * N;
         const float* src = a.input + ((b0 + lb) * N + n) * a.D;
-        if (TW) reinterpret_cast<float4*>(feat)[i] = make_float4(src[0], src[1], src[2], src[3]);
-        else reinterpret_cast<float2*>(feat)[i] = make_float2(src[0], src[1]);
         const float d = src[a.D - 1];
         for (int w = 0; w < W; ++w) dem[(w * IB + lb) * NP + n] = d;
     }
@@ -247,12 +273,13 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
         const int lr = warp * RPW + i, wb = lr / IB, lb = lr - wb * IB;
         if (wb >= W || lb >= IBv) continue;
         for (int n = lane; n < N; n += 32) maskb[lr * NP + n] = (n == n_cust) ? 1 : (dem[lr * NP + n] == 0.0f ? 1 : 0);
-        const float* fdep = feat + (size_t)(lb * N + n_cust) * FD;
+        const float* fdep = gfeat + (size_t)(lb * N + n_cust) * D;
         if (lane == 0) {
             float* rs = rowst + lr * kRowState;
-            rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = fdep[0]; rs[3] = fdep[1]; rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
+            rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = __ldcg(fdep + 0); rs[3] = __ldcg(fdep + 1); rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
             reinterpret_cast<int*>(rs)[8] = 0;
-            rs[9] = fdep[0]; rs[10] = fdep[1]; rs[11] = TW ? fdep[2] : 0.0f; rs[12] = TW ? fdep[FD - 1] : 0.0f;
+            reinterpret_cast<int*>(rs)[14] = 0;
+            rs[9] = __ldcg(fdep + 0); rs[10] = __ldcg(fdep + 1); rs[11] = TW ? __ldcg(fdep + 2) : 0.0f; rs[12] = TW ? __ldcg(fdep + 3) : 0.0f;
         }
     }
     const int unit = 32 * sp + lane;                           // this thread's hidden unit in the LSTM / query epilogues
@@ -260,6 +287,37 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
 #pragma unroll
     for (int r = 0; r < RPT; ++r) cst[r] = 0.0f;
     named_bar(5, NT);
+
+    // Env mask of the rows that moved in the previous step (vrptw_utils.py:328-348).  It is not needed before the item
+    // list of the next step, so it runs after the LSTM epilogue has released the query GEMM: its L2 feature reads and
+    // square roots hide behind the wait for q instead of sitting on the critical path of the choice.
+    auto update_masks = [&]() {
+        const int sub = lane / LPR, sl = lane % LPR;
+        const int lr = warp * (32 / LPR) + sub;
+        const int wb = lr / IB, lb = lr - wb * IB;
+        const bool rvalid = lr < RB && wb < W && lb < IBv;
+        const int lrs = rvalid ? lr : 0, lbs = rvalid ? lb : 0;
+        float* rs = rowst + lrs * kRowState;
+        const bool dirty = rvalid && reinterpret_cast<const int*>(rs)[14] != 0;
+        const float nload = rs[0], ntime = rs[1], sx = rs[2], sy = rs[3], sumdem = rs[13], dep = rs[15];
+        const float* frow = gfeat + (size_t)lbs * N * D;
+        const float* drow = dem + lrs * NP;
+        unsigned char* mk = maskb + lrs * NP;
+        __syncwarp();
+        if (dirty) {
+#pragma unroll
+            for (int j = 0; j < NPL; ++j) {
+                const int n = sl + LPR * j;
+                const int nn = n < N ? n : N - 1;
+                float nx = 0.f, ny = 0.f, ne = 0.f;
+                if (TW) { nx = __ldcg(frow + nn * D); ny = __ldcg(frow + nn * D + 1); ne = __ldcg(frow + nn * D + 3); }
+                const int m = node_mask<TW>(nn, n_cust, drow[nn], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem);
+                if (n < N) mk[n] = (unsigned char)m;
+            }
+            if (sl == 0) reinterpret_cast<int*>(rs)[14] = 0;
+        }
+        __syncwarp();
+    };
 
 #ifdef VRPB200_PHASE_CLOCKS
     long long pc_[6] = {0, 0, 0, 0, 0, 0}, pc_last_ = clock64();
@@ -326,6 +384,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             named_bar(5, NT);
             if (tid == 0) mbar_arrive(bar_x);      // h' is in place: the streaming warp may issue q(t) and gates(t+1)
         }
+        update_masks();   // masks of the previous step's moves, hidden behind the query GEMM
+        named_bar(5, NT); // (the item list below reads masks written by other warps)
         VRP_CLK(1);
         // ================= C0: item list ============================================================================
         for (int i = 0; i < RPW; ++i) {
@@ -419,9 +479,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                     const int code = items[it];
                     r = code >> 7; n = code & 127;
                     const int lb = r % IB;
-                    const float* fr = feat + ((size_t)lb * N + n) * FD;
-                    if (TW) { const float4 f4 = *reinterpret_cast<const float4*>(fr); f[0] = f4.x; f[1] = f4.y; f[2] = f4.z; f[3] = f4.w; }
-                    else { const float2 f2 = *reinterpret_cast<const float2*>(fr); f[0] = f2.x; f[1] = f2.y; }
+                    const float* fr = gfeat + ((size_t)lb * N + n) * D;
+                    f[0] = __ldcg(fr); f[1] = __ldcg(fr + 1);
+                    if (TW) { f[2] = __ldcg(fr + 2); f[3] = __ldcg(fr + 3); }
                     f[4] = dem[r * NP + n];
                 }
                 {
@@ -509,7 +569,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             const bool live = rvalid && !was_done;
             if (live && sl == 0) ++n_rowsteps;
             float* ulog = logits + lrs * NP;
-            const float* frow = feat + (size_t)lbs * N * FD;
+            const float* frow = gfeat + (size_t)lbs * N * D;
             {   // (a) every row: log(prob[n]) for all nodes, in place of the logits (finished rows: depot with prob 1)
                 unsigned char* mk = maskb + lrs * NP;
                 const int fl = flag_s[lrs];
@@ -533,11 +593,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                 }
 #pragma unroll
                 for (int o = LPR / 2; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-                float se = 0.0f;
-#pragma unroll
-                for (int j = 0; j < NPL; ++j) se += (lg[j] == -INFINITY) ? 0.0f : expf(lg[j] - mx);
-#pragma unroll
-                for (int o = LPR / 2; o; o >>= 1) se += __shfl_xor_sync(kFull, se, o);
+                const float se = softmax_denominator<LPR>(lg, mx);
                 const float lse = logf(se);
                 const bool tracing = a.tr_logits || a.tr_probs || a.tr_masks;
                 const long long tro = ((long long)t * R + row) * N;
@@ -614,15 +670,15 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             {
                 const bool p_done = reinterpret_cast<const int*>(srs)[8] != 0;
                 const float load = srs[0], time = TW ? srs[1] : 0.0f;
-                const float* fsel = frow + idx * FD;
-                const float sx = fsel[0], sy = fsel[1];
+                const float* fsel = frow + idx * D;
+                const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
                 const float px = srs[2], py = srs[3];
                 const float d_idx = sdem[idx];
                 const float d_sat = fminf(d_idx, load);
                 float nload = __fsub_rn(load, d_sat);
                 const float ts = dist_rn(px, py, sx, sy);
                 float ntime = 0.0f;
-                if (TW) ntime = fmaxf(__fadd_rn(time, ts), fsel[2]);
+                if (TW) ntime = fmaxf(__fadd_rn(time, ts), __ldcg(fsel + 2));
                 const float dep = (idx == n_cust) ? 1.0f : 0.0f;
                 nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
                 if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
@@ -641,16 +697,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
 #pragma unroll
                     for (int j = 0; j < NPL; ++j) {
                         const int n = sl + LPR * j;
-                        if (n < N) {
-                            float nx = 0.f, ny = 0.f, ne = 0.f;
-                            if (TW) {
-                                const float4 f4 = *reinterpret_cast<const float4*>(frow + n * 4);
-                                nx = f4.x; ny = f4.y; ne = f4.w;
-                            }
-                            dem[lr * NP + n] = dn[j];
-                            maskb[lr * NP + n] =
-                                (unsigned char)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem);
-                        }
+                        if (n < N) dem[lr * NP + n] = dn[j];
                     }
                 }
                 const int done_now = (!a.full && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
@@ -659,7 +706,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                     if (t == 0) { rs[4] = 0.0f; rs[5] = sx; rs[6] = sy; }
                     else { rs[4] = __fadd_rn(srs[4], ts); rs[5] = srs[5]; rs[6] = srs[6]; }
                     reinterpret_cast<int*>(rs)[8] = done_now;
-                    rs[9] = sx; rs[10] = sy; rs[11] = TW ? fsel[2] : 0.0f; rs[12] = TW ? fsel[FD - 1] : 0.0f;
+                    rs[13] = sumdem; reinterpret_cast<int*>(rs)[14] = 1; rs[15] = dep;   // mask update is deferred
+                    rs[9] = sx; rs[10] = sy; rs[11] = TW ? __ldcg(fsel + 2) : 0.0f; rs[12] = TW ? __ldcg(fsel + 3) : 0.0f;
                     prevlog_s[lr] = reinterpret_cast<float*>(ftile)[lr];
                     a.idx_out[(long long)t * R + row] = idx;
                     if (a.parent_out) a.parent_out[(long long)t * R + row] = par;
@@ -685,7 +733,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             const int lrs = rvalid ? lr : 0, lbs = rvalid ? lb : 0;
             const float load = rs[0], time = TW ? rs[1] : 0.0f;
             unsigned char* mk = maskb + lrs * NP;
-            const float* frow = feat + (size_t)lbs * N * FD;
+            const float* frow = gfeat + (size_t)lbs * N * D;
             float* drow = dem + lrs * NP;
             float* ulog = logits + lrs * NP;
             const int fl = flag_s[lrs];
@@ -708,11 +756,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             }
 #pragma unroll
             for (int o = LPR / 2; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
-            float se = 0.0f;
-#pragma unroll
-            for (int j = 0; j < NPL; ++j) se += (lg[j] == -INFINITY) ? 0.0f : expf(lg[j] - mx);
-#pragma unroll
-            for (int o = LPR / 2; o; o >>= 1) se += __shfl_xor_sync(kFull, se, o);
+            const float se = softmax_denominator<LPR>(lg, mx);
             const float lse = logf(se);
             float bestp = -1.0f;
             int besti = 0x7fffffff;
@@ -766,8 +810,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                 __syncwarp();
             }
             if (idx < 0 || idx >= N) idx = 0;   // rows that are not live carry garbage
-            const float* fsel = frow + idx * FD;
-            const float sx = fsel[0], sy = fsel[1];
+            const float* fsel = frow + idx * D;
+            const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
             const float px = rs[2], py = rs[3];
             const float d_idx = drow[idx];
             __syncwarp();
@@ -775,7 +819,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             float nload = __fsub_rn(load, d_sat);
             const float ts = dist_rn(px, py, sx, sy);
             float ntime = 0.0f;
-            if (TW) ntime = fmaxf(__fadd_rn(time, ts), fsel[2]);
+            if (TW) ntime = fmaxf(__fadd_rn(time, ts), __ldcg(fsel + 2));
             const float dep = (idx == n_cust) ? 1.0f : 0.0f;
             nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
             if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
@@ -790,27 +834,14 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             }
 #pragma unroll
             for (int o = LPR / 2; o; o >>= 1) sumdem += __shfl_xor_sync(kFull, sumdem, o);
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < NPL; ++j) {
-                    const int n = sl + LPR * j;
-                    if (n < N) {
-                        float nx = 0.f, ny = 0.f, ne = 0.f;
-                        if (TW) {
-                            const float4 f4 = *reinterpret_cast<const float4*>(frow + n * 4);
-                            nx = f4.x; ny = f4.y; ne = f4.w;
-                        }
-                        mk[n] = (unsigned char)node_mask<TW>(n, n_cust, lg[j], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem);
-                    }
-                }
-            }
             const int done_now = (!a.full && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
             if (live && sl == 0) {
                 rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
                 if (t == 0) { rs[5] = sx; rs[6] = sy; }
                 else rs[4] = __fadd_rn(rs[4], ts);
                 reinterpret_cast<int*>(rs)[8] = done_now;
-                rs[9] = sx; rs[10] = sy; rs[11] = TW ? fsel[2] : 0.0f; rs[12] = TW ? fsel[FD - 1] : 0.0f;
+                rs[13] = sumdem; reinterpret_cast<int*>(rs)[14] = 1; rs[15] = dep;   // mask update is deferred
+                rs[9] = sx; rs[10] = sy; rs[11] = TW ? __ldcg(fsel + 2) : 0.0f; rs[12] = TW ? __ldcg(fsel + 3) : 0.0f;
                 a.idx_out[(long long)t * R + row] = idx;
                 if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
             }
@@ -830,6 +861,8 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
         __threadfence_block();
         mbar_arrive(bar_x);
     }
+    update_masks();            // the masks of the last moves (final-state outputs)
+    named_bar(5, NT);
     const int t_end = t;
 
     for (int i = 0; i < RPW; ++i) {

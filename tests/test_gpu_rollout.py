@@ -252,6 +252,28 @@ def test_fused_beam_search_vs_oracle(task, B, W, seed):
         env.step(idx[t][:, None], par[t][:, None])
 
 
+def test_results_do_not_depend_on_rows_per_cta_or_chunking():
+    """rows_per_cta is a tuning knob: every reduction that feeds a decision is done in one fixed order, so the tours
+    are bit-identical for every block size - and the chunked host entry point equals the one-shot device call."""
+    import torch
+    pkg = load_pkg()
+    args = O.default_args("vrptw50")
+    params = O.init_params(args, seed=61)
+    data = O.create_dataset("vrptw50", 3000, seed=21).astype(np.float32)
+    x = torch.from_numpy(data).cuda()
+    outs = []
+    for rb in (16, 32, 48, 64):
+        eng, _ = _engine(args, params, rows_per_cta=rb)
+        try:
+            outs.append(eng.rollout(x, "greedy", want_logprobs=True))
+        except pkg.VrpB200Error as e:
+            assert "shared memory" in str(e)
+    torch.cuda.synchronize()
+    assert len(outs) >= 3
+    for o in outs[1:]:
+        assert torch.equal(o.idxs, outs[0].idxs) and torch.equal(o.R, outs[0].R) and torch.equal(o.logprobs, outs[0].logprobs)
+
+
 def test_errors_are_reported_not_thrown():
     pkg = load_pkg()
     args = O.default_args("vrptw10")
