@@ -17,7 +17,7 @@ extra = sys.argv[5:]
 args = pkg.task_specific_params.default_args(task)
 eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))
-x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2).astype(np.float32)).cuda()
+x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2, ups=bool(os.environ.get("UPS"))).astype(np.float32)).cuda()
 eng.rollout(x)
 stats = torch.zeros(16, dtype=torch.int64, device="cuda")
 tr = L.Trace(); tr.d_stats = stats.data_ptr()
@@ -27,7 +27,8 @@ rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 0, 1, None
 torch.cuda.synchronize()
 s = stats.cpu().numpy()
 blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
-names = ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"]
+names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epilogue", "C1 scores", "C2 select/env"] if gemm == "tc3" else
+         ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"])
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
 for n, v in zip(names, s[4:10]):
     print(f"  {n:30s} {v / blocksteps:10.0f} clk/step")
