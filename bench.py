@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-cta", type=int, default=0)
-    ap.add_argument("--kernel", default="tc3", choices=["tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout3)")
+    ap.add_argument("--kernel", default="tc3", choices=["tc4", "tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout3)")
     return ap.parse_args()
 
 

@@ -1,0 +1,841 @@
+// rollout4_kernel: rollout3 with the per-row tail of the decode step (selection, Env.step, mask, item list) taken off
+// the critical path and the pointer-score phase re-built as a real software pipeline.
+//
+//  * warp specialisation inside the step: compute warps 0..11 (three groups of four) evaluate the pointer scores (C1);
+//    compute warps 12..15 are "row warps": as soon as every tile that holds items of a row has been scored they run
+//    log-softmax, the choice, Env.step, the new mask AND the item list of the next step for that row (8 lanes per row,
+//    16 rows in flight), while the score warps keep the MUFU pipe busy with the tiles of later rows;
+//  * C1 per group: the 128 hidden units of a 128-item tile arrive in four N = 32 quarters that alternate between two
+//    TMEM buffers; a quarter is copied to registers as soon as its MMA has landed, which frees the buffer, so the MMA two
+//    quarters ahead is always in flight behind the arithmetic; the features of the NEXT tile are fetched from L2
+//    (volatile loads, issued before the arithmetic of this tile) and written to the F tile when the last MMA of this tile
+//    has completed; the arithmetic runs on 16 independent elements at a time (v_h comes from the constant bank);
+//  * q^T has its own TMEM columns (192..255), so the first tiles of a step are staged and their MMAs issued while the
+//    query GEMM is still running;
+//  * item lists are per row (node ids, uint8); a tile finds the row of an item with a binary search in the row offsets.
+//
+// Greedy and stochastic decoding; beam search stays on rollout3 (rows of one instance compete, no per-row streaming).
+#pragma once
+#include "rollout3_kernel.cuh"
+
+namespace vrpb200 {
+
+constexpr int kV4Threads = 576;   // 16 compute warps + weight feeder warp + MMA issuer warp
+
+struct Smem4 {
+    int ring, X, qq, F, logits, items, bc, vsm, dem, mask, rs, meta, bar, total, stages;
+};
+
+__host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw) {
+    Smem4 L;
+    const int NP = align_up(N, 4);
+    int off = 0;
+    L.stages = stages;
+    L.ring = off;   off += stages * kSlabBytes;
+    L.X = off;      off += 2 * RB * kH * 4;
+    L.qq = off;     off += RB * kH * 4;
+    L.F = off;      off += (nsw / 4) * 2 * kC1TileBytes;
+    L.logits = off; off += RB * NP * 4;
+    L.items = off;  off += align_up(RB * NP, 16);             // node ids of the items of every row
+    L.bc = off;     off += 2 * 4096;
+    L.vsm = off;    off += 512;                               // -2 v
+    L.dem = off;    off += RB * NP * 4;
+    L.mask = off;   off += align_up(RB * NP, 16);
+    L.rs = off;     off += RB * kRowState * 4;
+    L.meta = off;   off += align_up((RB + 68 + RB + 64 + 20) * 4, 16);   // nact[RB], off[<=65 (+pad)], flags[RB], tilecnt[64], done[16], stop
+    L.bar = off;    off += 320;
+    L.total = off;
+    return L;
+}
+
+VRP_DEVINL void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+VRP_DEVINL void tc_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+VRP_DEVINL float ldcg_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+VRP_DEVINL int lds_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+// NSW = number of score warps: 12 -> warps 12..15 are row warps that stream the per-row tail behind C1;
+//                               16 -> every warp scores, then every warp runs the per-row tail (lock-step)
+template <int RB, bool TW, int STAGES, int NSW>
+__global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_constant__ RolloutArgs a) {
+    constexpr int NT = 512, RPW = RB / 16, RPT = RB / 4, FD = TW ? 4 : 2;
+    constexpr int NG = NSW / 4;                                  // score groups, 64 TMEM columns each
+    constexpr int kQCol = NSW == 12 ? 192 : 256 + 4 * RB;        // q^T: its own columns
+    constexpr int kGCol = 256;                                   // gates^T: tile m at kGCol + RB m
+    static_assert(NSW == 12 || (NSW == 16 && RB <= 48), "TMEM columns");
+    constexpr int LPR = 8, NB = RB / 16;   // row warps: lanes per row, batches of 16 rows
+    static_assert(RB % 16 == 0 && RB <= 48, "rows");
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int N = a.N, NP = align_up(N, 4), T = a.T, n_cust = a.n_cust;
+    const Smem4 L = make_layout4(RB, N, STAGES, NSW);
+    unsigned char* xt = smem + L.X;
+    float* qq = reinterpret_cast<float*>(smem + L.qq);
+    unsigned char* ftile = smem + L.F;
+    float* logits = reinterpret_cast<float*>(smem + L.logits);
+    unsigned char* items = smem + L.items;
+    float* vsm = reinterpret_cast<float*>(smem + L.vsm);
+    float* dem = reinterpret_cast<float*>(smem + L.dem);
+    unsigned char* maskb = smem + L.mask;
+    float* rowst = reinterpret_cast<float*>(smem + L.rs);
+    int* nact_s = reinterpret_cast<int*>(smem + L.meta);
+    int* off_s = nact_s + RB;            // [RB + 1] exclusive prefix of nact (this step)
+    int* flag_s = off_s + 68;            // [RB] every node of the row is an item
+    int* tilecnt = flag_s + RB;          // [64] warps that have finished tile i in this step
+    int* done_s = tilecnt + 64;          // [16] per warp: every row of the warp is finished
+    volatile int* stop_s = done_s + 16;
+    const uint32_t bar0 = smem_u32(smem + L.bar);
+    const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, tmem_slot = bar0 + 120,
+                   bar_grp = bar0 + 128;   // group g at +40 g: full[0], full[1] (MMA commit), free[0], free[1] (4 warps copied the buffer), F ready (4 warps)
+    const uint32_t ring_u32 = smem_u32(smem + L.ring), bc_u32 = smem_u32(smem + L.bc);
+    const uint32_t x_hi = smem_u32(xt), x_lo = x_hi + RB * kH * 4;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int sp = warp & 3, ub = warp >> 2;
+    const long long b0 = (long long)blockIdx.x * RB;
+    const int IBv = (int)min((long long)RB, a.B - b0);
+    const long long R = a.B;
+    const int D = a.D;
+    const float* gfeat = a.input + b0 * (long long)N * D;
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
+        mbar_init(bar_q, 1); mbar_init(bar_g, 1); mbar_init(bar_x, 1);
+        for (int g = 0; g < NG; ++g) {
+            mbar_init(bar_grp + 40 * g, 1); mbar_init(bar_grp + 40 * g + 8, 1);
+            mbar_init(bar_grp + 40 * g + 16, 4); mbar_init(bar_grp + 40 * g + 24, 4); mbar_init(bar_grp + 40 * g + 32, 4);
+        }
+        *stop_s = 0;
+        for (int w = 0; w < 16; ++w) done_s[w] = 1;
+        fence_mbar_init();
+    }
+    __syncwarp();
+    if (warp == 0) tc_alloc(tmem_slot, kTcCols);
+    for (int i = tid; i < 128 * 8; i += kV4Threads) {
+        const int h = i >> 3, k = i & 7;
+        float val = 0.0f;
+        if (k < FD) val = a.att.A[k * kH + h];
+        else if (k == 4) val = a.att.gd[h];
+        const float hi = tf32_rna(val), lo = tf32_rna(val - hi);
+        const int o = (h >> 3) * 256 + (k >> 2) * 128 + (h & 7) * 16 + (k & 3) * 4;
+        *reinterpret_cast<float*>(smem + L.bc + o) = hi;
+        *reinterpret_cast<float*>(smem + L.bc + 4096 + o) = lo;
+    }
+    if (tid < 128) vsm[tid] = a.vm2[tid];
+    for (int i = tid; i < 2 * RB * kH; i += kV4Threads) reinterpret_cast<float*>(xt)[i] = 0.0f;   // h_0 = 0
+    for (int i = tid; i < IBv * N; i += kV4Threads) {
+        const int lb = i / N, n = i - lb * N;
+        dem[lb * NP + n] = a.input[((b0 + lb) * N + n) * D + D - 1];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.bar + 120);
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
+    constexpr uint32_t idescL = tc_idesc(128, RB), idescQ = tc_idesc(128, 32);
+
+    if (warp >= 16) {
+        // ============ streaming warps: warp 16 feeds the weight ring from L2, warp 17 issues every LSTM / query MMA.
+        // (Two warps: as two lanes of one warp a blocking mbarrier.try_wait of one role stalls the other.)
+        if (warp == 16 && lane == 0) {
+            uint32_t c = 0;
+            int pre = 0;
+            auto issue = [&](int u) {
+                const uint32_t st = c % STAGES;
+                mbar_wait(bar_empty + 8 * st, ((c / STAGES) & 1) ^ 1);
+                mbar_expect_tx(bar0 + 8 * st, kSlabBytes);
+                const float* src = u < kV3UsesQ ? a.WqTc + (size_t)u * kSlabFloats : a.WgT3 + (size_t)(u - kV3UsesQ) * kSlabFloats;
+                bulk_g2s(ring_u32 + st * kSlabBytes, src, kSlabBytes, bar0 + 8 * st);
+                ++c;
+            };
+            for (int step = 0;; ++step) {
+                mbar_wait(bar_x, step & 1);
+                if (*stop_s) {
+                    for (uint32_t j = c - pre; j < c; ++j) mbar_wait(bar0 + 8 * (j % STAGES), (j / STAGES) & 1);
+                    break;
+                }
+                for (int u = pre; u < kV3UsesQ + kV3UsesG; ++u) issue(u);
+                pre = STAGES < kV3UsesQ ? STAGES : kV3UsesQ;
+                for (int u = 0; u < pre; ++u) issue(u);
+            }
+        } else if (warp == 17 && lane == 0) {
+            uint32_t c = 0;
+            int step = 0;
+            for (;; ++step) {
+                mbar_wait(bar_x, step & 1);
+                tc_fence_after();
+                if (*stop_s) break;
+#pragma unroll 1
+                for (int u = 0; u < kV3UsesQ; ++u, ++c) {          // q^T[unit, row] = W_q^T . h^T  -> columns kQCol..
+                    const uint32_t st = c % STAGES;
+                    mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int kk = 0; kk < 2; ++kk) {
+                        const int kc = 2 * u + kk;
+                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192, 128, 256);
+                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192 + 4096, 128, 256);
+                        const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
+                        tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
+                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
+                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                    }
+                    tc_commit(bar_empty + 8 * st);
+                }
+                tc_commit(bar_q);
+#pragma unroll 1
+                for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
+                    const uint32_t st = c % STAGES;
+                    mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
+                    if (u > 0) {   // throttle: this GEMM has a whole step of slack, the score MMAs of C1 queue behind it
+                        const uint32_t cp = c - 1;
+                        mbar_wait(bar_empty + 8 * (cp % STAGES), (cp / STAGES) & 1);
+                    }
+                    tc_fence_after();
+                    const int kc = u >> 1, mp = u & 1;
+                    const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
+#pragma unroll
+                    for (int mi = 0; mi < 2; ++mi) {
+                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192, 128, 256);
+                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192 + 4096, 128, 256);
+                        const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
+                        tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
+                        tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
+                        tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                    }
+                    tc_commit(bar_empty + 8 * st);
+                }
+                tc_commit(bar_g);
+            }
+            if (step > 0) mbar_wait(bar_g, (step - 1) & 1);
+        }
+        __syncwarp();
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
+
+    // =============================== 16 compute warps ===========================================================
+    // Code size matters here: the kernel has three warp roles running different code at the same time, and straight-line
+    // (fully unrolled) phases of a few thousand instructions each thrash the instruction caches.  Every per-node loop
+    // below is a rolled loop with a uniform trip count NJ (guards inside), the LSTM epilogue rotates its cell-state
+    // registers instead of unrolling over row chunks, and the C1 quarter loop is rolled.
+    const int NJ = (N + LPR - 1) / LPR;   // nodes per lane of a row sub-warp: n = sl + 8 j
+    // 8-lane sub-warp of a row: the item list (+ count, + "all nodes" flag) of the next step from the row's mask.
+    // All four sub-warps of a warp call this together (ballots are warp-wide).
+    auto build_items = [&](int lrs, bool rvalid, bool finished, int sub, int sl) -> int {
+        const unsigned char* mk = maskb + lrs * NP;
+        unsigned char* it = items + lrs * NP;
+        const bool on = rvalid && !finished;
+        int nun = 0;
+#pragma unroll 1
+        for (int j = 0; j < NJ; ++j) {
+            const int n = sl + LPR * j;
+            const bool act = on && n < N && mk[n] == 0;
+            const unsigned bits = (__ballot_sync(kFull, act) >> (8 * sub)) & 0xffu;
+            if (act) it[nun + __popc(bits & ((1u << sl) - 1))] = (unsigned char)n;
+            nun += __popc(bits);
+        }
+        int fl = 0, na = nun;
+        if (on && (a.full || nun == 0 || !a.mask_pointer)) {   // every node is evaluated
+            fl = 1; na = N;
+            for (int n = sl; n < N; n += LPR) it[n] = (unsigned char)n;
+        }
+        if (sl == 0 && rvalid) { nact_s[lrs] = na; flag_s[lrs] = fl; }
+        return nun;
+    };
+
+    for (int i = 0; i < RPW; ++i) {   // Env.reset (vrptw_utils.py:199-252) + prologue
+        const int lr = warp * RPW + i;
+        if (lane == 0) { nact_s[lr] = 0; flag_s[lr] = 0; }
+        if (lr >= IBv) continue;
+        int nzc = 0;
+        for (int n = lane; n < N; n += 32) {
+            const bool z = dem[lr * NP + n] == 0.0f;
+            maskb[lr * NP + n] = (n == n_cust) ? 1 : (z ? 1 : 0);
+            nzc += z ? 0 : 1;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(kFull, nzc, o);
+        const float* fdep = gfeat + (size_t)(lr * N + n_cust) * D;
+        if (lane == 0) {
+            float* rs = rowst + lr * kRowState;
+            rs[13] = (float)nzc;
+            rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = __ldcg(fdep + 0); rs[3] = __ldcg(fdep + 1); rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
+            reinterpret_cast<int*>(rs)[8] = 0;
+            rs[9] = __ldcg(fdep + 0); rs[10] = __ldcg(fdep + 1); rs[11] = TW ? __ldcg(fdep + 2) : 0.0f; rs[12] = TW ? __ldcg(fdep + 3) : 0.0f;
+        }
+    }
+    named_bar(5, NT);
+    if (warp < RB / 4) {
+        const int sub = lane >> 3, sl = lane & 7, lr = 4 * warp + sub;
+        build_items(lr < IBv ? lr : 0, lr < IBv, false, sub, sl);
+    }
+    const int unit = 32 * sp + lane;
+    float cst[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) cst[r] = 0.0f;
+    named_bar(5, NT);
+
+#ifdef VRPB200_PHASE_CLOCKS
+    long long pc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc_last_ = clock64();
+#endif
+    // C1: the two TMEM buffers of a group are used strictly in turn, so one counter of consumed quarters (every thread)
+    // and one of issued quarters (issuer thread) give buffer index and mbarrier parity
+    uint32_t c1_nq = 0, c1_ni = 0, c1_nf = 0;
+    unsigned long long n_eval = 0, n_rowsteps = 0;
+    int t = 0;
+#pragma unroll 1
+    for (; t < T; ++t) {
+        // ================= row offsets of this step's item lists (every warp, redundantly; warp 0 publishes them) ======
+        int m_tot;
+        {
+            const int n0 = (lane < RB) ? nact_s[lane] : 0, n1 = (lane + 32 < RB) ? nact_s[lane + 32] : 0;
+            int s0 = n0, s1 = n1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t0 = __shfl_up_sync(kFull, s0, o), t1 = __shfl_up_sync(kFull, s1, o);
+                if (lane >= o) { s0 += t0; s1 += t1; }
+            }
+            const int tot0 = __shfl_sync(kFull, s0, 31);
+            m_tot = tot0 + __shfl_sync(kFull, s1, 31);
+            if (warp == 0) {
+                if (lane < RB) off_s[lane] = s0 - n0;
+                if (lane + 32 < RB) off_s[lane + 32] = tot0 + s1 - n1;
+                if (lane == 0) off_s[RB] = m_tot;
+            }
+            if (tid < 64) tilecnt[tid] = 0;
+        }
+        // ================= LSTM epilogue: gates = gates^T(TMEM, h part) + x part + bias ; c, h' ; h' -> X ==========
+        {
+            float wx[4][4], bgt[4];
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                bgt[m] = __ldg(a.bgT + m * kH + unit);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) wx[k][m] = __ldg(a.WxT + (k * 4 + m) * kH + unit);
+            }
+            if (t > 0) {
+                mbar_wait(bar_g, (t - 1) & 1);
+                tc_fence_after();
+            }
+            VRP_CLK(0);
+#pragma unroll 1
+            for (int c4 = 0; c4 < RPT / 4; ++c4) {
+                const int r0 = ub * RPT + 4 * c4;
+                float g[4][4];
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if (t > 0) tc_ld4(tmem_lane + kGCol + RB * m + r0, g[m]);
+                    else { g[m][0] = g[m][1] = g[m][2] = g[m][3] = 0.0f; }
+                }
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* rs = rowst + (r0 + i) * kRowState;
+                    const float xf[4] = {rs[9], rs[10], rs[11], rs[12]};
+                    float gg[4];
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        float s = bgt[m];
+#pragma unroll
+                        for (int k = 0; k < FD; ++k) s = fmaf(xf[k], wx[k][m], s);
+                        gg[m] = g[m][i] + s;
+                    }
+                    const float cn = __fadd_rn(__fmul_rn(cst[i], sigmoid_fast(gg[2] + a.forget_bias)),
+                                               __fmul_rn(sigmoid_fast(gg[0]), tanh_fast(gg[1])));
+                    cst[i] = cn;
+                    const float hn = __fmul_rn(tanh_fast(cn), sigmoid_fast(gg[3]));
+                    hi[i] = tf32_rna(hn);
+                    lo[i] = hn - hi[i];
+                }
+                if (RPT > 4) {   // rotate the cell-state registers: the chunk just updated goes to the back
+                    const float t0 = cst[0], t1 = cst[1], t2 = cst[2], t3 = cst[3];
+#pragma unroll
+                    for (int r = 0; r + 4 < RPT; ++r) cst[r] = cst[r + 4];
+                    cst[RPT - 4] = t0; cst[RPT - 3] = t1; cst[RPT - 2] = t2; cst[RPT - 1] = t3;
+                }
+                transpose4(hi, lane);
+                transpose4(lo, lane);
+                {
+                    const int rr = r0 + (lane & 3);
+                    const int off = (rr >> 3) * 4096 + (unit >> 2) * 128 + (rr & 7) * 16;
+                    *reinterpret_cast<float4*>(xt + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(xt + RB * kH * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar(5, NT);
+            if (tid == 0) mbar_arrive(bar_x);      // h' is in place: the streaming warp may issue q(t) and gates(t+1)
+        }
+        VRP_CLK(1);
+
+        // ================= C1 set-up (score warps): first tile of every group, staged while the query GEMM runs ========
+        const int ntiles = (m_tot + 127) >> 7;
+        const int g = ub;                                                // score group (warps 0..11)
+        unsigned char* fhi = ftile + (g < NG ? g : 0) * 2 * kC1TileBytes;
+        const uint32_t f_hi = smem_u32(fhi), f_lo = f_hi + kC1TileBytes;
+        const uint32_t d_g = tmem_base + 64 * g;
+        const uint32_t bfull = bar_grp + 40 * (g < NG ? g : 0), bfree = bfull + 16, bfrdy = bfull + 32;
+        const int m = 32 * sp + lane;
+        const bool issuer = (sp == 0 && lane == 0);
+        // item `it` of the step -> (row, node): binary search in the row offsets, then the row's node list
+        auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5]) {
+            const int it = tile * 128 + m;
+            valid = tile < ntiles && it < m_tot;
+            r = 0; n = 0;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) f[k] = 0.0f;
+            if (valid) {
+                int lo = 0, hi = RB;
+#pragma unroll
+                for (int s = 0; s < 6; ++s) {
+                    const int mid = (lo + hi) >> 1;
+                    if (off_s[mid] <= it) lo = mid; else hi = mid;
+                }
+                r = lo;
+                n = items[r * NP + (it - off_s[r])];
+                const float* fr = gfeat + ((size_t)r * N + n) * D;
+                f[0] = ldcg_volatile(fr); f[1] = ldcg_volatile(fr + 1);
+                if (TW) { f[2] = ldcg_volatile(fr + 2); f[3] = ldcg_volatile(fr + 3); }
+                f[4] = dem[r * NP + n];
+            }
+        };
+        auto store_F = [&](const float (&f)[5]) {
+            float hi[5], lo[5];
+#pragma unroll
+            for (int k = 0; k < 5; ++k) { hi[k] = tf32_rna(f[k]); lo[k] = f[k] - hi[k]; }
+            const int off = (m >> 3) * 256 + (m & 7) * 16;
+            *reinterpret_cast<float4*>(fhi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(fhi + off + 128) = make_float4(hi[4], 0.0f, 0.0f, 0.0f);
+            *reinterpret_cast<float4*>(fhi + kC1TileBytes + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<float4*>(fhi + kC1TileBytes + off + 128) = make_float4(lo[4], 0.0f, 0.0f, 0.0f);
+            fence_proxy_async();
+        };
+        auto issue_quarter = [&](int q) {   // issuer thread only: E[:, 32q .. 32q+31] -> the next TMEM buffer in turn
+            const uint32_t b = c1_ni & 1, k = c1_ni >> 1;
+            ++c1_ni;
+            if (k > 0) mbar_wait(bfree + 8 * b, (k - 1) & 1);   // the 4 warps have copied its previous content
+            tc_fence_after();
+            const uint64_t dfh = tc_desc(f_hi, 128, 256), dfl = tc_desc(f_lo, 128, 256);
+            const uint64_t dbh = tc_desc(bc_u32 + q * 1024, 128, 256), dbl = tc_desc(bc_u32 + 4096 + q * 1024, 128, 256);
+            tc_mma_tf32(d_g + 32 * b, dfl, dbh, idescQ, 0);
+            tc_mma_tf32(d_g + 32 * b, dfh, dbl, idescQ, 1);
+            tc_mma_tf32(d_g + 32 * b, dfh, dbh, idescQ, 1);
+            tc_commit(bfull + 8 * b);
+        };
+        int r_cur = 0, n_cur = 0;
+        bool v_cur = false;
+        const bool scoring = warp < NSW && g < ntiles;
+        if (scoring) {
+            float fc[5];
+            load_item(g, r_cur, n_cur, v_cur, fc);
+            store_F(fc);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bfrdy);
+            if (issuer) {
+                mbar_wait(bfrdy, c1_nf & 1); ++c1_nf;      // the four warps of the group have written their part of F
+                issue_quarter(0); issue_quarter(1);
+            }
+            __syncwarp();
+        }
+        VRP_CLK(2);
+        // ================= query epilogue: base'[row][unit] = 2log2e (q + b + load g_ld + time g_t) ===================
+        {
+            const float bqv = __ldg(a.att.bq + unit), glv = __ldg(a.att.gl + unit), gtv = __ldg(a.att.gt + unit);
+            mbar_wait(bar_q, t & 1);
+            tc_fence_after();
+            VRP_CLK(3);
+#pragma unroll 1
+            for (int c4 = 0; c4 < RPT / 4; ++c4) {
+                const int r0 = ub * RPT + 4 * c4;
+                float q4[4];
+                tc_ld4(tmem_lane + kQCol + r0, q4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* rs = rowst + (r0 + i) * kRowState;
+                    float s = fmaf(rs[0], glv, q4[i] + bqv);
+                    if (TW) s = fmaf(rs[1], gtv, s);
+                    qq[(r0 + i) * kH + unit] = s * kTwoLog2e;
+                }
+            }
+        }
+        tc_fence_before();
+        named_bar(5, NT);
+        tc_fence_after();
+        VRP_CLK(4);
+
+        if (warp < NSW) {
+            // ================= C1: scores =================================================================
+            if (scoring) {
+                int r_nx, n_nx;
+                bool v_nx;
+                float fn[5];
+#pragma unroll 1
+                for (int tile = g; tile < ntiles; tile += NG) {
+                    const bool has_next = tile + NG < ntiles;
+                    load_item(tile + NG, r_nx, n_nx, v_nx, fn);          // in flight during the arithmetic below
+                    const float* brow = qq + r_cur * kH;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t b = c1_nq & 1, par = (c1_nq >> 1) & 1;
+                        ++c1_nq;
+                        VRP_CLK(11);
+                        mbar_wait(bfull + 8 * b, par);
+                        tc_fence_after();
+                        VRP_CLK(7);
+                        if (q == 3 && has_next) {   // every MMA of this tile has completed: the F tile may be replaced
+                            store_F(fn);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bfrdy);
+                            if (issuer) { mbar_wait(bfrdy, c1_nf & 1); ++c1_nf; issue_quarter(0); }
+                            __syncwarp();
+                        }
+                        VRP_CLK(8);
+                        uint32_t cur[32];
+                        tc_ld32_issue(tmem_lane + 64 * g + 32 * b, cur);
+                        tc_ld_wait32(cur);
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(bfree + 8 * b);
+                        if (issuer) {
+                            if (q < 2) issue_quarter(q + 2);
+                            else if (q == 3 && has_next) issue_quarter(1);
+                        }
+                        __syncwarp();
+                        VRP_CLK(9);
+                        const float* bq = brow + 32 * q;
+                        const float* vq = vsm + 32 * q;
+#pragma unroll
+                        for (int hf = 0; hf < 2; ++hf) {    // 16 independent elements at a time
+                            float e[16];
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 b4 = *reinterpret_cast<const float4*>(bq + 16 * hf + 4 * k4);
+                                e[4 * k4 + 0] = __uint_as_float(cur[16 * hf + 4 * k4 + 0]) + b4.x;
+                                e[4 * k4 + 1] = __uint_as_float(cur[16 * hf + 4 * k4 + 1]) + b4.y;
+                                e[4 * k4 + 2] = __uint_as_float(cur[16 * hf + 4 * k4 + 2]) + b4.z;
+                                e[4 * k4 + 3] = __uint_as_float(cur[16 * hf + 4 * k4 + 3]) + b4.w;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) e[i] = 1.0f + ex2_approx(fminf(e[i], 30.0f));   // t = 1 + 2^arg <= 2^30 + 1
+                            // sum_j w_j / t_j over 4 elements with ONE reciprocal (w = -2 v):
+                            //   (w0 t1 + w1 t0) t2 t3 + (w2 t3 + w3 t2) t0 t1  over  t0 t1 t2 t3       (no overflow: t <= 2^30 + 1)
+#pragma unroll
+                            for (int k4 = 0; k4 < 4; ++k4) {
+                                const float4 v4 = *reinterpret_cast<const float4*>(vq + 16 * hf + 4 * k4);
+                                const float t0 = e[4 * k4], t1 = e[4 * k4 + 1], t2 = e[4 * k4 + 2], t3 = e[4 * k4 + 3];
+                                const float p01 = t0 * t1, p23 = t2 * t3;
+                                const float n01 = fmaf(v4.x, t1, v4.y * t0), n23 = fmaf(v4.z, t3, v4.w * t2);
+                                const float num = fmaf(n01, p23, n23 * p01);
+                                const float r = rcp_approx(p01 * p23);
+                                if (k4 & 1) acc1 = fmaf(num, r, acc1); else acc0 = fmaf(num, r, acc0);
+                            }
+                        }
+                        VRP_CLK(10);
+                    }
+                    // u = sum_h v_h tanh(.) = sum_h v_h - sum_h 2 v_h / (1 + 2^arg)
+                    if (v_cur) logits[r_cur * NP + n_cur] = a.sumv + (acc0 + acc1);
+                    n_eval += v_cur ? 1 : 0;
+                    if (NSW != 16) {   // tell the row warps
+                        __syncwarp();
+                        if (lane == 0) {
+                            __threadfence_block();
+                            atomicAdd(tilecnt + tile, 1);
+                        }
+                    }
+                    r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                }
+            }
+            VRP_CLK(5);
+        }
+        if (NSW == 16) named_bar(5, NT);   // lock-step variant: every logit of the step is in place
+        if (NSW == 16 ? warp < RB / 4 : warp >= 12) {
+            // ================= per-row tail: log-softmax, choice, Env.step, mask, next item list ==========================
+            // 8 lanes per row, lane sl owns nodes sl, sl + 8, ...; masked logits and probabilities live in the row's logits
+            // slots (shared memory), so no per-lane arrays are needed and every node loop stays rolled.
+            // NSW == 12: warps 12..15 stream batches of 16 rows behind the score warps; NSW == 16: warp w owns rows 4w..4w+3
+            const int sub = lane >> 3, sl = lane & 7;
+            int warp_done = 1;
+#pragma unroll 1
+            for (int bt = 0; bt < (NSW == 16 ? 1 : NB); ++bt) {
+                const int r0 = NSW == 16 ? 4 * warp : 16 * bt + 4 * (warp - 12);
+                const int lr = r0 + sub;
+                if (NSW != 16) {   // wait for every tile that holds items of rows r0 .. r0+3
+                    const int i0 = off_s[r0], i1 = off_s[r0 + 4];
+                    if (i1 > i0) {
+                        const int tl = (i1 - 1) >> 7;
+                        for (int tile = i0 >> 7; tile <= tl; ++tile)
+                            while (lds_volatile(tilecnt + tile) < 4) __nanosleep(40);
+                        __threadfence_block();
+                    }
+                    __syncwarp();
+                }
+                const bool rvalid = lr < IBv;
+                const int lrs = rvalid ? lr : 0;
+                float* rs = rowst + lrs * kRowState;
+                const long long row = b0 + lrs;
+                const bool was_done = rvalid && reinterpret_cast<int*>(rs)[8] != 0;
+                const bool live = rvalid && !was_done;
+                if (was_done && sl == 0) {
+                    a.idx_out[(long long)t * R + row] = n_cust;
+                    if (a.logprob_out) a.logprob_out[(long long)t * R + row] = 0.0f;
+                }
+                if (live && sl == 0) ++n_rowsteps;
+                const float load = rs[0], time = TW ? rs[1] : 0.0f;
+                unsigned char* mk = maskb + lrs * NP;
+                const float* frow = gfeat + (size_t)lrs * N * D;
+                float* drow = dem + lrs * NP;
+                float* ulog = logits + lrs * NP;
+                const int fl = flag_s[lrs];
+                const bool tracing = a.tr_logits || a.tr_probs || a.tr_masks;
+                const long long tro = ((long long)t * R + row) * N;
+                // ---- masked logits (decode_step.py:231-232) back into the row's slots; maximum, its first index, runner-up
+                float mx = -INFINITY, second = -INFINITY;
+                int mxi = 0x7fffffff;
+#pragma unroll 2
+                for (int j = 0; j < NJ; ++j) {
+                    const int n = sl + LPR * j;
+                    float u = -INFINITY;
+                    if (n < N && live) {
+                        const int mm = mk[n];
+                        if (fl || mm == 0) {
+                            u = ulog[n];
+                            if (a.use_tanh) u = a.tanh_C * tanhf(u);
+                            if (a.mask_pointer) u = __fsub_rn(u, __fmul_rn(kBig, (float)mm));
+                        }
+                        ulog[n] = u;
+                        if (tracing) {
+                            if (a.tr_logits) a.tr_logits[tro + n] = u;
+                            if (a.tr_masks) a.tr_masks[tro + n] = (float)mm;
+                        }
+                    }
+                    if (u > mx) { second = mx; mx = u; mxi = n; }      // (nodes come in increasing order: first maximum wins)
+                    else second = fmaxf(second, u);
+                }
+#pragma unroll
+                for (int o = LPR / 2; o; o >>= 1) {
+                    const float ov = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, second, o);
+                    const int oi = __shfl_xor_sync(kFull, mxi, o);
+                    second = fmaxf(fmaxf(second, os), fminf(mx, ov));
+                    if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
+                }
+                int idx;
+                float psel = 1.0f;
+                // Greedy decoding takes argmax(prob) (attention_agent.py:146-147).  exp is monotone up to a few ulp, so when the
+                // runner-up logit is more than 1e-5 below the maximum its probability is strictly smaller and the arg-max of
+                // the logits IS the reference's choice; the softmax is then only evaluated if somebody asked for its values.
+                const bool need_softmax = a.mode != 0 || tracing || a.logprob_out != nullptr || !(second < mx - 1e-5f);
+                if (__any_sync(kFull, need_softmax && live)) {
+                    // ---- softmax denominator in the fixed order of softmax_denominator<LPR> (rollout3): node n belongs to
+                    //      virtual lane n % 32 (= sl + 8 qv), which adds its nodes n, n + 32, ... in sequence
+                    float P0 = 0.0f, P1 = 0.0f, P2 = 0.0f, P3 = 0.0f;
+#pragma unroll 1
+                    for (int k = 0; k < 4; ++k) {
+                        const int nb = sl + 32 * k;
+                        float ev[4];
+#pragma unroll
+                        for (int qv = 0; qv < 4; ++qv) {
+                            const int n = nb + 8 * qv;
+                            const float u = (n < N && live) ? ulog[n] : -INFINITY;
+                            ev[qv] = (u == -INFINITY) ? 0.0f : expf(u - mx);
+                        }
+                        P0 = __fadd_rn(P0, ev[0]); P1 = __fadd_rn(P1, ev[1]); P2 = __fadd_rn(P2, ev[2]); P3 = __fadd_rn(P3, ev[3]);
+                    }
+                    float se = __fadd_rn(__fadd_rn(P0, P2), __fadd_rn(P1, P3));
+#pragma unroll
+                    for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
+                    const float lse = logf(se);
+                    // ---- probabilities (decode_step.py:125-126) and the greedy candidate
+                    float bestp = -1.0f;
+                    int besti = 0x7fffffff;
+#pragma unroll 1
+                    for (int j = 0; j < NJ; ++j) {
+                        const int n = sl + LPR * j;
+                        if (n < N) {
+                            const float u = live ? ulog[n] : -INFINITY;
+                            const float p = (u == -INFINITY) ? 0.0f : expf((u - mx) - lse);
+                            if (p > bestp) { bestp = p; besti = n; }
+                            if (live) {
+                                if (a.mode != 0) ulog[n] = p;   // probabilities for the sequential CDF below
+                                if (a.tr_probs) a.tr_probs[tro + n] = p;
+                            }
+                        }
+                    }
+                    if (a.mode == 0) {   // greedy: argmax(prob), first maximal index
+#pragma unroll
+                        for (int o = LPR / 2; o; o >>= 1) {
+                            const float ov = __shfl_xor_sync(kFull, bestp, o);
+                            const int oi = __shfl_xor_sync(kFull, besti, o);
+                            if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+                        }
+                        idx = besti;
+                        psel = bestp;
+                    } else {             // inverse-CDF sampling with one (per-row) retry (attention_agent.py:148-167)
+                        __syncwarp();
+                        int sel = -1;
+                        if (sl == 0 && live) {
+                            const long long o = (long long)t * R + row;
+                            for (int draw = 0; draw < 2 && sel < 0; ++draw) {
+                                const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
+                                const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
+                                float cum = 0.0f;   // tf.cumsum: sequential fp32 (masked nodes add exactly 0)
+                                for (int n = 0; n < N; ++n) {
+                                    cum = __fadd_rn(cum, ulog[n]);
+                                    if (cum > u) { sel = n; break; }
+                                }
+                            }
+                        }
+                        if (sel < 0) sel = 0;
+                        idx = __shfl_sync(kFull, sel, sub * LPR);
+                        __syncwarp();
+                        psel = ulog[idx < N ? idx : 0];
+                        __syncwarp();
+                    }
+                } else {
+                    idx = mxi;
+                }
+                if (idx < 0 || idx >= N) idx = 0;   // rows that are not live carry garbage
+                // ---- Env.step (vrptw_utils.py:254-358): demand, load, time, position
+                const float* fsel = frow + idx * D;
+                const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
+                const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
+                const float px = rs[2], py = rs[3];
+                const float d_idx = drow[idx];
+                float nz = rs[13];                       // customers with demand left: sum(demand) > 0  <=>  nz > 0
+                __syncwarp();
+                const float d_sat = fminf(d_idx, load);
+                const float d_new = __fsub_rn(d_idx, d_sat);
+                float nload = __fsub_rn(load, d_sat);
+                const float ts = dist_rn(px, py, sx, sy);
+                float ntime = 0.0f;
+                if (TW) ntime = fmaxf(__fadd_rn(time, ts), sb);
+                const float dep = (idx == n_cust) ? 1.0f : 0.0f;
+                nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
+                if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
+                if (d_idx != 0.0f && d_new == 0.0f) nz -= 1.0f;
+                if (live && sl == 0) drow[idx] = d_new;
+                __syncwarp();
+                const int done_now = (!a.full && idx == n_cust && nz == 0.0f) ? 1 : 0;
+                if (live && sl == 0) {
+                    rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
+                    if (t == 0) { rs[5] = sx; rs[6] = sy; }
+                    else rs[4] = __fadd_rn(rs[4], ts);
+                    reinterpret_cast<int*>(rs)[8] = done_now;
+                    rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz;
+                    a.idx_out[(long long)t * R + row] = idx;
+                    if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
+                }
+                // ---- new mask (vrptw_utils.py:328-348); node features come from L2, eight nodes' loads in flight at a time
+                // (when nobody reads the mask VALUES, a customer without demand or an empty vehicle is masked whatever its time
+                //  window says and its features are not fetched - unless no node at all stays un-masked: then the choice
+                //  depends on the mask counts and the pass is repeated exactly)
+#pragma unroll 1
+                for (int pass = 0; pass < 2; ++pass) {
+                    const bool exact = a.full || a.fin_mask != nullptr || pass == 1;
+                    if (live) {
+#pragma unroll 1
+                        for (int jb = 0; jb < NJ; jb += 8) {
+                            float nx[8], ny[8], ne[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int n = sl + LPR * (jb + j);
+                                const int nn = n < N ? n : N - 1;
+                                const float* fp = frow + nn * D;
+                                nx[j] = ny[j] = ne[j] = 0.0f;
+                                if (TW && nn != n_cust && (exact || (nload != 0.0f && drow[nn] != 0.0f))) {
+                                    nx[j] = ldcg_volatile(fp); ny[j] = ldcg_volatile(fp + 1); ne[j] = ldcg_volatile(fp + 3);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int n = sl + LPR * (jb + j);
+                                const int nn = n < N ? n : N - 1;
+                                const int mm = node_mask<TW>(nn, n_cust, drow[nn], nload, ntime, sx, sy, nx[j], ny[j], ne[j], dep, nz);
+                                if (n < N) mk[n] = (unsigned char)mm;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    const int nun = build_items(lrs, rvalid, was_done || done_now, sub, sl);
+                    if (exact || !__any_sync(kFull, live && !done_now && nun == 0)) break;
+                }
+                warp_done &= __all_sync(kFull, !live || done_now);
+            }
+            if (lane == 0) done_s[warp] = warp_done;
+            VRP_CLK(5);
+        }
+        named_bar(5, NT);
+        int all_done = 1;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) all_done &= done_s[w];
+        VRP_CLK(6);
+        named_bar(5, NT);
+        if (all_done) { ++t; break; }
+    }
+    if (tid == 0) {
+        *stop_s = 1;
+        __threadfence_block();
+        mbar_arrive(bar_x);
+    }
+    const int t_end = t;
+
+    for (int i = 0; i < RPW; ++i) {
+        const int lr = warp * RPW + i;
+        if (lr >= IBv) continue;
+        const long long row = b0 + lr;
+        for (int tt = t_end + lane; tt < T; tt += 32) {
+            a.idx_out[(long long)tt * R + row] = n_cust;
+            if (a.logprob_out) a.logprob_out[(long long)tt * R + row] = 0.0f;
+        }
+        const float* rs = rowst + lr * kRowState;
+        if (lane == 0) a.cost_out[row] = __fadd_rn(rs[4], dist_rn(rs[2], rs[3], rs[5], rs[6]));
+        for (int n = lane; n < N; n += 32) {
+            if (a.fin_demand) a.fin_demand[row * N + n] = dem[lr * NP + n];
+            if (a.fin_mask) a.fin_mask[row * N + n] = (float)maskb[lr * NP + n];
+        }
+        if (lane == 0) {
+            if (a.fin_load) a.fin_load[row] = rs[0];
+            if (a.fin_time) a.fin_time[row] = rs[1];
+        }
+    }
+    if (tid == 0 && a.steps_out) a.steps_out[blockIdx.x] = t_end;
+    if (a.stats) {
+        if (n_eval) atomicAdd(a.stats + 0, n_eval);
+        if (n_rowsteps) atomicAdd(a.stats + 1, n_rowsteps);
+        if (tid == 0) {
+            atomicAdd(a.stats + 2, (unsigned long long)t_end * RB);
+            atomicAdd(a.stats + 3, 1ull);
+        }
+#ifdef VRPB200_PHASE_CLOCKS
+        if (tid == 64 || tid == 384)   // a score warp and a row warp
+            for (int i = 0; i < 12; ++i) atomicAdd(a.stats + 4 + i + (tid == 384 ? 12 : 0), (unsigned long long)pc_[i]);
+#endif
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc_dealloc(tmem_base, kTcCols);
+}
+
+}  // namespace vrpb200

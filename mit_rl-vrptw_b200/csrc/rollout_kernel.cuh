@@ -94,6 +94,8 @@ struct RolloutArgs {
     int full;                // evaluate every node every step, never exit early (trace mode)
     int use_tanh, mask_pointer;
     float capacity, tanh_C, forget_bias;
+    float sumv;              // rollout4: sum_h v_h of the pointer attention
+    float vm2[128];          // rollout4: -2 v_h (read as constant-bank operands)
 };
 
 struct SmemLayout {

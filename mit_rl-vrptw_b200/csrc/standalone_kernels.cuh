@@ -287,11 +287,13 @@ __global__ void __launch_bounds__(512) pipe_peak_kernel(int kind, int iters, flo
 #pragma unroll
     for (int i = 0; i < 16; ++i) x[i] = 0.5f + 0.001f * (threadIdx.x + i);
     if (kind == 0) {
+        // one chain link = the kernel's own sequence rcp(1 + ex2(x)): 2 MUFU + 1 FADD.  (A bare rcp(ex2(x)) is folded by
+        // ptxas into a single MUFU.EX2 of -x and reports twice the real rate.)
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int u = 0; u < 32; ++u) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = rcp_approx(ex2_approx(x[i]));   // 2 MUFU per chain link
+                for (int i = 0; i < 8; ++i) x[i] = rcp_approx(1.0f + ex2_approx(x[i]));
             }
         }
     } else {

@@ -16,6 +16,7 @@
 #include "rollout_kernel.cuh"
 #include "rollout2_kernel.cuh"
 #include "rollout3_kernel.cuh"
+#include "rollout4_kernel.cuh"
 #include "standalone_kernels.cuh"
 
 using namespace vrpb200;
@@ -51,6 +52,8 @@ struct vrpb200_handle {
     cudaStream_t streams[kChunks] = {nullptr, nullptr, nullptr};
     unsigned long long* dev_stats = nullptr;
     int32_t last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float vm2[128];                   // -2 v of the pointer attention and sum v (rollout4 kernel parameters)
+    float sumv = 0.0f;
     int max_smem_optin = 0;
     int num_sms = 0;
 };
@@ -123,7 +126,7 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path < 0 || c.gemm_path > 3) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..3");
+    if (c.gemm_path < 0 || c.gemm_path > 5) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..5");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -361,6 +364,12 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         ra.proj_t_k = d + o.pt_k; ra.proj_t_b = d + o.pt_b;
         ra.proj_q_k = d + o.pq_k; ra.proj_q_b = d + o.pq_b; ra.proj_ref_k = d + o.pr_k; ra.proj_ref_b = d + o.pr_b;
     }
+    {
+        const RawHost& r = rh[natt - 1];
+        double sv = 0.0;
+        for (int hh = 0; hh < H; ++hh) { h->vm2[hh] = -2.0f * r.v[hh]; sv += (double)r.v[hh]; }
+        h->sumv = (float)sv;
+    }
     h->raw.lstm_k = d + o_lstm_k;
     h->raw.lstm_b = d + o_lstm_b;
     h->raw.n_glimpses = c.n_glimpses;
@@ -398,13 +407,40 @@ int launch_rollout3_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int sme
     return 0;
 }
 
+template <int RB, bool TW, int STAGES, int NSW>
+int launch_rollout4_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout4_kernel<RB, TW, STAGES, NSW><<<grid, kV4Threads, smem, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+template <int RB>
+int launch_rollout4_any(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st, int stages, int nsw) {
+    if constexpr (RB <= 48) {
+#define V4(TWv, STv, NSv) launch_rollout4_t<RB, TWv, STv, NSv>(h, a, grid, smem, st)
+        if (nsw == 12) return h->tw ? (stages == 3 ? V4(true, 3, 12) : V4(true, 2, 12)) : (stages == 3 ? V4(false, 3, 12) : V4(false, 2, 12));
+        return h->tw ? (stages == 3 ? V4(true, 3, 16) : V4(true, 2, 16)) : (stages == 3 ? V4(false, 3, 16) : V4(false, 2, 16));
+#undef V4
+    } else {
+        return fail(h, VRPB200_E_ARG, "rollout4 supports rows_per_cta <= 48");
+    }
+}
+
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
-    const bool v3 = c.gemm_path == 3;
+    const bool v4 = c.gemm_path >= 4 && a.mode != 2;             // rollout4: greedy / stochastic; beam search stays on rollout3
+    const int nsw = c.gemm_path == 5 ? 12 : 16;                  // 5: four row warps stream the per-row tail behind the scores
+    const bool v3 = c.gemm_path == 3 || (c.gemm_path >= 4 && !v4);
     const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
     int stages3 = 2;
     auto smem_of = [&](int rb) {
+        if (v4) {
+            if (rb > 48) return 1 << 30;                        // TMEM: q^T and the score buffers need their own columns
+            stages3 = make_layout4(rb, c.n_nodes, 3, nsw).total <= h->max_smem_optin ? 3 : 2;
+            return make_layout4(rb, c.n_nodes, stages3, nsw).total;
+        }
         if (v3) {
             if (rb < a.W) return 1 << 30;                       // every beam of an instance lives in one CTA
             const int ib = rb / a.W, np = (c.n_nodes + 3) / 4 * 4;
@@ -435,12 +471,13 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
         return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, total, h->max_smem_optin);
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
-    h->last_launch[0] = (int)grid; h->last_launch[1] = v3 ? kV3Threads : tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
+    h->last_launch[0] = (int)grid; h->last_launch[1] = v4 ? kV4Threads : v3 ? kV3Threads : tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
     h->last_launch[4] = 1; h->last_launch[5] = c.gemm_path;
     int rc = 0;
 #define DISPATCH(rb)                                                                                   \
     case rb:                                                                                           \
-        if (v3) { if (stages3 == 3) rc = h->tw ? launch_rollout3_t<rb, true, 3>(h, a, (int)grid, total, st)    \
+        if (v4) { rc = launch_rollout4_any<rb>(h, a, (int)grid, total, st, stages3, nsw); }                     \
+        else if (v3) { if (stages3 == 3) rc = h->tw ? launch_rollout3_t<rb, true, 3>(h, a, (int)grid, total, st)    \
                                                : launch_rollout3_t<rb, false, 3>(h, a, (int)grid, total, st);  \
                   else rc = h->tw ? launch_rollout3_t<rb, true, 2>(h, a, (int)grid, total, st)                 \
                                   : launch_rollout3_t<rb, false, 2>(h, a, (int)grid, total, st); }             \
@@ -472,7 +509,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     if (!d_input || !d_cost || !d_idx) return fail(h, VRPB200_E_ARG, "d_input, d_idx and d_cost are required");
     if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
     if (mode != VRPB200_GREEDY && mode != VRPB200_STOCHASTIC && mode != VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "bad mode %d", mode);
-    if (mode == VRPB200_BEAM && h->cfg.gemm_path != 3) return fail(h, VRPB200_E_ARG, "beam search needs the rollout3 kernel (gemm_path 3)");
+    if (mode == VRPB200_BEAM && h->cfg.gemm_path < 3) return fail(h, VRPB200_E_ARG, "beam search needs the rollout3 kernel (gemm_path 3 or 4)");
     if (mode == VRPB200_BEAM && (beam_width < 1 || beam_width > 64)) return fail(h, VRPB200_E_ARG, "beam_width outside [1,64]");
     if (mode == VRPB200_BEAM && trace && (trace->d_logits || trace->d_probs || trace->d_masks) && false) return VRPB200_E_ARG;
     if (h->cfg.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "n_glimpses > 0 is not implemented by the fused kernel yet (use decode_step)");
@@ -498,6 +535,8 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.seed = seed; a.B = B; a.row_base = row_base; a.W = mode == VRPB200_BEAM ? beam_width : 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
     a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
+    a.sumv = h->sumv;
+    memcpy(a.vm2, h->vm2, sizeof a.vm2);
     return launch_rollout(h, a, (cudaStream_t)stream);
 }
 

@@ -19,7 +19,7 @@ eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))
 x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2, ups=bool(os.environ.get("UPS"))).astype(np.float32)).cuda()
 eng.rollout(x)
-stats = torch.zeros(16, dtype=torch.int64, device="cuda")
+stats = torch.zeros(32, dtype=torch.int64, device="cuda")
 tr = L.Trace(); tr.d_stats = stats.data_ptr()
 idx = torch.empty((eng.T, B), dtype=torch.int32, device="cuda"); cost = torch.empty(B, device="cuda")
 rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 0, 1, None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
@@ -30,6 +30,15 @@ blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
 names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epilogue", "C1 scores", "C2 select/env"] if gemm == "tc3" else
          ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"])
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
-for n, v in zip(names, s[4:10]):
-    print(f"  {n:30s} {v / blocksteps:10.0f} clk/step")
-print(f"  total {s[4:10].sum() / blocksteps:.0f} clk/step")
+if gemm in ("tc4", "tc4s"):
+    names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
+             "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop"]
+    for who, o in (("score warp 2", 4), ("row warp 12", 16)):
+        print(" ", who)
+        for n, v in zip(names, s[o:o + len(names)]):
+            print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
+        print(f"    total {s[o:o + 12].sum() / blocksteps:.0f} clk/step")
+    sys.exit(0)
+for n, v in zip(names, s[4:4 + len(names)]):
+    print(f"  {n:40s} {v / blocksteps:10.0f} clk/step")
+print(f"  total {s[4:16].sum() / blocksteps:.0f} clk/step")
