@@ -20,10 +20,10 @@
 
 namespace vrpb200 {
 
-constexpr int kV4Threads = 576;   // 16 compute warps + weight feeder warp + MMA issuer warp
+constexpr int kV4Threads = 640;   // 16 compute warps + weight feeder warp + LSTM/query MMA issuer warp + 2 score-MMA issuer warps
 
 struct Smem4 {
-    int ring, X, qq, F, logits, items, bc, vsm, dem, mask, rs, meta, bar, total, stages;
+    int ring, X, qq, F, logits, items, alive, bc, vsm, dem, mask, rs, meta, bar, total, stages;
 };
 
 __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw) {
@@ -34,16 +34,18 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
     L.ring = off;   off += stages * kSlabBytes;
     L.X = off;      off += 2 * RB * kH * 4;
     L.qq = off;     off += RB * kH * 4;
-    L.F = off;      off += (nsw / 4) * 2 * kC1TileBytes;
+    L.F = off;      off += 4 * 2 * kC1TileBytes;               // nsw 16: 4 groups x 1 F tile; nsw 8: 2 groups x 2 F tiles
+    (void)nsw;
     L.logits = off; off += RB * NP * 4;
     L.items = off;  off += align_up(RB * NP, 16);             // node ids of the items of every row
+    L.alive = off;  off += align_up(RB * NP, 16);             // node ids of the customers with demand left, per row
     L.bc = off;     off += 2 * 4096;
     L.vsm = off;    off += 512;                               // -2 v
     L.dem = off;    off += RB * NP * 4;
     L.mask = off;   off += align_up(RB * NP, 16);
     L.rs = off;     off += RB * kRowState * 4;
-    L.meta = off;   off += align_up((RB + 68 + RB + 64 + 20) * 4, 16);   // nact[RB], off[<=65 (+pad)], flags[RB], tilecnt[64], done[16], stop
-    L.bar = off;    off += 320;
+    L.meta = off;   off += align_up((RB + 68 + RB + RB + 20) * 4, 16);   // nact[RB], off[<=65 (+pad)], flags[RB], nalive[RB], done[16], stop
+    L.bar = off;    off += 320 + 64 * 8;                      // ... + one mbarrier per tile of the step (row warps wait on them)
     L.total = off;
     return L;
 }
@@ -68,6 +70,9 @@ VRP_DEVINL void tc_ld_wait32(uint32_t (&r)[32]) {
                  :
                  : "memory");
 }
+VRP_DEVINL void mbar_arrive_n(uint32_t bar, uint32_t n) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
+}
 VRP_DEVINL float ldcg_volatile(const float* p) {
     float v;
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
@@ -75,16 +80,21 @@ VRP_DEVINL float ldcg_volatile(const float* p) {
 }
 VRP_DEVINL int lds_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
-// NSW = number of score warps: 12 -> warps 12..15 are row warps that stream the per-row tail behind C1;
-//                               16 -> every warp scores, then every warp runs the per-row tail (lock-step)
+// NSW = number of score warps:
+//   16 -> every warp scores (4 groups, 2 TMEM quarter buffers each, the MMAs are issued by a thread of the group), then
+//         every warp runs the per-row tail (lock-step);
+//    8 -> warps 0..7 score (2 groups; 4 TMEM quarter buffers and 2 F tiles each, so the MMAs of the NEXT tile are in
+//         flight during the arithmetic of this one; they are issued by two dedicated warps, 18 and 19, and a score warp
+//         never waits for its peers), warps 8..15 are row warps that stream the per-row tail behind the scores
 template <int RB, bool TW, int STAGES, int NSW>
 __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_constant__ RolloutArgs a) {
     constexpr int NT = 512, RPW = RB / 16, RPT = RB / 4, FD = TW ? 4 : 2;
     constexpr int NG = NSW / 4;                                  // score groups, 64 TMEM columns each
-    constexpr int kQCol = NSW == 12 ? 192 : 256 + 4 * RB;        // q^T: its own columns
+    constexpr int kQCol = 256 + 4 * RB;                          // q^T: its own columns
     constexpr int kGCol = 256;                                   // gates^T: tile m at kGCol + RB m
-    static_assert(NSW == 12 || (NSW == 16 && RB <= 48), "TMEM columns");
-    constexpr int LPR = 8, NB = RB / 16;   // row warps: lanes per row, batches of 16 rows
+    static_assert(NSW == 8 || NSW == 16, "score warps");
+    constexpr int LPR = 8;                                       // lanes per row in the per-row tail
+    constexpr int NBT = NSW == 16 ? 1 : (RB + 31) / 32;          // row warps: batches of (up to) 32 rows
     static_assert(RB % 16 == 0 && RB <= 48, "rows");
     extern __shared__ __align__(128) unsigned char smem[];
     const int N = a.N, NP = align_up(N, 4), T = a.T, n_cust = a.n_cust;
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     unsigned char* ftile = smem + L.F;
     float* logits = reinterpret_cast<float*>(smem + L.logits);
     unsigned char* items = smem + L.items;
+    unsigned char* alive = smem + L.alive;
     float* vsm = reinterpret_cast<float*>(smem + L.vsm);
     float* dem = reinterpret_cast<float*>(smem + L.dem);
     unsigned char* maskb = smem + L.mask;
@@ -101,12 +112,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     int* nact_s = reinterpret_cast<int*>(smem + L.meta);
     int* off_s = nact_s + RB;            // [RB + 1] exclusive prefix of nact (this step)
     int* flag_s = off_s + 68;            // [RB] every node of the row is an item
-    int* tilecnt = flag_s + RB;          // [64] warps that have finished tile i in this step
-    int* done_s = tilecnt + 64;          // [16] per warp: every row of the warp is finished
+    int* nalive_s = flag_s + RB;         // [RB] customers with demand left
+    int* done_s = nalive_s + RB;         // [16] per warp: every row of the warp is finished
     volatile int* stop_s = done_s + 16;
     const uint32_t bar0 = smem_u32(smem + L.bar);
     const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, tmem_slot = bar0 + 120,
-                   bar_grp = bar0 + 128;   // group g at +40 g: full[0], full[1] (MMA commit), free[0], free[1] (4 warps copied the buffer), F ready (4 warps)
+                   bar_tile = bar0 + 320, bar_grp = bar0 + 128;   // group g at +40 g: full[0], full[1] (MMA commit), free[0], free[1] (4 warps copied the buffer), F ready (4 warps)
     const uint32_t ring_u32 = smem_u32(smem + L.ring), bc_u32 = smem_u32(smem + L.bc);
     const uint32_t x_hi = smem_u32(xt), x_lo = x_hi + RB * kH * 4;
 
@@ -121,10 +132,18 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_q, 1); mbar_init(bar_g, 1); mbar_init(bar_x, 1);
-        for (int g = 0; g < NG; ++g) {
-            mbar_init(bar_grp + 40 * g, 1); mbar_init(bar_grp + 40 * g + 8, 1);
-            mbar_init(bar_grp + 40 * g + 16, 4); mbar_init(bar_grp + 40 * g + 24, 4); mbar_init(bar_grp + 40 * g + 32, 4);
+        if (NSW == 16) {
+            for (int g = 0; g < 4; ++g) {   // per group: full[2] (MMA commit), free[2] (4 warps copied the buffer), F ready (4 warps)
+                mbar_init(bar_grp + 40 * g, 1); mbar_init(bar_grp + 40 * g + 8, 1);
+                mbar_init(bar_grp + 40 * g + 16, 4); mbar_init(bar_grp + 40 * g + 24, 4); mbar_init(bar_grp + 40 * g + 32, 4);
+            }
+        } else {
+            for (int g = 0; g < 2; ++g) {   // per group: full[4], free[4], F ready[2]
+                for (int q = 0; q < 4; ++q) { mbar_init(bar_grp + 80 * g + 8 * q, 1); mbar_init(bar_grp + 80 * g + 32 + 8 * q, 4); }
+                mbar_init(bar_grp + 80 * g + 64, 4); mbar_init(bar_grp + 80 * g + 72, 4);
+            }
         }
+        for (int i = 0; i < 64; ++i) mbar_init(bar_tile + 8 * i, 4);   // 4 arrivals per step: the 4 warps that scored the tile
         *stop_s = 0;
         for (int w = 0; w < 16; ++w) done_s[w] = 1;
         fence_mbar_init();
@@ -229,6 +248,30 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             }
             if (step > 0) mbar_wait(bar_g, (step - 1) & 1);
         }
+        else if (NSW == 8 && warp >= 18 && lane == 0) {
+            // ---- score-MMA issuer of group g: one tile per "F ready"; quarter q goes to TMEM buffer q once the four score
+            //      warps have copied the previous tile's quarter q out of it
+            const int g = warp - 18;
+            const uint32_t bfull = bar_grp + 80 * g, bfree = bfull + 32, bfrdy = bfull + 64;
+            const uint32_t fbase = smem_u32(smem + L.F) + g * 4 * kC1TileBytes;
+            for (uint32_t tc = 0;; ++tc) {
+                const uint32_t fb = tc & 1;
+                mbar_wait(bfrdy + 8 * fb, (tc >> 1) & 1);
+                if (*stop_s) break;
+                const uint64_t dfh = tc_desc(fbase + fb * 2 * kC1TileBytes, 128, 256), dfl = tc_desc(fbase + fb * 2 * kC1TileBytes + kC1TileBytes, 128, 256);
+#pragma unroll 1
+                for (int q = 0; q < 4; ++q) {
+                    if (tc > 0) mbar_wait(bfree + 8 * q, (tc - 1) & 1);
+                    tc_fence_after();
+                    const uint64_t dbh = tc_desc(bc_u32 + q * 1024, 128, 256), dbl = tc_desc(bc_u32 + 4096 + q * 1024, 128, 256);
+                    const uint32_t d = tmem_base + 128 * g + 32 * q;
+                    tc_mma_tf32(d, dfl, dbh, idescQ, 0);
+                    tc_mma_tf32(d, dfh, dbl, idescQ, 1);
+                    tc_mma_tf32(d, dfh, dbh, idescQ, 1);
+                    tc_commit(bfull + 8 * q);
+                }
+            }
+        }
         __syncwarp();
         tc_fence_before();
         __syncthreads();
@@ -265,6 +308,41 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         return nun;
     };
 
+    // list of the customers with demand left, from the row's demands (8-lane sub-warp; all four sub-warps together)
+    auto build_alive = [&](int lrs, bool rvalid, int sub, int sl) {
+        const float* drow = dem + lrs * NP;
+        unsigned char* al = alive + lrs * NP;
+        int cnt = 0;
+#pragma unroll 1
+        for (int j = 0; j < NJ; ++j) {
+            const int n = sl + LPR * j;
+            const bool keep = rvalid && n < N && n != n_cust && drow[n] != 0.0f;
+            const unsigned bits = (__ballot_sync(kFull, keep) >> (8 * sub)) & 0xffu;
+            if (keep) al[cnt + __popc(bits & ((1u << sl) - 1))] = (unsigned char)n;
+            cnt += __popc(bits);
+        }
+        if (sl == 0 && rvalid) nalive_s[lrs] = cnt;
+    };
+    // exact mask of every node of a row from its state: Env.reset's mask before the first step (vrptw_utils.py:233-240),
+    // Env.step's afterwards (:328-348).  Used when the fast per-row tail (which keeps no mask bytes) hands a row over.
+    auto recompute_masks = [&](int lrs, bool rvalid, int sl, int step) {
+        if (!rvalid) return;
+        const float* rs = rowst + lrs * kRowState;
+        const float* drow = dem + lrs * NP;
+        const float* frow = gfeat + (size_t)lrs * N * D;
+        unsigned char* mk = maskb + lrs * NP;
+        for (int n = sl; n < N; n += LPR) {
+            int mm;
+            if (step == 0) mm = (n == n_cust) ? 1 : (drow[n] == 0.0f ? 1 : 0);
+            else {
+                float nx = 0.f, ny = 0.f, ne = 0.f;
+                if (TW) { nx = __ldcg(frow + n * D); ny = __ldcg(frow + n * D + 1); ne = __ldcg(frow + n * D + 3); }
+                mm = node_mask<TW>(n, n_cust, drow[n], rs[0], TW ? rs[1] : 0.0f, rs[2], rs[3], nx, ny, ne, rs[15], rs[13]);
+            }
+            mk[n] = (unsigned char)mm;
+        }
+    };
+
     for (int i = 0; i < RPW; ++i) {   // Env.reset (vrptw_utils.py:199-252) + prologue
         const int lr = warp * RPW + i;
         if (lane == 0) { nact_s[lr] = 0; flag_s[lr] = 0; }
@@ -280,7 +358,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         const float* fdep = gfeat + (size_t)(lr * N + n_cust) * D;
         if (lane == 0) {
             float* rs = rowst + lr * kRowState;
-            rs[13] = (float)nzc;
+            rs[13] = (float)nzc; rs[15] = 0.0f;
             rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = __ldcg(fdep + 0); rs[3] = __ldcg(fdep + 1); rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
             reinterpret_cast<int*>(rs)[8] = 0;
             rs[9] = __ldcg(fdep + 0); rs[10] = __ldcg(fdep + 1); rs[11] = TW ? __ldcg(fdep + 2) : 0.0f; rs[12] = TW ? __ldcg(fdep + 3) : 0.0f;
@@ -290,7 +368,11 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     if (warp < RB / 4) {
         const int sub = lane >> 3, sl = lane & 7, lr = 4 * warp + sub;
         build_items(lr < IBv ? lr : 0, lr < IBv, false, sub, sl);
+        build_alive(lr < IBv ? lr : 0, lr < IBv, sub, sl);
     }
+    // the fast per-row tail serves plain greedy decoding when nobody reads probabilities, log-probabilities or masks
+    const bool fastk = a.mode == 0 && !a.full && a.mask_pointer && !a.use_tanh && a.logprob_out == nullptr && a.fin_mask == nullptr &&
+                       a.tr_logits == nullptr && a.tr_probs == nullptr && a.tr_masks == nullptr;
     const int unit = 32 * sp + lane;
     float cst[RPT];
 #pragma unroll
@@ -298,7 +380,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     named_bar(5, NT);
 
 #ifdef VRPB200_PHASE_CLOCKS
-    long long pc_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc_last_ = clock64();
+    long long pc_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc_last_ = clock64();
 #endif
     // C1: the two TMEM buffers of a group are used strictly in turn, so one counter of consumed quarters (every thread)
     // and one of issued quarters (issuer thread) give buffer index and mbarrier parity
@@ -324,7 +406,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 if (lane + 32 < RB) off_s[lane + 32] = tot0 + s1 - n1;
                 if (lane == 0) off_s[RB] = m_tot;
             }
-            if (tid < 64) tilecnt[tid] = 0;
+            if (tid < 64 && tid >= ((m_tot + 127) >> 7)) mbar_arrive_n(bar_tile + 8 * tid, 4);   // tiles that do not exist in this step
         }
         // ================= LSTM epilogue: gates = gates^T(TMEM, h part) + x part + bias ; c, h' ; h' -> X ==========
         {
@@ -391,15 +473,17 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
         VRP_CLK(1);
 
-        // ================= C1 set-up (score warps): first tile of every group, staged while the query GEMM runs ========
+        // ================= C1 set-up (score warps): first tile(s) of every group, staged while the query GEMM runs ======
         const int ntiles = (m_tot + 127) >> 7;
-        const int g = ub;                                                // score group (warps 0..11)
-        unsigned char* fhi = ftile + (g < NG ? g : 0) * 2 * kC1TileBytes;
-        const uint32_t f_hi = smem_u32(fhi), f_lo = f_hi + kC1TileBytes;
-        const uint32_t d_g = tmem_base + 64 * g;
-        const uint32_t bfull = bar_grp + 40 * (g < NG ? g : 0), bfree = bfull + 16, bfrdy = bfull + 32;
+        const int g = ub;                                                // score group
         const int m = 32 * sp + lane;
-        const bool issuer = (sp == 0 && lane == 0);
+        // NSW 16: group g owns F tile g and TMEM columns 64 g (2 buffers x 32); NSW 8: F tiles 2g, 2g+1, columns 128 g (4 x 32)
+        unsigned char* fgrp = ftile + (g < NG ? g : 0) * (NSW == 16 ? 2 : 4) * kC1TileBytes;
+        const uint32_t f_hi = smem_u32(fgrp), f_lo = f_hi + kC1TileBytes;
+        const uint32_t d_g = tmem_base + 64 * g;
+        const uint32_t bfull = bar_grp + (NSW == 16 ? 40 : 80) * (g < NG ? g : 0), bfree = bfull + (NSW == 16 ? 16 : 32),
+                       bfrdy = bfull + (NSW == 16 ? 32 : 64);
+        const bool issuer = (NSW == 16 && sp == 0 && lane == 0);
         // item `it` of the step -> (row, node): binary search in the row offsets, then the row's node list
         auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5]) {
             const int it = tile * 128 + m;
@@ -422,7 +506,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 f[4] = dem[r * NP + n];
             }
         };
-        auto store_F = [&](const float (&f)[5]) {
+        auto store_F = [&](unsigned char* fhi, const float (&f)[5]) {
             float hi[5], lo[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) { hi[k] = tf32_rna(f[k]); lo[k] = f[k] - hi[k]; }
@@ -433,7 +517,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             *reinterpret_cast<float4*>(fhi + kC1TileBytes + off + 128) = make_float4(lo[4], 0.0f, 0.0f, 0.0f);
             fence_proxy_async();
         };
-        auto issue_quarter = [&](int q) {   // issuer thread only: E[:, 32q .. 32q+31] -> the next TMEM buffer in turn
+        auto issue_quarter = [&](int q) {   // NSW 16, issuer thread only: E[:, 32q .. 32q+31] -> the next TMEM buffer in turn
             const uint32_t b = c1_ni & 1, k = c1_ni >> 1;
             ++c1_ni;
             if (k > 0) mbar_wait(bfree + 8 * b, (k - 1) & 1);   // the 4 warps have copied its previous content
@@ -445,20 +529,62 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             tc_mma_tf32(d_g + 32 * b, dfh, dbh, idescQ, 1);
             tc_commit(bfull + 8 * b);
         };
-        int r_cur = 0, n_cur = 0;
-        bool v_cur = false;
+        // 32 hidden units of one item: acc += sum_h w_h / (1 + 2^(E_h + base'_h)), w = -2 v, 16 independent elements at a
+        // time, ONE reciprocal per 4 elements:  (w0 t1 + w1 t0) t2 t3 + (w2 t3 + w3 t2) t0 t1  over  t0 t1 t2 t3
+        // (t = 1 + 2^min(arg, 30) <= 2^30 + 1: the product cannot overflow, and tanh is 1.0f exactly from arg = 26 on)
+        auto quarter_arith = [&](const uint32_t (&cur)[32], const float* bq, const float* vq, float& acc0, float& acc1) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float e[16];
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bq + 16 * hf + 4 * k4);
+                    e[4 * k4 + 0] = __uint_as_float(cur[16 * hf + 4 * k4 + 0]) + b4.x;
+                    e[4 * k4 + 1] = __uint_as_float(cur[16 * hf + 4 * k4 + 1]) + b4.y;
+                    e[4 * k4 + 2] = __uint_as_float(cur[16 * hf + 4 * k4 + 2]) + b4.z;
+                    e[4 * k4 + 3] = __uint_as_float(cur[16 * hf + 4 * k4 + 3]) + b4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) e[i] = 1.0f + ex2_approx(fminf(e[i], 30.0f));
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 v4 = *reinterpret_cast<const float4*>(vq + 16 * hf + 4 * k4);
+                    const float t0 = e[4 * k4], t1 = e[4 * k4 + 1], t2 = e[4 * k4 + 2], t3 = e[4 * k4 + 3];
+                    const float p01 = t0 * t1, p23 = t2 * t3;
+                    const float n01 = fmaf(v4.x, t1, v4.y * t0), n23 = fmaf(v4.z, t3, v4.w * t2);
+                    const float num = fmaf(n01, p23, n23 * p01);
+                    const float r = rcp_approx(p01 * p23);
+                    if (k4 & 1) acc1 = fmaf(num, r, acc1); else acc0 = fmaf(num, r, acc0);
+                }
+            }
+        };
+        int r_cur = 0, n_cur = 0, r_nx = 0, n_nx = 0;
+        bool v_cur = false, v_nx = false;
         const bool scoring = warp < NSW && g < ntiles;
         if (scoring) {
             float fc[5];
             load_item(g, r_cur, n_cur, v_cur, fc);
-            store_F(fc);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bfrdy);
-            if (issuer) {
-                mbar_wait(bfrdy, c1_nf & 1); ++c1_nf;      // the four warps of the group have written their part of F
-                issue_quarter(0); issue_quarter(1);
+            if (NSW == 16) {
+                store_F(fgrp, fc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bfrdy);
+                if (issuer) {
+                    mbar_wait(bfrdy, c1_nf & 1); ++c1_nf;      // the four warps of the group have written their part of F
+                    issue_quarter(0); issue_quarter(1);
+                }
+                __syncwarp();
+            } else {   // the F tiles of the group's first two tiles of the step; warp 18 + g issues the MMAs
+                float f2[5];
+                load_item(g + NG, r_nx, n_nx, v_nx, f2);
+                store_F(fgrp + (c1_nq & 1) * 2 * kC1TileBytes, fc);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bfrdy + 8 * (c1_nq & 1));
+                if (g + NG < ntiles) {
+                    store_F(fgrp + ((c1_nq + 1) & 1) * 2 * kC1TileBytes, f2);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bfrdy + 8 * ((c1_nq + 1) & 1));
+                }
             }
-            __syncwarp();
         }
         VRP_CLK(2);
         // ================= query epilogue: base'[row][unit] = 2log2e (q + b + load g_ld + time g_t) ===================
@@ -488,9 +614,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
 
         if (warp < NSW) {
             // ================= C1: scores =================================================================
-            if (scoring) {
-                int r_nx, n_nx;
-                bool v_nx;
+            if (a.tune > 0 && (g & 1)) __nanosleep(a.tune);   // experiment: odd groups start later (warps of one SM sub-partition out of phase)
+            if (scoring && NSW == 16) {
                 float fn[5];
 #pragma unroll 1
                 for (int tile = g; tile < ntiles; tile += NG) {
@@ -507,7 +632,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         tc_fence_after();
                         VRP_CLK(7);
                         if (q == 3 && has_next) {   // every MMA of this tile has completed: the F tile may be replaced
-                            store_F(fn);
+                            store_F(fgrp, fn);
                             __syncwarp();
                             if (lane == 0) mbar_arrive(bfrdy);
                             if (issuer) { mbar_wait(bfrdy, c1_nf & 1); ++c1_nf; issue_quarter(0); }
@@ -525,74 +650,84 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         }
                         __syncwarp();
                         VRP_CLK(9);
-                        const float* bq = brow + 32 * q;
-                        const float* vq = vsm + 32 * q;
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {    // 16 independent elements at a time
-                            float e[16];
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 b4 = *reinterpret_cast<const float4*>(bq + 16 * hf + 4 * k4);
-                                e[4 * k4 + 0] = __uint_as_float(cur[16 * hf + 4 * k4 + 0]) + b4.x;
-                                e[4 * k4 + 1] = __uint_as_float(cur[16 * hf + 4 * k4 + 1]) + b4.y;
-                                e[4 * k4 + 2] = __uint_as_float(cur[16 * hf + 4 * k4 + 2]) + b4.z;
-                                e[4 * k4 + 3] = __uint_as_float(cur[16 * hf + 4 * k4 + 3]) + b4.w;
-                            }
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) e[i] = 1.0f + ex2_approx(fminf(e[i], 30.0f));   // t = 1 + 2^arg <= 2^30 + 1
-                            // sum_j w_j / t_j over 4 elements with ONE reciprocal (w = -2 v):
-                            //   (w0 t1 + w1 t0) t2 t3 + (w2 t3 + w3 t2) t0 t1  over  t0 t1 t2 t3       (no overflow: t <= 2^30 + 1)
-#pragma unroll
-                            for (int k4 = 0; k4 < 4; ++k4) {
-                                const float4 v4 = *reinterpret_cast<const float4*>(vq + 16 * hf + 4 * k4);
-                                const float t0 = e[4 * k4], t1 = e[4 * k4 + 1], t2 = e[4 * k4 + 2], t3 = e[4 * k4 + 3];
-                                const float p01 = t0 * t1, p23 = t2 * t3;
-                                const float n01 = fmaf(v4.x, t1, v4.y * t0), n23 = fmaf(v4.z, t3, v4.w * t2);
-                                const float num = fmaf(n01, p23, n23 * p01);
-                                const float r = rcp_approx(p01 * p23);
-                                if (k4 & 1) acc1 = fmaf(num, r, acc1); else acc0 = fmaf(num, r, acc0);
-                            }
-                        }
+                        quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
                         VRP_CLK(10);
                     }
                     // u = sum_h v_h tanh(.) = sum_h v_h - sum_h 2 v_h / (1 + 2^arg)
                     if (v_cur) logits[r_cur * NP + n_cur] = a.sumv + (acc0 + acc1);
                     n_eval += v_cur ? 1 : 0;
-                    if (NSW != 16) {   // tell the row warps
-                        __syncwarp();
-                        if (lane == 0) {
-                            __threadfence_block();
-                            atomicAdd(tilecnt + tile, 1);
-                        }
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished (release: logits visible)
                     r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                }
+            }
+            if (scoring && NSW == 8) {
+                // c1_nq counts the tiles of this group (all steps): tile k uses F tile k & 1, its quarter q TMEM buffer q
+                int r_n2 = 0, n_n2 = 0;
+                bool v_n2 = false;
+                float fn[5];
+#pragma unroll 1
+                for (int tile = g; tile < ntiles; tile += NG) {
+                    load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn);      // two tiles ahead: in flight during the arithmetic below
+                    const float* brow = qq + r_cur * kH;
+                    const uint32_t par = c1_nq & 1;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll 1
+                    for (int q = 0; q < 4; ++q) {
+                        VRP_CLK(11);
+                        mbar_wait(bfull + 8 * q, par);
+                        tc_fence_after();
+                        VRP_CLK(7);
+                        uint32_t cur[32];
+                        tc_ld32_issue(tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * g + 32 * q, cur);
+                        tc_ld_wait32(cur);
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(bfree + 8 * q);      // warp 18 + g may send the next tile's quarter q here
+                        __syncwarp();
+                        VRP_CLK(9);
+                        quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
+                        VRP_CLK(10);
+                    }
+                    if (v_cur) logits[r_cur * NP + n_cur] = a.sumv + (acc0 + acc1);
+                    n_eval += v_cur ? 1 : 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // tell the row warps (release: the logits are visible)
+                    if (tile + 2 * NG < ntiles) {   // all four MMAs of this tile are complete: its F tile takes the tile two ahead
+                        store_F(fgrp + par * 2 * kC1TileBytes, fn);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bfrdy + 8 * par);
+                    }
+                    VRP_CLK(8);
+                    ++c1_nq;
+                    r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                    r_nx = r_n2; n_nx = n_n2; v_nx = v_n2;
                 }
             }
             VRP_CLK(5);
         }
-        if (NSW == 16) named_bar(5, NT);   // lock-step variant: every logit of the step is in place
-        if (NSW == 16 ? warp < RB / 4 : warp >= 12) {
+        if (NSW == 16 ? warp < RB / 4 : warp >= 8) {
             // ================= per-row tail: log-softmax, choice, Env.step, mask, next item list ==========================
             // 8 lanes per row, lane sl owns nodes sl, sl + 8, ...; masked logits and probabilities live in the row's logits
             // slots (shared memory), so no per-lane arrays are needed and every node loop stays rolled.
-            // NSW == 12: warps 12..15 stream batches of 16 rows behind the score warps; NSW == 16: warp w owns rows 4w..4w+3
+            // NSW == 8: warps 8..15 stream batches of up to 32 rows behind the score warps; NSW == 16: warp w owns rows 4w..4w+3
             const int sub = lane >> 3, sl = lane & 7;
             int warp_done = 1;
 #pragma unroll 1
-            for (int bt = 0; bt < (NSW == 16 ? 1 : NB); ++bt) {
-                const int r0 = NSW == 16 ? 4 * warp : 16 * bt + 4 * (warp - 12);
+            for (int bt = 0; bt < NBT; ++bt) {
+                const int nrow = NSW == 16 ? RB : min(32, RB - 32 * bt);   // rows of this batch, spread evenly over the row warps
+                const int rpw = NSW == 16 ? 4 : nrow / 8;                  // rows per warp (4 or 2)
+                const int r0 = NSW == 16 ? 4 * warp : 32 * bt + rpw * (warp - 8);
                 const int lr = r0 + sub;
-                if (NSW != 16) {   // wait for every tile that holds items of rows r0 .. r0+3
-                    const int i0 = off_s[r0], i1 = off_s[r0 + 4];
+                {   // wait for every tile that holds items of rows r0 .. r0+rpw-1
+                    const int i0 = off_s[r0], i1 = off_s[r0 + rpw];
                     if (i1 > i0) {
                         const int tl = (i1 - 1) >> 7;
-                        for (int tile = i0 >> 7; tile <= tl; ++tile)
-                            while (lds_volatile(tilecnt + tile) < 4) __nanosleep(40);
-                        __threadfence_block();
+                        for (int tile = i0 >> 7; tile <= tl; ++tile) mbar_wait(bar_tile + 8 * tile, t & 1);
                     }
                     __syncwarp();
                 }
-                const bool rvalid = lr < IBv;
+                VRP_CLK(12);
+                const bool rvalid = sub < rpw && lr < IBv;
                 const int lrs = rvalid ? lr : 0;
                 float* rs = rowst + lrs * kRowState;
                 const long long row = b0 + lrs;
@@ -611,177 +746,303 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 const int fl = flag_s[lrs];
                 const bool tracing = a.tr_logits || a.tr_probs || a.tr_masks;
                 const long long tro = ((long long)t * R + row) * N;
-                // ---- masked logits (decode_step.py:231-232) back into the row's slots; maximum, its first index, runner-up
-                float mx = -INFINITY, second = -INFINITY;
-                int mxi = 0x7fffffff;
+                int done_now = 0;
+                bool handled = false;
+                if (fastk) {
+                    // ============ fast tail (plain greedy decoding): the choice is the arg-max of the logits over the row's
+                    // items; feasibility is only evaluated for the customers that still have demand, whose list (and the item
+                    // list of the next step) is rebuilt by compaction; no mask bytes, no softmax.  A row with a near-tie of its
+                    // two best logits, or without any un-masked node, goes through the exact tail below.
+                    const int nal = live ? nalive_s[lrs] : 0;
+                    unsigned char* al = alive + lrs * NP;
+                    unsigned char* it = items + lrs * NP;
+                    // (0) features of this lane's first 8 customers: issued now, used after the choice
+                    int pn[8];
+                    float pxx[8], pyy[8], pee[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = sl + LPR * j;
+                        pn[j] = k < nal ? (int)al[k] : -1;
+                        pxx[j] = pyy[j] = pee[j] = 0.0f;
+                        if (TW && pn[j] >= 0) {
+                            const float* fp = frow + pn[j] * D;
+                            pxx[j] = ldcg_volatile(fp); pyy[j] = ldcg_volatile(fp + 1); pee[j] = ldcg_volatile(fp + 3);
+                        }
+                    }
+                    // (1) arg-max (first index on ties) and runner-up over the items
+                    float mx = -INFINITY, second = -INFINITY;
+                    int mxi = 0x7fffffff;
+                    const int na = live ? nact_s[lrs] : 0;
 #pragma unroll 2
-                for (int j = 0; j < NJ; ++j) {
-                    const int n = sl + LPR * j;
-                    float u = -INFINITY;
-                    if (n < N && live) {
-                        const int mm = mk[n];
-                        if (fl || mm == 0) {
-                            u = ulog[n];
-                            if (a.use_tanh) u = a.tanh_C * tanhf(u);
-                            if (a.mask_pointer) u = __fsub_rn(u, __fmul_rn(kBig, (float)mm));
-                        }
-                        ulog[n] = u;
-                        if (tracing) {
-                            if (a.tr_logits) a.tr_logits[tro + n] = u;
-                            if (a.tr_masks) a.tr_masks[tro + n] = (float)mm;
-                        }
+                    for (int k = sl; k < na; k += LPR) {
+                        const int n = it[k];
+                        const float u = ulog[n];
+                        if (u > mx || (u == mx && n < mxi)) { second = fmaxf(second, mx); mx = u; mxi = n; }
+                        else second = fmaxf(second, u);
                     }
-                    if (u > mx) { second = mx; mx = u; mxi = n; }      // (nodes come in increasing order: first maximum wins)
-                    else second = fmaxf(second, u);
-                }
 #pragma unroll
-                for (int o = LPR / 2; o; o >>= 1) {
-                    const float ov = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, second, o);
-                    const int oi = __shfl_xor_sync(kFull, mxi, o);
-                    second = fmaxf(fmaxf(second, os), fminf(mx, ov));
-                    if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
-                }
-                int idx;
-                float psel = 1.0f;
-                // Greedy decoding takes argmax(prob) (attention_agent.py:146-147).  exp is monotone up to a few ulp, so when the
-                // runner-up logit is more than 1e-5 below the maximum its probability is strictly smaller and the arg-max of
-                // the logits IS the reference's choice; the softmax is then only evaluated if somebody asked for its values.
-                const bool need_softmax = a.mode != 0 || tracing || a.logprob_out != nullptr || !(second < mx - 1e-5f);
-                if (__any_sync(kFull, need_softmax && live)) {
-                    // ---- softmax denominator in the fixed order of softmax_denominator<LPR> (rollout3): node n belongs to
-                    //      virtual lane n % 32 (= sl + 8 qv), which adds its nodes n, n + 32, ... in sequence
-                    float P0 = 0.0f, P1 = 0.0f, P2 = 0.0f, P3 = 0.0f;
-#pragma unroll 1
-                    for (int k = 0; k < 4; ++k) {
-                        const int nb = sl + 32 * k;
-                        float ev[4];
-#pragma unroll
-                        for (int qv = 0; qv < 4; ++qv) {
-                            const int n = nb + 8 * qv;
-                            const float u = (n < N && live) ? ulog[n] : -INFINITY;
-                            ev[qv] = (u == -INFINITY) ? 0.0f : expf(u - mx);
-                        }
-                        P0 = __fadd_rn(P0, ev[0]); P1 = __fadd_rn(P1, ev[1]); P2 = __fadd_rn(P2, ev[2]); P3 = __fadd_rn(P3, ev[3]);
+                    for (int o = LPR / 2; o; o >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, second, o);
+                        const int oi = __shfl_xor_sync(kFull, mxi, o);
+                        second = fmaxf(fmaxf(second, os), fminf(mx, ov));
+                        if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                     }
-                    float se = __fadd_rn(__fadd_rn(P0, P2), __fadd_rn(P1, P3));
-#pragma unroll
-                    for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
-                    const float lse = logf(se);
-                    // ---- probabilities (decode_step.py:125-126) and the greedy candidate
-                    float bestp = -1.0f;
-                    int besti = 0x7fffffff;
+                    handled = !__any_sync(kFull, live && (fl != 0 || !(second < mx - 1e-5f)));
+                    if (handled) {
+                        const int idx = live ? mxi : 0;
+                        // (2) Env.step (vrptw_utils.py:254-358): demand, load, time, position
+                        const float* fsel = frow + idx * D;
+                        const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
+                        const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
+                        const float px = rs[2], py = rs[3];
+                        const float d_idx = drow[idx];
+                        float nz = rs[13];
+                        __syncwarp();
+                        const float d_sat = fminf(d_idx, load);
+                        const float d_new = __fsub_rn(d_idx, d_sat);
+                        float nload = __fsub_rn(load, d_sat);
+                        const float ts = dist_rn(px, py, sx, sy);
+                        float ntime = 0.0f;
+                        if (TW) ntime = fmaxf(__fadd_rn(time, ts), sb);
+                        const float dep = (idx == n_cust) ? 1.0f : 0.0f;
+                        nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
+                        if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
+                        if (d_idx != 0.0f && d_new == 0.0f) nz -= 1.0f;
+                        if (live && sl == 0) drow[idx] = d_new;
+                        done_now = (idx == n_cust && nz == 0.0f) ? 1 : 0;
+                        if (live && sl == 0) {
+                            rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
+                            if (t == 0) { rs[5] = sx; rs[6] = sy; }
+                            else rs[4] = __fadd_rn(rs[4], ts);
+                            reinterpret_cast<int*>(rs)[8] = done_now;
+                            rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz; rs[15] = dep;
+                            a.idx_out[(long long)t * R + row] = idx;
+                        }
+                        // (3) customers with demand left -> new list; those that are feasible (vehicle not empty, time window
+                        //     reachable: vrptw_utils.py:328-348) -> items of the next step; the depot unless the vehicle stands
+                        //     there with demand left
+                        const bool on = live && !done_now;
+                        const bool cust_ok = nload != 0.0f;
+                        int nal2 = 0, nit = 0;
+                        const int jmax = __reduce_max_sync(kFull, (unsigned)((nal + LPR - 1) / LPR));
 #pragma unroll 1
+                        for (int jb = 0; jb < jmax; jb += 8) {
+                            if (jb > 0) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int k = sl + LPR * (jb + j);
+                                    pn[j] = k < nal ? (int)al[k] : -1;
+                                    pxx[j] = pyy[j] = pee[j] = 0.0f;
+                                    if (TW && pn[j] >= 0) {
+                                        const float* fp = frow + pn[j] * D;
+                                        pxx[j] = ldcg_volatile(fp); pyy[j] = ldcg_volatile(fp + 1); pee[j] = ldcg_volatile(fp + 3);
+                                    }
+                                }
+                            }
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int n = pn[j];
+                                const float dn = n < 0 ? 0.0f : (n == idx ? d_new : drow[n]);
+                                const bool keep = on && n >= 0 && dn != 0.0f;
+                                bool feas = keep && cust_ok;
+                                if (TW && feas) feas = !(__fadd_rn(ntime, dist_rn(sx, sy, pxx[j], pyy[j])) > pee[j]);
+                                const unsigned bk = (__ballot_sync(kFull, keep) >> (8 * sub)) & 0xffu;
+                                const unsigned bf = (__ballot_sync(kFull, feas) >> (8 * sub)) & 0xffu;
+                                const unsigned below = (1u << sl) - 1;
+                                if (keep) al[nal2 + __popc(bk & below)] = (unsigned char)n;
+                                if (feas) it[nit + __popc(bf & below)] = (unsigned char)n;
+                                nal2 += __popc(bk);
+                                nit += __popc(bf);
+                            }
+                        }
+                        const bool depot_ok = on && !(nz > 0.0f && dep != 0.0f);
+                        if (depot_ok && sl == 0) it[nit] = (unsigned char)n_cust;
+                        nit += depot_ok ? 1 : 0;
+                        int flv = 0;
+                        if (on && nit == 0) {   // nothing un-masked: every node is evaluated, the mask counts decide (exact tail)
+                            flv = 1; nit = N;
+                            for (int n = sl; n < N; n += LPR) it[n] = (unsigned char)n;
+                        }
+                        if (sl == 0 && rvalid) { nact_s[lrs] = on ? nit : 0; flag_s[lrs] = flv; nalive_s[lrs] = nal2; }
+                    }
+                }
+                if (!handled) {
+                    if (fastk) { recompute_masks(lrs, rvalid, sl, t); __syncwarp(); }
+                    // ---- masked logits (decode_step.py:231-232) back into the row's slots; maximum, its first index, runner-up
+                    float mx = -INFINITY, second = -INFINITY;
+                    int mxi = 0x7fffffff;
+    #pragma unroll 2
                     for (int j = 0; j < NJ; ++j) {
                         const int n = sl + LPR * j;
-                        if (n < N) {
-                            const float u = live ? ulog[n] : -INFINITY;
-                            const float p = (u == -INFINITY) ? 0.0f : expf((u - mx) - lse);
-                            if (p > bestp) { bestp = p; besti = n; }
-                            if (live) {
-                                if (a.mode != 0) ulog[n] = p;   // probabilities for the sequential CDF below
-                                if (a.tr_probs) a.tr_probs[tro + n] = p;
+                        float u = -INFINITY;
+                        if (n < N && live) {
+                            const int mm = mk[n];
+                            if (fl || mm == 0) {
+                                u = ulog[n];
+                                if (a.use_tanh) u = a.tanh_C * tanhf(u);
+                                if (a.mask_pointer) u = __fsub_rn(u, __fmul_rn(kBig, (float)mm));
+                            }
+                            ulog[n] = u;
+                            if (tracing) {
+                                if (a.tr_logits) a.tr_logits[tro + n] = u;
+                                if (a.tr_masks) a.tr_masks[tro + n] = (float)mm;
                             }
                         }
+                        if (u > mx) { second = mx; mx = u; mxi = n; }      // (nodes come in increasing order: first maximum wins)
+                        else second = fmaxf(second, u);
                     }
-                    if (a.mode == 0) {   // greedy: argmax(prob), first maximal index
-#pragma unroll
-                        for (int o = LPR / 2; o; o >>= 1) {
-                            const float ov = __shfl_xor_sync(kFull, bestp, o);
-                            const int oi = __shfl_xor_sync(kFull, besti, o);
-                            if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+    #pragma unroll
+                    for (int o = LPR / 2; o; o >>= 1) {
+                        const float ov = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, second, o);
+                        const int oi = __shfl_xor_sync(kFull, mxi, o);
+                        second = fmaxf(fmaxf(second, os), fminf(mx, ov));
+                        if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
+                    }
+                    int idx;
+                    float psel = 1.0f;
+                    // Greedy decoding takes argmax(prob) (attention_agent.py:146-147).  exp is monotone up to a few ulp, so when the
+                    // runner-up logit is more than 1e-5 below the maximum its probability is strictly smaller and the arg-max of
+                    // the logits IS the reference's choice; the softmax is then only evaluated if somebody asked for its values.
+                    const bool need_softmax = a.mode != 0 || tracing || a.logprob_out != nullptr || !(second < mx - 1e-5f);
+                    if (__any_sync(kFull, need_softmax && live)) {
+                        // ---- softmax denominator in the fixed order of softmax_denominator<LPR> (rollout3): node n belongs to
+                        //      virtual lane n % 32 (= sl + 8 qv), which adds its nodes n, n + 32, ... in sequence
+                        float P0 = 0.0f, P1 = 0.0f, P2 = 0.0f, P3 = 0.0f;
+    #pragma unroll 1
+                        for (int k = 0; k < 4; ++k) {
+                            const int nb = sl + 32 * k;
+                            float ev[4];
+    #pragma unroll
+                            for (int qv = 0; qv < 4; ++qv) {
+                                const int n = nb + 8 * qv;
+                                const float u = (n < N && live) ? ulog[n] : -INFINITY;
+                                ev[qv] = (u == -INFINITY) ? 0.0f : expf(u - mx);
+                            }
+                            P0 = __fadd_rn(P0, ev[0]); P1 = __fadd_rn(P1, ev[1]); P2 = __fadd_rn(P2, ev[2]); P3 = __fadd_rn(P3, ev[3]);
                         }
-                        idx = besti;
-                        psel = bestp;
-                    } else {             // inverse-CDF sampling with one (per-row) retry (attention_agent.py:148-167)
-                        __syncwarp();
-                        int sel = -1;
-                        if (sl == 0 && live) {
-                            const long long o = (long long)t * R + row;
-                            for (int draw = 0; draw < 2 && sel < 0; ++draw) {
-                                const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
-                                const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
-                                float cum = 0.0f;   // tf.cumsum: sequential fp32 (masked nodes add exactly 0)
-                                for (int n = 0; n < N; ++n) {
-                                    cum = __fadd_rn(cum, ulog[n]);
-                                    if (cum > u) { sel = n; break; }
+                        float se = __fadd_rn(__fadd_rn(P0, P2), __fadd_rn(P1, P3));
+    #pragma unroll
+                        for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
+                        const float lse = logf(se);
+                        // ---- probabilities (decode_step.py:125-126) and the greedy candidate
+                        float bestp = -1.0f;
+                        int besti = 0x7fffffff;
+    #pragma unroll 1
+                        for (int j = 0; j < NJ; ++j) {
+                            const int n = sl + LPR * j;
+                            if (n < N) {
+                                const float u = live ? ulog[n] : -INFINITY;
+                                const float p = (u == -INFINITY) ? 0.0f : expf((u - mx) - lse);
+                                if (p > bestp) { bestp = p; besti = n; }
+                                if (live) {
+                                    if (a.mode != 0) ulog[n] = p;   // probabilities for the sequential CDF below
+                                    if (a.tr_probs) a.tr_probs[tro + n] = p;
                                 }
                             }
                         }
-                        if (sel < 0) sel = 0;
-                        idx = __shfl_sync(kFull, sel, sub * LPR);
-                        __syncwarp();
-                        psel = ulog[idx < N ? idx : 0];
-                        __syncwarp();
-                    }
-                } else {
-                    idx = mxi;
-                }
-                if (idx < 0 || idx >= N) idx = 0;   // rows that are not live carry garbage
-                // ---- Env.step (vrptw_utils.py:254-358): demand, load, time, position
-                const float* fsel = frow + idx * D;
-                const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
-                const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
-                const float px = rs[2], py = rs[3];
-                const float d_idx = drow[idx];
-                float nz = rs[13];                       // customers with demand left: sum(demand) > 0  <=>  nz > 0
-                __syncwarp();
-                const float d_sat = fminf(d_idx, load);
-                const float d_new = __fsub_rn(d_idx, d_sat);
-                float nload = __fsub_rn(load, d_sat);
-                const float ts = dist_rn(px, py, sx, sy);
-                float ntime = 0.0f;
-                if (TW) ntime = fmaxf(__fadd_rn(time, ts), sb);
-                const float dep = (idx == n_cust) ? 1.0f : 0.0f;
-                nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
-                if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
-                if (d_idx != 0.0f && d_new == 0.0f) nz -= 1.0f;
-                if (live && sl == 0) drow[idx] = d_new;
-                __syncwarp();
-                const int done_now = (!a.full && idx == n_cust && nz == 0.0f) ? 1 : 0;
-                if (live && sl == 0) {
-                    rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
-                    if (t == 0) { rs[5] = sx; rs[6] = sy; }
-                    else rs[4] = __fadd_rn(rs[4], ts);
-                    reinterpret_cast<int*>(rs)[8] = done_now;
-                    rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz;
-                    a.idx_out[(long long)t * R + row] = idx;
-                    if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
-                }
-                // ---- new mask (vrptw_utils.py:328-348); node features come from L2, eight nodes' loads in flight at a time
-                // (when nobody reads the mask VALUES, a customer without demand or an empty vehicle is masked whatever its time
-                //  window says and its features are not fetched - unless no node at all stays un-masked: then the choice
-                //  depends on the mask counts and the pass is repeated exactly)
-#pragma unroll 1
-                for (int pass = 0; pass < 2; ++pass) {
-                    const bool exact = a.full || a.fin_mask != nullptr || pass == 1;
-                    if (live) {
-#pragma unroll 1
-                        for (int jb = 0; jb < NJ; jb += 8) {
-                            float nx[8], ny[8], ne[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int n = sl + LPR * (jb + j);
-                                const int nn = n < N ? n : N - 1;
-                                const float* fp = frow + nn * D;
-                                nx[j] = ny[j] = ne[j] = 0.0f;
-                                if (TW && nn != n_cust && (exact || (nload != 0.0f && drow[nn] != 0.0f))) {
-                                    nx[j] = ldcg_volatile(fp); ny[j] = ldcg_volatile(fp + 1); ne[j] = ldcg_volatile(fp + 3);
+                        if (a.mode == 0) {   // greedy: argmax(prob), first maximal index
+    #pragma unroll
+                            for (int o = LPR / 2; o; o >>= 1) {
+                                const float ov = __shfl_xor_sync(kFull, bestp, o);
+                                const int oi = __shfl_xor_sync(kFull, besti, o);
+                                if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+                            }
+                            idx = besti;
+                            psel = bestp;
+                        } else {             // inverse-CDF sampling with one (per-row) retry (attention_agent.py:148-167)
+                            __syncwarp();
+                            int sel = -1;
+                            if (sl == 0 && live) {
+                                const long long o = (long long)t * R + row;
+                                for (int draw = 0; draw < 2 && sel < 0; ++draw) {
+                                    const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
+                                    const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
+                                    float cum = 0.0f;   // tf.cumsum: sequential fp32 (masked nodes add exactly 0)
+                                    for (int n = 0; n < N; ++n) {
+                                        cum = __fadd_rn(cum, ulog[n]);
+                                        if (cum > u) { sel = n; break; }
+                                    }
                                 }
                             }
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int n = sl + LPR * (jb + j);
-                                const int nn = n < N ? n : N - 1;
-                                const int mm = node_mask<TW>(nn, n_cust, drow[nn], nload, ntime, sx, sy, nx[j], ny[j], ne[j], dep, nz);
-                                if (n < N) mk[n] = (unsigned char)mm;
-                            }
+                            if (sel < 0) sel = 0;
+                            idx = __shfl_sync(kFull, sel, sub * LPR);
+                            __syncwarp();
+                            psel = ulog[idx < N ? idx : 0];
+                            __syncwarp();
                         }
+                    } else {
+                        idx = mxi;
                     }
+                    if (idx < 0 || idx >= N) idx = 0;   // rows that are not live carry garbage
+                    // ---- Env.step (vrptw_utils.py:254-358): demand, load, time, position
+                    const float* fsel = frow + idx * D;
+                    const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
+                    const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
+                    const float px = rs[2], py = rs[3];
+                    const float d_idx = drow[idx];
+                    float nz = rs[13];                       // customers with demand left: sum(demand) > 0  <=>  nz > 0
                     __syncwarp();
-                    const int nun = build_items(lrs, rvalid, was_done || done_now, sub, sl);
-                    if (exact || !__any_sync(kFull, live && !done_now && nun == 0)) break;
+                    const float d_sat = fminf(d_idx, load);
+                    const float d_new = __fsub_rn(d_idx, d_sat);
+                    float nload = __fsub_rn(load, d_sat);
+                    const float ts = dist_rn(px, py, sx, sy);
+                    float ntime = 0.0f;
+                    if (TW) ntime = fmaxf(__fadd_rn(time, ts), sb);
+                    const float dep = (idx == n_cust) ? 1.0f : 0.0f;
+                    nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
+                    if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
+                    if (d_idx != 0.0f && d_new == 0.0f) nz -= 1.0f;
+                    if (live && sl == 0) drow[idx] = d_new;
+                    __syncwarp();
+                    done_now = (!a.full && idx == n_cust && nz == 0.0f) ? 1 : 0;
+                    if (live && sl == 0) {
+                        rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
+                        if (t == 0) { rs[5] = sx; rs[6] = sy; }
+                        else rs[4] = __fadd_rn(rs[4], ts);
+                        reinterpret_cast<int*>(rs)[8] = done_now;
+                        rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz; rs[15] = dep;
+                        a.idx_out[(long long)t * R + row] = idx;
+                        if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
+                    }
+                    // ---- new mask (vrptw_utils.py:328-348); node features come from L2, eight nodes' loads in flight at a time
+                    // (when nobody reads the mask VALUES, a customer without demand or an empty vehicle is masked whatever its time
+                    //  window says and its features are not fetched - unless no node at all stays un-masked: then the choice
+                    //  depends on the mask counts and the pass is repeated exactly)
+    #pragma unroll 1
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const bool exact = a.full || a.fin_mask != nullptr || pass == 1;
+                        if (live) {
+    #pragma unroll 1
+                            for (int jb = 0; jb < NJ; jb += 8) {
+                                float nx[8], ny[8], ne[8];
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int n = sl + LPR * (jb + j);
+                                    const int nn = n < N ? n : N - 1;
+                                    const float* fp = frow + nn * D;
+                                    nx[j] = ny[j] = ne[j] = 0.0f;
+                                    if (TW && nn != n_cust && (exact || (nload != 0.0f && drow[nn] != 0.0f))) {
+                                        nx[j] = ldcg_volatile(fp); ny[j] = ldcg_volatile(fp + 1); ne[j] = ldcg_volatile(fp + 3);
+                                    }
+                                }
+    #pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const int n = sl + LPR * (jb + j);
+                                    const int nn = n < N ? n : N - 1;
+                                    const int mm = node_mask<TW>(nn, n_cust, drow[nn], nload, ntime, sx, sy, nx[j], ny[j], ne[j], dep, nz);
+                                    if (n < N) mk[n] = (unsigned char)mm;
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        const int nun = build_items(lrs, rvalid, was_done || done_now, sub, sl);
+                        if (exact || !__any_sync(kFull, live && !done_now && nun == 0)) break;
+                    }
+                    if (fastk) { __syncwarp(); build_alive(lrs, rvalid, sub, sl); }
                 }
                 warp_done &= __all_sync(kFull, !live || done_now);
+                VRP_CLK(13);
             }
             if (lane == 0) done_s[warp] = warp_done;
             VRP_CLK(5);
@@ -798,6 +1059,10 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         *stop_s = 1;
         __threadfence_block();
         mbar_arrive(bar_x);
+    }
+    if (NSW == 8) {   // wake the score-MMA issuers (they wait for the F tile of the group's next tile)
+        named_bar(5, NT);
+        if (warp < 8 && lane == 0) mbar_arrive(bar_grp + 80 * (warp >> 2) + 64 + 8 * (c1_nq & 1));
     }
     const int t_end = t;
 
@@ -830,7 +1095,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
 #ifdef VRPB200_PHASE_CLOCKS
         if (tid == 64 || tid == 384)   // a score warp and a row warp
-            for (int i = 0; i < 12; ++i) atomicAdd(a.stats + 4 + i + (tid == 384 ? 12 : 0), (unsigned long long)pc_[i]);
+            for (int i = 0; i < 14; ++i) atomicAdd(a.stats + 4 + i + (tid == 384 ? 14 : 0), (unsigned long long)pc_[i]);
 #endif
     }
     tc_fence_before();

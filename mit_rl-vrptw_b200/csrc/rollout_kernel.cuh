@@ -94,6 +94,7 @@ struct RolloutArgs {
     int full;                // evaluate every node every step, never exit early (trace mode)
     int use_tanh, mask_pointer;
     float capacity, tanh_C, forget_bias;
+    int tune;                // experiments only (VRPB200_TUNE): start offset in ns of the odd score groups of rollout4
     float sumv;              // rollout4: sum_h v_h of the pointer attention
     float vm2[128];          // rollout4: -2 v_h (read as constant-bank operands)
 };
@@ -129,14 +130,16 @@ VRP_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
 VRP_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes instead of
+// spinning through the loop (a spinning waiter takes issue slots from the warps that do the arithmetic)
 VRP_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred P1;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 VRP_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

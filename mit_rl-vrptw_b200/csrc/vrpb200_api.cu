@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
 #include "rollout_kernel.cuh"
 #include "rollout2_kernel.cuh"
 #include "rollout3_kernel.cuh"
@@ -419,7 +420,7 @@ template <int RB>
 int launch_rollout4_any(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st, int stages, int nsw) {
     if constexpr (RB <= 48) {
 #define V4(TWv, STv, NSv) launch_rollout4_t<RB, TWv, STv, NSv>(h, a, grid, smem, st)
-        if (nsw == 12) return h->tw ? (stages == 3 ? V4(true, 3, 12) : V4(true, 2, 12)) : (stages == 3 ? V4(false, 3, 12) : V4(false, 2, 12));
+        if (nsw == 8) return h->tw ? (stages == 3 ? V4(true, 3, 8) : V4(true, 2, 8)) : (stages == 3 ? V4(false, 3, 8) : V4(false, 2, 8));
         return h->tw ? (stages == 3 ? V4(true, 3, 16) : V4(true, 2, 16)) : (stages == 3 ? V4(false, 3, 16) : V4(false, 2, 16));
 #undef V4
     } else {
@@ -431,7 +432,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
     const bool v4 = c.gemm_path >= 4 && a.mode != 2;             // rollout4: greedy / stochastic; beam search stays on rollout3
-    const int nsw = c.gemm_path == 5 ? 12 : 16;                  // 5: four row warps stream the per-row tail behind the scores
+    const int nsw = c.gemm_path == 5 ? 8 : 16;                   // 5: eight row warps stream the per-row tail behind the scores
     const bool v3 = c.gemm_path == 3 || (c.gemm_path >= 4 && !v4);
     const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
     int stages3 = 2;
@@ -535,6 +536,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.seed = seed; a.B = B; a.row_base = row_base; a.W = mode == VRPB200_BEAM ? beam_width : 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
     a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
+    { const char* tv = getenv("VRPB200_TUNE"); a.tune = tv ? atoi(tv) : 0; }
     a.sumv = h->sumv;
     memcpy(a.vm2, h->vm2, sizeof a.vm2);
     return launch_rollout(h, a, (cudaStream_t)stream);

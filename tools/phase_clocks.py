@@ -32,12 +32,12 @@ names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epi
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
 if gemm in ("tc4", "tc4s"):
     names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
-             "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop"]
-    for who, o in (("score warp 2", 4), ("row warp 12", 16)):
+             "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop", "rows: wait for logits", "rows: processing"]
+    for who, o in (("warp 2", 4), ("warp 12", 18)):
         print(" ", who)
         for n, v in zip(names, s[o:o + len(names)]):
             print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
-        print(f"    total {s[o:o + 12].sum() / blocksteps:.0f} clk/step")
+        print(f"    total {s[o:o + 14].sum() / blocksteps:.0f} clk/step")
     sys.exit(0)
 for n, v in zip(names, s[4:4 + len(names)]):
     print(f"  {n:40s} {v / blocksteps:10.0f} clk/step")
