@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-cta", type=int, default=0)
-    ap.add_argument("--kernel", default="tc3", choices=["tc4", "tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout3)")
+    ap.add_argument("--kernel", default="tc4", choices=["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout4)")
     return ap.parse_args()
 
 
@@ -263,7 +263,11 @@ def main():
         # executed work of one launch, from the kernel's own counters:
         #   node_evals     (row, node) pairs whose 128 tanh terms were evaluated
         #   gemm_rowsteps  rows x executed steps that went through the LSTM + query GEMMs
-        mufu_ops = 2.0 * H * node_evals + 10.0 * H * gemm_rowsteps + 3.0 * node_evals   # tanh grid, LSTM gates, softmax exp
+        if a.kernel in ("tc4x", "tc4", "tc4s"):
+            # rollout4: 4 ex2 + ONE shared rcp per 4 tanh terms; LSTM gates 5 x (ex2 + rcp); greedy fast tail: no softmax
+            mufu_ops = 1.25 * H * node_evals + 10.0 * H * gemm_rowsteps
+        else:
+            mufu_ops = 2.0 * H * node_evals + 10.0 * H * gemm_rowsteps + 3.0 * node_evals   # tanh grid, LSTM gates, softmax exp
         gemm_macs = (128 * 512 + 128 * 128 + 4 * 512) * gemm_rowsteps                    # h.W_h, h'.W_q, x.W_x
         score_macs = 5.0 * H * node_evals                                                # feat.A + demand.g  (K = 5)
         if a.kernel == "ffma":
@@ -272,6 +276,9 @@ def main():
         elif a.kernel == "tc":
             fp32_ops = 8.0 * H * node_evals + 30.0 * H * gemm_rowsteps
             tensor_flops = 3 * 2.0 * gemm_macs                                           # 3xTF32 split
+        elif a.kernel in ("tc4x", "tc4", "tc4s"):
+            fp32_ops = 7.25 * H * node_evals + 46.0 * H * gemm_rowsteps                  # add, clamp, +1, shared-reciprocal algebra
+            tensor_flops = 3 * 2.0 * (gemm_macs + score_macs * 8.0 / 5.0)
         else:
             fp32_ops = 4.0 * H * node_evals + 46.0 * H * gemm_rowsteps                   # tanh/dot epilogue; LSTM epilogue + x part
             tensor_flops = 3 * 2.0 * (gemm_macs + score_macs * 8.0 / 5.0)                # K padded to 8 for the scores
@@ -296,13 +303,13 @@ def main():
         bound = max(("mufu", "fp32", "hbm", "tensor"), key=lambda k: pipes[k]["frac"])
         roofline = {"bound": bound, "achieved": pipes[bound]["achieved"], "peak": pipes[bound]["peak"], "unit": pipes[bound]["unit"],
                     "frac": pipes[bound]["frac"], "traffic": None,
-                    "peak_source": "pipe peaks measured live by vrpb200_pipe_peak (register-only micro-benchmark on all SMs); "
+                    "peak_source": "pipe peaks measured live by vrpb200_pipe_peak (register-only micro-benchmark on all SMs; MUFU = chains of rcp(1 + ex2(x)), 16 lanes/clk/SM); "
                                    "MEASURED_PEAKS.json holds only HBM and bf16-tensor peaks and neither binds this path",
                     "work_per_launch": {"node_evaluations": node_evals, "live_row_steps": live_rowsteps, "gemm_row_steps": gemm_rowsteps,
                                         "blocks": blocks, "mean_steps_per_block": float(st.steps.float().mean().item()),
                                         "mufu_ops": mufu_ops, "fp32_lane_ops": fp32_ops, "tensor_flops": tensor_flops, "hbm_bytes": hbm_bytes},
                     "pipes": pipes,
-                    "kernel": f"{ {'tc3': 'rollout3_kernel', 'tc2': 'rollout2_kernel'}.get(a.kernel, 'rollout_kernel') }<{launch['rows_per_cta']},TW> ({a.kernel}) grid {launch['grid']} x {launch['block']} thr, {launch['smem']} B smem, "
+                    "kernel": f"{ {'tc4x': 'rollout4_kernel', 'tc4': 'rollout4_kernel', 'tc4s': 'rollout4_kernel', 'tc3': 'rollout3_kernel', 'tc2': 'rollout2_kernel'}.get(a.kernel, 'rollout_kernel') }<{launch['rows_per_cta']},TW> ({a.kernel}) grid {launch['grid']} x {launch['block']} thr, {launch['smem']} B smem, "
                               f"1 launch per step, {ms_step:.3f} ms per launch (CUDA events)"}
         # profiles/ holds the ncu capture of the same kernel; dram bytes per launch from it if present
         tr_path = os.path.join(ROOT, "profiles", "traffic.json")

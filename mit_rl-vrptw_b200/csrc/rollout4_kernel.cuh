@@ -23,7 +23,7 @@ namespace vrpb200 {
 constexpr int kV4Threads = 640;   // 16 compute warps + weight feeder warp + LSTM/query MMA issuer warp + 2 score-MMA issuer warps
 
 struct Smem4 {
-    int ring, X, qq, F, logits, items, alive, bc, vsm, dem, mask, rs, meta, bar, total, stages;
+    int ring, X, qq, F, logits, items, alive, bc, vsm, psum, dem, mask, rs, meta, bar, total, stages;
 };
 
 __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw) {
@@ -41,6 +41,7 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
     L.alive = off;  off += align_up(RB * NP, 16);             // node ids of the customers with demand left, per row
     L.bc = off;     off += 2 * 4096;
     L.vsm = off;    off += 512;                               // -2 v
+    L.psum = off;   off += 2 * 2 * 128 * 4;                   // split variant: partial score sums, [group][tile parity][item]
     L.dem = off;    off += RB * NP * 4;
     L.mask = off;   off += align_up(RB * NP, 16);
     L.rs = off;     off += RB * kRowState * 4;
@@ -78,6 +79,11 @@ VRP_DEVINL float ldcg_volatile(const float* p) {
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+VRP_DEVINL float4 ldcg4_volatile(const float4* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
 VRP_DEVINL int lds_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // NSW = number of score warps:
@@ -86,13 +92,18 @@ VRP_DEVINL int lds_volatile(const int* p) { return *reinterpret_cast<const volat
 //    8 -> warps 0..7 score (2 groups; 4 TMEM quarter buffers and 2 F tiles each, so the MMAs of the NEXT tile are in
 //         flight during the arithmetic of this one; they are issued by two dedicated warps, 18 and 19, and a score warp
 //         never waits for its peers), warps 8..15 are row warps that stream the per-row tail behind the scores
-template <int RB, bool TW, int STAGES, int NSW>
+//   16 + SPLIT -> every warp scores, in 2 groups of 8 warps with the deep buffering of the 8-warp variant: the two warps of a
+//         TMEM sub-partition share the 32 items of a tile and take hidden units 0..63 / 64..127 (partial sums meet in
+//         shared memory and are added in a fixed order); then every warp runs the per-row tail
+template <int RB, bool TW, int STAGES, int NSW, bool SPLIT>
 __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_constant__ RolloutArgs a) {
     constexpr int NT = 512, RPW = RB / 16, RPT = RB / 4, FD = TW ? 4 : 2;
-    constexpr int NG = NSW / 4;                                  // score groups, 64 TMEM columns each
+    constexpr bool DEEP = NSW == 8 || SPLIT;                     // 4 TMEM buffers + 2 F tiles per group, MMAs issued by warps 18/19
+    constexpr int NG = DEEP ? 2 : 4;                             // score groups
     constexpr int kQCol = 256 + 4 * RB;                          // q^T: its own columns
     constexpr int kGCol = 256;                                   // gates^T: tile m at kGCol + RB m
     static_assert(NSW == 8 || NSW == 16, "score warps");
+    static_assert(!SPLIT || NSW == 16, "split");
     constexpr int LPR = 8;                                       // lanes per row in the per-row tail
     constexpr int NBT = NSW == 16 ? 1 : (RB + 31) / 32;          // row warps: batches of (up to) 32 rows
     static_assert(RB % 16 == 0 && RB <= 48, "rows");
@@ -106,6 +117,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     unsigned char* items = smem + L.items;
     unsigned char* alive = smem + L.alive;
     float* vsm = reinterpret_cast<float*>(smem + L.vsm);
+    float* psum = reinterpret_cast<float*>(smem + L.psum);
     float* dem = reinterpret_cast<float*>(smem + L.dem);
     unsigned char* maskb = smem + L.mask;
     float* rowst = reinterpret_cast<float*>(smem + L.rs);
@@ -127,12 +139,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     const int IBv = (int)min((long long)RB, a.B - b0);
     const long long R = a.B;
     const int D = a.D;
-    const float* gfeat = a.input + b0 * (long long)N * D;
+    // node features re-packed by repack_features_kernel: (x, y, b_tw, e_tw) of a node in ONE 16-byte load (the [B, N, D]
+    // input has 12- or 20-byte records: three or four scattered 4-byte loads per node otherwise)
+    const float4* gfeat4 = a.feat4 + b0 * (long long)N;
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         mbar_init(bar_q, 1); mbar_init(bar_g, 1); mbar_init(bar_x, 1);
-        if (NSW == 16) {
+        if (!DEEP) {
             for (int g = 0; g < 4; ++g) {   // per group: full[2] (MMA commit), free[2] (4 warps copied the buffer), F ready (4 warps)
                 mbar_init(bar_grp + 40 * g, 1); mbar_init(bar_grp + 40 * g + 8, 1);
                 mbar_init(bar_grp + 40 * g + 16, 4); mbar_init(bar_grp + 40 * g + 24, 4); mbar_init(bar_grp + 40 * g + 32, 4);
@@ -141,6 +155,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             for (int g = 0; g < 2; ++g) {   // per group: full[4], free[4], F ready[2]
                 for (int q = 0; q < 4; ++q) { mbar_init(bar_grp + 80 * g + 8 * q, 1); mbar_init(bar_grp + 80 * g + 32 + 8 * q, 4); }
                 mbar_init(bar_grp + 80 * g + 64, 4); mbar_init(bar_grp + 80 * g + 72, 4);
+                mbar_init(bar_grp + 160 + 8 * g, 4);   // split variant: the partial sums of a tile are in place
             }
         }
         for (int i = 0; i < 64; ++i) mbar_init(bar_tile + 8 * i, 4);   // 4 arrivals per step: the 4 warps that scored the tile
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             }
             if (step > 0) mbar_wait(bar_g, (step - 1) & 1);
         }
-        else if (NSW == 8 && warp >= 18 && lane == 0) {
+        else if (DEEP && warp >= 18 && lane == 0) {
             // ---- score-MMA issuer of group g: one tile per "F ready"; quarter q goes to TMEM buffer q once the four score
             //      warps have copied the previous tile's quarter q out of it
             const int g = warp - 18;
@@ -329,14 +344,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         if (!rvalid) return;
         const float* rs = rowst + lrs * kRowState;
         const float* drow = dem + lrs * NP;
-        const float* frow = gfeat + (size_t)lrs * N * D;
+        const float4* frow = gfeat4 + (size_t)lrs * N;
         unsigned char* mk = maskb + lrs * NP;
         for (int n = sl; n < N; n += LPR) {
             int mm;
             if (step == 0) mm = (n == n_cust) ? 1 : (drow[n] == 0.0f ? 1 : 0);
             else {
                 float nx = 0.f, ny = 0.f, ne = 0.f;
-                if (TW) { nx = __ldcg(frow + n * D); ny = __ldcg(frow + n * D + 1); ne = __ldcg(frow + n * D + 3); }
+                if (TW) { const float4 fv = __ldcg(frow + n); nx = fv.x; ny = fv.y; ne = fv.w; }
                 mm = node_mask<TW>(n, n_cust, drow[n], rs[0], TW ? rs[1] : 0.0f, rs[2], rs[3], nx, ny, ne, rs[15], rs[13]);
             }
             mk[n] = (unsigned char)mm;
@@ -355,13 +370,13 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) nzc += __shfl_xor_sync(kFull, nzc, o);
-        const float* fdep = gfeat + (size_t)(lr * N + n_cust) * D;
+        const float4 fdep = __ldcg(gfeat4 + (size_t)lr * N + n_cust);
         if (lane == 0) {
             float* rs = rowst + lr * kRowState;
             rs[13] = (float)nzc; rs[15] = 0.0f;
-            rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = __ldcg(fdep + 0); rs[3] = __ldcg(fdep + 1); rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
+            rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = fdep.x; rs[3] = fdep.y; rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
             reinterpret_cast<int*>(rs)[8] = 0;
-            rs[9] = __ldcg(fdep + 0); rs[10] = __ldcg(fdep + 1); rs[11] = TW ? __ldcg(fdep + 2) : 0.0f; rs[12] = TW ? __ldcg(fdep + 3) : 0.0f;
+            rs[9] = fdep.x; rs[10] = fdep.y; rs[11] = TW ? fdep.z : 0.0f; rs[12] = TW ? fdep.w : 0.0f;
         }
     }
     named_bar(5, NT);
@@ -380,7 +395,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     named_bar(5, NT);
 
 #ifdef VRPB200_PHASE_CLOCKS
-    long long pc_[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc_last_ = clock64();
+    long long pc_[28], pc_last_ = clock64();
+    for (int i = 0; i < 28; ++i) pc_[i] = 0;
 #endif
     // C1: the two TMEM buffers of a group are used strictly in turn, so one counter of consumed quarters (every thread)
     // and one of issued quarters (issuer thread) give buffer index and mbarrier parity
@@ -475,17 +491,18 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
 
         // ================= C1 set-up (score warps): first tile(s) of every group, staged while the query GEMM runs ======
         const int ntiles = (m_tot + 127) >> 7;
-        const int g = ub;                                                // score group
+        const int g = SPLIT ? (warp >> 3) : ub;                          // score group
+        const int half = SPLIT ? (ub & 1) : 0;                           // split variant: hidden units 64 half .. 64 half + 63
         const int m = 32 * sp + lane;
         // NSW 16: group g owns F tile g and TMEM columns 64 g (2 buffers x 32); NSW 8: F tiles 2g, 2g+1, columns 128 g (4 x 32)
-        unsigned char* fgrp = ftile + (g < NG ? g : 0) * (NSW == 16 ? 2 : 4) * kC1TileBytes;
+        unsigned char* fgrp = ftile + (g < NG ? g : 0) * (DEEP ? 4 : 2) * kC1TileBytes;
         const uint32_t f_hi = smem_u32(fgrp), f_lo = f_hi + kC1TileBytes;
         const uint32_t d_g = tmem_base + 64 * g;
-        const uint32_t bfull = bar_grp + (NSW == 16 ? 40 : 80) * (g < NG ? g : 0), bfree = bfull + (NSW == 16 ? 16 : 32),
-                       bfrdy = bfull + (NSW == 16 ? 32 : 64);
-        const bool issuer = (NSW == 16 && sp == 0 && lane == 0);
+        const uint32_t bfull = bar_grp + (DEEP ? 80 : 40) * (g < NG ? g : 0), bfree = bfull + (DEEP ? 32 : 16),
+                       bfrdy = bfull + (DEEP ? 64 : 32), bpsum = bar_grp + 160 + 8 * (g < NG ? g : 0);
+        const bool issuer = (!DEEP && sp == 0 && lane == 0);
         // item `it` of the step -> (row, node): binary search in the row offsets, then the row's node list
-        auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5]) {
+        auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5], bool feats = true) {
             const int it = tile * 128 + m;
             valid = tile < ntiles && it < m_tot;
             r = 0; n = 0;
@@ -500,10 +517,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 }
                 r = lo;
                 n = items[r * NP + (it - off_s[r])];
-                const float* fr = gfeat + ((size_t)r * N + n) * D;
-                f[0] = ldcg_volatile(fr); f[1] = ldcg_volatile(fr + 1);
-                if (TW) { f[2] = ldcg_volatile(fr + 2); f[3] = ldcg_volatile(fr + 3); }
-                f[4] = dem[r * NP + n];
+                if (feats) {
+                    const float4 fv = ldcg4_volatile(gfeat4 + (size_t)r * N + n);
+                    f[0] = fv.x; f[1] = fv.y;
+                    if (TW) { f[2] = fv.z; f[3] = fv.w; }
+                    f[4] = dem[r * NP + n];
+                }
             }
         };
         auto store_F = [&](unsigned char* fhi, const float (&f)[5]) {
@@ -563,8 +582,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         const bool scoring = warp < NSW && g < ntiles;
         if (scoring) {
             float fc[5];
-            load_item(g, r_cur, n_cur, v_cur, fc);
-            if (NSW == 16) {
+            load_item(g, r_cur, n_cur, v_cur, fc, half == 0);
+            if (!DEEP) {
                 store_F(fgrp, fc);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bfrdy);
@@ -575,14 +594,16 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 __syncwarp();
             } else {   // the F tiles of the group's first two tiles of the step; warp 18 + g issues the MMAs
                 float f2[5];
-                load_item(g + NG, r_nx, n_nx, v_nx, f2);
-                store_F(fgrp + (c1_nq & 1) * 2 * kC1TileBytes, fc);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bfrdy + 8 * (c1_nq & 1));
-                if (g + NG < ntiles) {
-                    store_F(fgrp + ((c1_nq + 1) & 1) * 2 * kC1TileBytes, f2);
+                load_item(g + NG, r_nx, n_nx, v_nx, f2, half == 0);
+                if (half == 0) {
+                    store_F(fgrp + (c1_nq & 1) * 2 * kC1TileBytes, fc);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bfrdy + 8 * ((c1_nq + 1) & 1));
+                    if (lane == 0) mbar_arrive(bfrdy + 8 * (c1_nq & 1));
+                    if (g + NG < ntiles) {
+                        store_F(fgrp + ((c1_nq + 1) & 1) * 2 * kC1TileBytes, f2);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bfrdy + 8 * ((c1_nq + 1) & 1));
+                    }
                 }
             }
         }
@@ -615,7 +636,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         if (warp < NSW) {
             // ================= C1: scores =================================================================
             if (a.tune > 0 && (g & 1)) __nanosleep(a.tune);   // experiment: odd groups start later (warps of one SM sub-partition out of phase)
-            if (scoring && NSW == 16) {
+            if (scoring && !DEEP) {
                 float fn[5];
 #pragma unroll 1
                 for (int tile = g; tile < ntiles; tile += NG) {
@@ -659,6 +680,60 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished (release: logits visible)
                     r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                }
+            }
+            if (scoring && SPLIT) {
+                // c1_nq counts the tiles of this group (all steps): tile k uses F tile k & 1, its quarter q TMEM buffer q.
+                // Warps 8g..8g+3 (half 0) gather the items, write F and take quarters 0, 1; warps 8g+4..8g+7 take quarters 2, 3
+                // of the same items and hand their partial sum over through shared memory.
+                int r_n2 = 0, n_n2 = 0;
+                bool v_n2 = false;
+                float fn[5];
+                float* ps = psum + g * 256;
+#pragma unroll 1
+                for (int tile = g; tile < ntiles; tile += NG) {
+                    const float* brow = qq + r_cur * kH;
+                    const uint32_t par = c1_nq & 1;
+                    float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                    for (int qi = 0; qi < 2; ++qi) {
+                        const int q = 2 * half + qi;
+                        VRP_CLK(11);
+                        mbar_wait(bfull + 8 * q, par);
+                        tc_fence_after();
+                        VRP_CLK(7);
+                        uint32_t cur[32];
+                        tc_ld32_issue(tmem_base + ((uint32_t)(32 * sp) << 16) + 128 * g + 32 * q, cur);
+                        tc_ld_wait32(cur);
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(bfree + 8 * q);      // warp 18 + g may send the next tile's quarter q here
+                        __syncwarp();
+                        VRP_CLK(9);
+                        // the items two tiles ahead: row look-up and feature loads are scheduled into the arithmetic below
+                        if (qi == 0) load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn, half == 0);
+                        quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
+                        VRP_CLK(10);
+                    }
+                    if (half == 1) {
+                        ps[par * 128 + m] = acc0 + acc1;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bpsum);
+                    } else {
+                        mbar_wait(bpsum, par);      // (also: quarters 2 and 3 of this tile have been read, its F tile is free)
+                        if (v_cur) logits[r_cur * NP + n_cur] = (a.sumv + (acc0 + acc1)) + ps[par * 128 + m];
+                        n_eval += v_cur ? 1 : 0;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished
+                        if (tile + 2 * NG < ntiles) {
+                            store_F(fgrp + par * 2 * kC1TileBytes, fn);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bfrdy + 8 * par);
+                        }
+                    }
+                    VRP_CLK(8);
+                    ++c1_nq;
+                    r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                    r_nx = r_n2; n_nx = n_n2; v_nx = v_n2;
                 }
             }
             if (scoring && NSW == 8) {
@@ -740,7 +815,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 if (live && sl == 0) ++n_rowsteps;
                 const float load = rs[0], time = TW ? rs[1] : 0.0f;
                 unsigned char* mk = maskb + lrs * NP;
-                const float* frow = gfeat + (size_t)lrs * N * D;
+                const float4* frow = gfeat4 + (size_t)lrs * N;
                 float* drow = dem + lrs * NP;
                 float* ulog = logits + lrs * NP;
                 const int fl = flag_s[lrs];
@@ -765,10 +840,11 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         pn[j] = k < nal ? (int)al[k] : -1;
                         pxx[j] = pyy[j] = pee[j] = 0.0f;
                         if (TW && pn[j] >= 0) {
-                            const float* fp = frow + pn[j] * D;
-                            pxx[j] = ldcg_volatile(fp); pyy[j] = ldcg_volatile(fp + 1); pee[j] = ldcg_volatile(fp + 3);
+                            const float4 fv = ldcg4_volatile(frow + pn[j]);
+                            pxx[j] = fv.x; pyy[j] = fv.y; pee[j] = fv.w;
                         }
                     }
+                    VRP_CLK(14);
                     // (1) arg-max (first index on ties) and runner-up over the items
                     float mx = -INFINITY, second = -INFINITY;
                     int mxi = 0x7fffffff;
@@ -788,12 +864,13 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                     }
                     handled = !__any_sync(kFull, live && (fl != 0 || !(second < mx - 1e-5f)));
+                    VRP_CLK(15);
                     if (handled) {
                         const int idx = live ? mxi : 0;
                         // (2) Env.step (vrptw_utils.py:254-358): demand, load, time, position
-                        const float* fsel = frow + idx * D;
-                        const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
-                        const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
+                        const float4 fsel = __ldcg(frow + idx);
+                        const float sx = fsel.x, sy = fsel.y;
+                        const float sb = TW ? fsel.z : 0.0f, se_tw = TW ? fsel.w : 0.0f;
                         const float px = rs[2], py = rs[3];
                         const float d_idx = drow[idx];
                         float nz = rs[13];
@@ -818,6 +895,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz; rs[15] = dep;
                             a.idx_out[(long long)t * R + row] = idx;
                         }
+                        VRP_CLK(16);
                         // (3) customers with demand left -> new list; those that are feasible (vehicle not empty, time window
                         //     reachable: vrptw_utils.py:328-348) -> items of the next step; the depot unless the vehicle stands
                         //     there with demand left
@@ -834,8 +912,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                                     pn[j] = k < nal ? (int)al[k] : -1;
                                     pxx[j] = pyy[j] = pee[j] = 0.0f;
                                     if (TW && pn[j] >= 0) {
-                                        const float* fp = frow + pn[j] * D;
-                                        pxx[j] = ldcg_volatile(fp); pyy[j] = ldcg_volatile(fp + 1); pee[j] = ldcg_volatile(fp + 3);
+                                        const float4 fv = ldcg4_volatile(frow + pn[j]);
+                                        pxx[j] = fv.x; pyy[j] = fv.y; pee[j] = fv.w;
                                     }
                                 }
                             }
@@ -865,6 +943,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             for (int n = sl; n < N; n += LPR) it[n] = (unsigned char)n;
                         }
                         if (sl == 0 && rvalid) { nact_s[lrs] = on ? nit : 0; flag_s[lrs] = flv; nalive_s[lrs] = nal2; }
+                        VRP_CLK(17);
                     }
                 }
                 if (!handled) {
@@ -976,9 +1055,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     }
                     if (idx < 0 || idx >= N) idx = 0;   // rows that are not live carry garbage
                     // ---- Env.step (vrptw_utils.py:254-358): demand, load, time, position
-                    const float* fsel = frow + idx * D;
-                    const float sx = __ldcg(fsel + 0), sy = __ldcg(fsel + 1);
-                    const float sb = TW ? __ldcg(fsel + 2) : 0.0f, se_tw = TW ? __ldcg(fsel + 3) : 0.0f;
+                    const float4 fsel = __ldcg(frow + idx);
+                    const float sx = fsel.x, sy = fsel.y;
+                    const float sb = TW ? fsel.z : 0.0f, se_tw = TW ? fsel.w : 0.0f;
                     const float px = rs[2], py = rs[3];
                     const float d_idx = drow[idx];
                     float nz = rs[13];                       // customers with demand left: sum(demand) > 0  <=>  nz > 0
@@ -1020,10 +1099,11 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                                 for (int j = 0; j < 8; ++j) {
                                     const int n = sl + LPR * (jb + j);
                                     const int nn = n < N ? n : N - 1;
-                                    const float* fp = frow + nn * D;
+                                    const float4* fp = frow + nn;
                                     nx[j] = ny[j] = ne[j] = 0.0f;
                                     if (TW && nn != n_cust && (exact || (nload != 0.0f && drow[nn] != 0.0f))) {
-                                        nx[j] = ldcg_volatile(fp); ny[j] = ldcg_volatile(fp + 1); ne[j] = ldcg_volatile(fp + 3);
+                                        const float4 fv = ldcg4_volatile(fp);
+                                        nx[j] = fv.x; ny[j] = fv.y; ne[j] = fv.w;
                                     }
                                 }
     #pragma unroll
@@ -1060,9 +1140,10 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         __threadfence_block();
         mbar_arrive(bar_x);
     }
-    if (NSW == 8) {   // wake the score-MMA issuers (they wait for the F tile of the group's next tile)
+    if (DEEP) {   // wake the score-MMA issuers (they wait for the F tile of the group's next tile)
         named_bar(5, NT);
-        if (warp < 8 && lane == 0) mbar_arrive(bar_grp + 80 * (warp >> 2) + 64 + 8 * (c1_nq & 1));
+        if (SPLIT) { if (warp < 16 && ((warp >> 2) & 1) == 0 && lane == 0) mbar_arrive(bar_grp + 80 * (warp >> 3) + 64 + 8 * (c1_nq & 1)); }
+        else if (warp < 8 && lane == 0) mbar_arrive(bar_grp + 80 * (warp >> 2) + 64 + 8 * (c1_nq & 1));
     }
     const int t_end = t;
 
@@ -1094,8 +1175,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             atomicAdd(a.stats + 3, 1ull);
         }
 #ifdef VRPB200_PHASE_CLOCKS
-        if (tid == 64 || tid == 384)   // a score warp and a row warp
-            for (int i = 0; i < 14; ++i) atomicAdd(a.stats + 4 + i + (tid == 384 ? 14 : 0), (unsigned long long)pc_[i]);
+        if (tid == 64)
+            for (int i = 0; i < 28; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)pc_[i]);
 #endif
     }
     tc_fence_before();

@@ -282,6 +282,17 @@ __global__ void reward_kernel(const float* __restrict__ actions, long long T, lo
 
 // ---- pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not hold -----------------
 // kind 0: MUFU (ex2 + rcp alternating, 8 independent chains per thread); kind 1: FP32 FMA (16 chains).
+// [B, N, D] instances (D = 3: x, y, demand; D = 5: x, y, b_tw, e_tw, demand) -> [B, N] float4 (x, y, b_tw, e_tw):
+// one aligned 16-byte record per node for the gathers of the fused rollout (rollout4)
+__global__ void repack_features_kernel(const float* __restrict__ in, float4* __restrict__ out, long long n_nodes_total, int D) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes_total) return;
+    const float* p = in + i * D;
+    float4 v = make_float4(p[0], p[1], 0.0f, 0.0f);
+    if (D == 5) { v.z = p[2]; v.w = p[3]; }
+    out[i] = v;
+}
+
 __global__ void __launch_bounds__(512) pipe_peak_kernel(int kind, int iters, float* sink) {
     float x[16];
 #pragma unroll

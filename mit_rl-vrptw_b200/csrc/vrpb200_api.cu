@@ -52,6 +52,10 @@ struct vrpb200_handle {
     size_t dev_in_bytes[kChunks] = {0, 0, 0}, dev_idx_bytes[kChunks] = {0, 0, 0}, dev_cost_bytes[kChunks] = {0, 0, 0};
     cudaStream_t streams[kChunks] = {nullptr, nullptr, nullptr};
     unsigned long long* dev_stats = nullptr;
+    // rollout4: re-packed node features, one workspace per staging slot (+ one for vrpb200_rollout)
+    float4* ws_feat4[kChunks + 1] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_feat4_bytes[kChunks + 1] = {0, 0, 0, 0};
+    int ws_slot = kChunks;            // which workspace the next rollout_impl call uses
     int32_t last_launch[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     float vm2[128];                   // -2 v of the pointer attention and sum v (rollout4 kernel parameters)
     float sumv = 0.0f;
@@ -127,7 +131,7 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path < 0 || c.gemm_path > 5) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..5");
+    if (c.gemm_path < 0 || c.gemm_path > 6) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..6");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -161,6 +165,8 @@ int vrpb200_destroy(vrpb200_handle* h) {
         if (h->streams[i]) cudaStreamDestroy(h->streams[i]);
     }
     if (h->dev_stats) cudaFree(h->dev_stats);
+    for (int i = 0; i <= vrpb200_handle::kChunks; ++i)
+        if (h->ws_feat4[i]) cudaFree(h->ws_feat4[i]);
     delete h;
     return VRPB200_OK;
 }
@@ -408,10 +414,10 @@ int launch_rollout3_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int sme
     return 0;
 }
 
-template <int RB, bool TW, int STAGES, int NSW>
+template <int RB, bool TW, int STAGES, int NSW, bool SPLIT = false>
 int launch_rollout4_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, NSW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout4_kernel<RB, TW, STAGES, NSW><<<grid, kV4Threads, smem, st>>>(a);
+    CUDA_TRY(h, cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, NSW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    rollout4_kernel<RB, TW, STAGES, NSW, SPLIT><<<grid, kV4Threads, smem, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -420,6 +426,8 @@ template <int RB>
 int launch_rollout4_any(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st, int stages, int nsw) {
     if constexpr (RB <= 48) {
 #define V4(TWv, STv, NSv) launch_rollout4_t<RB, TWv, STv, NSv>(h, a, grid, smem, st)
+        if (nsw == 17) return h->tw ? (stages == 3 ? launch_rollout4_t<RB, true, 3, 16, true>(h, a, grid, smem, st) : launch_rollout4_t<RB, true, 2, 16, true>(h, a, grid, smem, st))
+                                    : (stages == 3 ? launch_rollout4_t<RB, false, 3, 16, true>(h, a, grid, smem, st) : launch_rollout4_t<RB, false, 2, 16, true>(h, a, grid, smem, st));
         if (nsw == 8) return h->tw ? (stages == 3 ? V4(true, 3, 8) : V4(true, 2, 8)) : (stages == 3 ? V4(false, 3, 8) : V4(false, 2, 8));
         return h->tw ? (stages == 3 ? V4(true, 3, 16) : V4(true, 2, 16)) : (stages == 3 ? V4(false, 3, 16) : V4(false, 2, 16));
 #undef V4
@@ -432,7 +440,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
     const bool v4 = c.gemm_path >= 4 && a.mode != 2;             // rollout4: greedy / stochastic; beam search stays on rollout3
-    const int nsw = c.gemm_path == 5 ? 8 : 16;                   // 5: eight row warps stream the per-row tail behind the scores
+    const int nsw = c.gemm_path == 5 ? 8 : c.gemm_path == 6 ? 17 : 16;   // 5: eight row warps stream the per-row tail; 6 (17): split variant
     const bool v3 = c.gemm_path == 3 || (c.gemm_path >= 4 && !v4);
     const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
     int stages3 = 2;
@@ -539,6 +547,15 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     { const char* tv = getenv("VRPB200_TUNE"); a.tune = tv ? atoi(tv) : 0; }
     a.sumv = h->sumv;
     memcpy(a.vm2, h->vm2, sizeof a.vm2);
+    if (c.gemm_path >= 4 && mode != VRPB200_BEAM) {   // rollout4 gathers node features as aligned 16-byte records
+        const int slot = h->ws_slot;
+        const long long nn = (long long)B * c.n_nodes;
+        int rc = ensure(h, &h->ws_feat4[slot], &h->ws_feat4_bytes[slot], (size_t)nn * sizeof(float4));
+        if (rc) return rc;
+        repack_features_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_input, h->ws_feat4[slot], nn, c.input_dim);
+        CUDA_TRY(h, cudaGetLastError());
+        a.feat4 = h->ws_feat4[slot];
+    }
     return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -583,8 +600,10 @@ int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int
         cudaStream_t st = h->streams[s];   // stream order protects the staging buffers of slot s
         CUDA_TRY(h, cudaMemcpyAsync(h->dev_in[s], (const char*)h_input + (size_t)off * inst_b, (size_t)nb * inst_b,
                                     cudaMemcpyHostToDevice, st));
+        h->ws_slot = s;
         rc = rollout_impl(h, h->dev_in[s], nb, mode, beam_width, nullptr, nullptr, seed, h->dev_idx[s], h->dev_cost[s],
                           nullptr, nullptr, &tr, st, off);
+        h->ws_slot = vrpb200_handle::kChunks;
         if (rc) return rc;
         ++launches;
         CUDA_TRY(h, cudaMemcpyAsync(h_cost + off, h->dev_cost[s], (size_t)nb * 4, cudaMemcpyDeviceToHost, st));

@@ -58,7 +58,7 @@ class Engine:
         if not torch.cuda.is_available():
             raise VrpB200Error("no CUDA device: the rollout path has no CPU implementation")
         self.args = dict(args)
-        self.cfg = config_from_args(args, rows_per_cta, {"tc2": 0, "ffma": 1, "tc": 2, "tc3": 3, "tc4": 4, "tc4s": 5}[gemm])
+        self.cfg = config_from_args(args, rows_per_cta, {"tc2": 0, "ffma": 1, "tc": 2, "tc3": 3, "tc4": 4, "tc4s": 5, "tc4x": 6}[gemm])
         self.device = torch.device("cuda", device)
         self.handle = C.c_void_p()
         rc = self.lib.vrpb200_create(C.byref(self.cfg), device, C.byref(self.handle))

@@ -53,7 +53,7 @@ FUSED_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
 
 @pytest.mark.parametrize("name", FUSED_CASES)
 @pytest.mark.parametrize("rows_per_cta", [0, 64])
-@pytest.mark.parametrize("gemm", ["tc4", "tc4s", "tc3", "tc2", "tc", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc", "ffma"])
 def test_rollout_matches_reference_fixture(name, rows_per_cta, gemm):
     fx, args, params = load_golden(name)
     meta = GOLDEN_INDEX[name]
@@ -86,7 +86,7 @@ def test_fast_path_equals_trace_path(name):
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
-@pytest.mark.parametrize("gemm", ["tc4", "tc4s", "tc3", "tc2", "tc", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc", "ffma"])
 def test_greedy_vs_oracle_seeded(task, B, seed, bias, gemm):
     """Ragged batch sizes, every task size; per-instance comparison up to the first near-tie."""
     args = O.default_args(task)
@@ -171,7 +171,7 @@ def test_host_entry_point_equals_device_entry_point():
     np.testing.assert_array_equal(cost_h, out.R.cpu().numpy())
 
 
-@pytest.mark.parametrize("gemm", ["tc4", "tc4s", "tc3", "tc2", "tc"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc"])
 def test_tensor_core_path_equals_fp32_path_up_to_near_ties(gemm):
     """The tcgen05 (3xTF32 split) GEMMs against the FP32-pipe GEMMs of the same kernel: logits within 2e-6,
     identical tours except at near-ties, every rows_per_cta."""

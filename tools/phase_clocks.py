@@ -30,14 +30,14 @@ blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
 names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epilogue", "C1 scores", "C2 select/env"] if gemm == "tc3" else
          ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"])
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
-if gemm in ("tc4", "tc4s"):
+if gemm in ("tc4", "tc4s", "tc4x"):
     names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
-             "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop", "rows: wait for logits", "rows: processing"]
-    for who, o in (("warp 2", 4), ("warp 12", 18)):
+             "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop", "rows: wait for logits", "rows: processing (rest)", "rows fast: prefetch issue", "rows fast: arg-max + merge", "rows fast: Env.step", "rows fast: feasibility + lists"]
+    for who, o in (("warp 2", 4),):
         print(" ", who)
         for n, v in zip(names, s[o:o + len(names)]):
             print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
-        print(f"    total {s[o:o + 14].sum() / blocksteps:.0f} clk/step")
+        print(f"    total {s[o:o + 28].sum() / blocksteps:.0f} clk/step")
     sys.exit(0)
 for n, v in zip(names, s[4:4 + len(names)]):
     print(f"  {n:40s} {v / blocksteps:10.0f} clk/step")
