@@ -58,7 +58,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=256, help="instances of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--rows-per-cta", type=int, default=0)
-    ap.add_argument("--kernel", default="tc4", choices=["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout4)")
+    ap.add_argument("--kernel", default="tc4x", choices=["tc4x", "tc4", "tc4s", "tc3", "tc2", "tc", "ffma"], help="fused kernel variant (default: rollout4)")
     return ap.parse_args()
 
 

@@ -466,6 +466,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     int RB = 0;
     if (c.rows_per_cta) {
         RB = c.rows_per_cta;
+        if (v4 && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
     } else {
         for (int i = 0; i < 4 && !RB; ++i) {
             const int rb = cand[i];

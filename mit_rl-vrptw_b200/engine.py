@@ -53,7 +53,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class Engine:
-    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0, gemm: str = "tc3"):
+    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0, gemm: str = "tc4x"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise VrpB200Error("no CUDA device: the rollout path has no CPU implementation")
