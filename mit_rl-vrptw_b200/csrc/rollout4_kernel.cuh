@@ -845,7 +845,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         }
                     }
                     VRP_CLK(14);
-                    // (1) arg-max (first index on ties) and runner-up over the items
+                    // (1) arg-max (first index on ties) over the items, and the largest logit strictly below the maximum.
+                    //     Exactly equal logits have exactly equal probabilities (first index wins, as in the reference); only a
+                    //     runner-up within 1e-5 BELOW the maximum could round to the same probability and needs the exact tail.
                     float mx = -INFINITY, second = -INFINITY;
                     int mxi = 0x7fffffff;
                     const int na = live ? nact_s[lrs] : 0;
@@ -853,17 +855,61 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     for (int k = sl; k < na; k += LPR) {
                         const int n = it[k];
                         const float u = ulog[n];
-                        if (u > mx || (u == mx && n < mxi)) { second = fmaxf(second, mx); mx = u; mxi = n; }
+                        if (u > mx) { second = mx; mx = u; mxi = n; }
+                        else if (u == mx) mxi = min(mxi, n);
                         else second = fmaxf(second, u);
                     }
 #pragma unroll
                     for (int o = LPR / 2; o; o >>= 1) {
                         const float ov = __shfl_xor_sync(kFull, mx, o), os = __shfl_xor_sync(kFull, second, o);
                         const int oi = __shfl_xor_sync(kFull, mxi, o);
-                        second = fmaxf(fmaxf(second, os), fminf(mx, ov));
+                        second = fmaxf(second, os);
+                        if (ov != mx) second = fmaxf(second, fminf(mx, ov));
                         if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                     }
-                    handled = !__any_sync(kFull, live && (fl != 0 || !(second < mx - 1e-5f)));
+                    handled = !__any_sync(kFull, live && fl != 0);
+                    if (handled && __any_sync(kFull, live && second > mx - 1e-5f)) {
+                        // near-tie: the reference takes argmax(prob) (attention_agent.py:146-147) and two close logits may round
+                        // to one probability, so evaluate the probabilities exactly as the exact tail does (masked nodes have
+                        // probability 0 and add 0 to the denominator; the mask bytes are kept as un-masked / masked flags)
+#ifdef VRPB200_PHASE_CLOCKS
+                        pc_[25] += 1;
+#endif
+                        float P0 = 0.0f, P1 = 0.0f, P2 = 0.0f, P3 = 0.0f;
+#pragma unroll 1
+                        for (int k = 0; k < 4; ++k) {
+                            const int nb = sl + 32 * k;
+                            float ev[4];
+#pragma unroll
+                            for (int qv = 0; qv < 4; ++qv) {
+                                const int n = nb + 8 * qv;
+                                const bool um = n < N && live && mk[n < N ? n : 0] == 0;
+                                ev[qv] = um ? expf(ulog[n] - mx) : 0.0f;
+                            }
+                            P0 = __fadd_rn(P0, ev[0]); P1 = __fadd_rn(P1, ev[1]); P2 = __fadd_rn(P2, ev[2]); P3 = __fadd_rn(P3, ev[3]);
+                        }
+                        float se = __fadd_rn(__fadd_rn(P0, P2), __fadd_rn(P1, P3));
+#pragma unroll
+                        for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
+                        const float lse = logf(se);
+                        float bestp = -1.0f;
+                        int besti = 0x7fffffff;
+#pragma unroll 1
+                        for (int j = 0; j < NJ; ++j) {
+                            const int n = sl + LPR * j;
+                            if (n < N) {
+                                const float p = (live && mk[n] == 0) ? expf((ulog[n] - mx) - lse) : 0.0f;
+                                if (p > bestp) { bestp = p; besti = n; }
+                            }
+                        }
+#pragma unroll
+                        for (int o = LPR / 2; o; o >>= 1) {
+                            const float ov = __shfl_xor_sync(kFull, bestp, o);
+                            const int oi = __shfl_xor_sync(kFull, besti, o);
+                            if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+                        }
+                        mxi = besti;
+                    }
                     VRP_CLK(15);
                     if (handled) {
                         const int idx = live ? mxi : 0;
@@ -930,12 +976,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                                 const unsigned below = (1u << sl) - 1;
                                 if (keep) al[nal2 + __popc(bk & below)] = (unsigned char)n;
                                 if (feas) it[nit + __popc(bf & below)] = (unsigned char)n;
+                                if (on && n >= 0) mk[n] = feas ? 0 : 1;      // un-masked / masked flag (the exact count is not needed)
                                 nal2 += __popc(bk);
                                 nit += __popc(bf);
                             }
                         }
                         const bool depot_ok = on && !(nz > 0.0f && dep != 0.0f);
                         if (depot_ok && sl == 0) it[nit] = (unsigned char)n_cust;
+                        if (on && sl == 0) mk[n_cust] = depot_ok ? 0 : 1;
                         nit += depot_ok ? 1 : 0;
                         int flv = 0;
                         if (on && nit == 0) {   // nothing un-masked: every node is evaluated, the mask counts decide (exact tail)
@@ -947,6 +995,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     }
                 }
                 if (!handled) {
+#ifdef VRPB200_PHASE_CLOCKS
+                    if (fastk) { pc_[26] += 1; pc_[27] += __popc(__ballot_sync(kFull, live && sl == 0 && (fl != 0))); }   // exact-tail visits of this warp; rows without un-masked node
+#endif
                     if (fastk) { recompute_masks(lrs, rvalid, sl, t); __syncwarp(); }
                     // ---- masked logits (decode_step.py:231-232) back into the row's slots; maximum, its first index, runner-up
                     float mx = -INFINITY, second = -INFINITY;
@@ -1176,7 +1227,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
 #ifdef VRPB200_PHASE_CLOCKS
         if (tid == 64)
-            for (int i = 0; i < 28; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)pc_[i]);
+            for (int i = 0; i < 25; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)pc_[i]);
+        if (lane == 0 && warp < 16) { atomicAdd(a.stats + 29, (unsigned long long)pc_[25]); atomicAdd(a.stats + 30, (unsigned long long)pc_[26]); atomicAdd(a.stats + 31, (unsigned long long)pc_[27]); }
 #endif
     }
     tc_fence_before();
