@@ -156,6 +156,8 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 for (int q = 0; q < 4; ++q) { mbar_init(bar_grp + 80 * g + 8 * q, 1); mbar_init(bar_grp + 80 * g + 32 + 8 * q, 4); }
                 mbar_init(bar_grp + 80 * g + 64, 4); mbar_init(bar_grp + 80 * g + 72, 4);
                 mbar_init(bar_grp + 160 + 8 * g, 4);   // split variant: the partial sums of a tile are in place
+                mbar_init(bar_grp + 176 + 8 * g, 4);   // split variant: ... and have been consumed (back-pressure: the producing
+                                                       // half may run at most one tile ahead, or the parity wait would alias)
             }
         }
         for (int i = 0; i < 64; ++i) mbar_init(bar_tile + 8 * i, 4);   // 4 arrivals per step: the 4 warps that scored the tile
@@ -401,6 +403,19 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     // C1: the two TMEM buffers of a group are used strictly in turn, so one counter of consumed quarters (every thread)
     // and one of issued quarters (issuer thread) give buffer index and mbarrier parity
     uint32_t c1_nq = 0, c1_ni = 0, c1_nf = 0;
+    // x part of the LSTM gates (rank D-1 through the linear embedding) and biases of this thread's unit.  They are (re)loaded
+    // right before the end-of-step barrier, so that the L2 latency is spent waiting there and not at the top of the epilogue
+    // (L1 keeps next to nothing beside 226 KB of shared memory)
+    float wx[4][4], bgt[4];
+    auto load_lstm_consts = [&]() {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            bgt[m] = ldcg_volatile(a.bgT + m * kH + unit);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) wx[k][m] = ldcg_volatile(a.WxT + (k * 4 + m) * kH + unit);
+        }
+    };
+    load_lstm_consts();
     unsigned long long n_eval = 0, n_rowsteps = 0;
     int t = 0;
 #pragma unroll 1
@@ -426,13 +441,6 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
         // ================= LSTM epilogue: gates = gates^T(TMEM, h part) + x part + bias ; c, h' ; h' -> X ==========
         {
-            float wx[4][4], bgt[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                bgt[m] = __ldg(a.bgT + m * kH + unit);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) wx[k][m] = __ldg(a.WxT + (k * 4 + m) * kH + unit);
-            }
             if (t > 0) {
                 mbar_wait(bar_g, (t - 1) & 1);
                 tc_fence_after();
@@ -499,7 +507,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         const uint32_t f_hi = smem_u32(fgrp), f_lo = f_hi + kC1TileBytes;
         const uint32_t d_g = tmem_base + 64 * g;
         const uint32_t bfull = bar_grp + (DEEP ? 80 : 40) * (g < NG ? g : 0), bfree = bfull + (DEEP ? 32 : 16),
-                       bfrdy = bfull + (DEEP ? 64 : 32), bpsum = bar_grp + 160 + 8 * (g < NG ? g : 0);
+                       bfrdy = bfull + (DEEP ? 64 : 32), bpsum = bar_grp + 160 + 8 * (g < NG ? g : 0), bpack = bpsum + 16;
         const bool issuer = (!DEEP && sp == 0 && lane == 0);
         // item `it` of the step -> (row, node): binary search in the row offsets, then the row's node list
         auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5], bool feats = true) {
@@ -684,7 +692,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             }
             if (scoring && SPLIT) {
                 // c1_nq counts the tiles of this group (all steps): tile k uses F tile k & 1, its quarter q TMEM buffer q.
-                // Warps 8g..8g+3 (half 0) gather the items, write F and take quarters 0, 1; warps 8g+4..8g+7 take quarters 2, 3
+                // Warps 8g..8g+3 (half 0) gather the items, write F and take quarters 0, 2; warps 8g+4..8g+7 take quarters 1, 3
                 // of the same items and hand their partial sum over through shared memory.
                 int r_n2 = 0, n_n2 = 0;
                 bool v_n2 = false;
@@ -697,7 +705,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
                     for (int qi = 0; qi < 2; ++qi) {
-                        const int q = 2 * half + qi;
+                        const int q = 2 * qi + half;      // half 0: quarters 0, 2; half 1: quarters 1, 3 (the MMAs land in order 0..3)
                         VRP_CLK(11);
                         mbar_wait(bfull + 8 * q, par);
                         tc_fence_after();
@@ -715,12 +723,16 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         VRP_CLK(10);
                     }
                     if (half == 1) {
+                        if (c1_nq > 0) mbar_wait(bpack, (c1_nq - 1) & 1);   // the other half has taken the previous tile's sums
                         ps[par * 128 + m] = acc0 + acc1;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bpsum);
                     } else {
-                        mbar_wait(bpsum, par);      // (also: quarters 2 and 3 of this tile have been read, its F tile is free)
-                        if (v_cur) logits[r_cur * NP + n_cur] = (a.sumv + (acc0 + acc1)) + ps[par * 128 + m];
+                        mbar_wait(bpsum, par);      // (also: quarters 1 and 3 of this tile have been read, its F tile is free)
+                        const float psv = ps[par * 128 + m];
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bpack);
+                        if (v_cur) logits[r_cur * NP + n_cur] = (a.sumv + (acc0 + acc1)) + psv;
                         n_eval += v_cur ? 1 : 0;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished
@@ -1178,6 +1190,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             if (lane == 0) done_s[warp] = warp_done;
             VRP_CLK(5);
         }
+        load_lstm_consts();
         named_bar(5, NT);
         int all_done = 1;
 #pragma unroll
