@@ -315,7 +315,10 @@ def main():
         tr_path = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tr_path):
             with open(tr_path) as f:
-                roofline["traffic"] = json.load(f).get(a.workload)
+                tr = json.load(f).get(a.workload)
+                if tr:   # DRAM bytes of one launch: measured per instance in the (smaller) ncu capture, scaled to this launch
+                    roofline["traffic"] = tr["dram_bytes_per_instance"] * Bg
+                    roofline["traffic_source"] = tr
         value = Bg * world * a.steps / (ms_total * 1e-3)
         line = {"metric": METRIC, "value": value, "unit": "instances/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
