@@ -160,6 +160,14 @@ int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp
 int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t R, int A, float* d_cost,
                    void* stream);
 
+/* reward_func(sample_solution, decode_len, n_nodes, depot) with a depot - the min_trucks objective
+ * (VRPTW/vrptw_utils.py:384-395, 410-412; VRP/vrp_utils.py:275-285, 302-304): d_actions [T, R, A] (A = 2: x, y; A = 4:
+ * x, y, b_tw, e_tw), d_depot [R, A] -> d_reward [R] = 70/n_nodes x depot returns + 30 x route length / sum of the
+ * distances to the depot.  As in the reference the depot test compares column 0 only and the normalising distance
+ * runs over all A columns. */
+int vrpb200_reward_min_trucks(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
+                              float n_nodes, float* d_reward, void* stream);
+
 /* Measured throughput of one SM pipe on the handle's device, for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: kind 0 = MUFU (ex2/rcp, ops/s), 1 = FP32 FMA (FMA/s, 2 flop each).
  * Runs a register-only micro-benchmark on every SM for ~`iters` x 4096 ops per thread.  Synchronous. */

@@ -280,6 +280,42 @@ __global__ void reward_kernel(const float* __restrict__ actions, long long T, lo
     cost[r] = s;
 }
 
+// ---- reward_func with a depot ("min_trucks": VRPTW/vrptw_utils.py:384-395, 410-412; VRP/vrp_utils.py:275-285, 302-304):
+// 70/n_nodes x returns to the depot (a stay counts once; the test compares column 0 only, as the reference does)
+// + 30 x route length (first XY columns) / sum over steps of the distance to the depot over ALL A action columns
+__global__ void reward_min_trucks_kernel(const float* __restrict__ actions, const float* __restrict__ depot, long long T, long long R,
+                                         int A, int XY, float inv_n_nodes, float* reward) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const float* dp = depot + r * A;
+    float counter = 0.0f, visits = 0.0f, route = 0.0f, maxlen = 0.0f;
+    const float* last = actions + ((T - 1) * R + r) * A;
+    float prev[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < XY; ++c) prev[c] = last[c];
+    for (long long t = 0; t < T; ++t) {
+        const float* at = actions + (t * R + r) * A;
+        const float interm = (at[0] == dp[0]) ? 1.0f : 0.0f;
+        if (t == 0) visits = interm;
+        else {
+            counter = __fadd_rn(__fmul_rn(counter, interm), interm);
+            visits = __fadd_rn(visits, __fmul_rn(interm, counter < 1.5f ? 1.0f : 0.0f));
+        }
+        float s = 0.0f, m = 0.0f;
+        for (int c = 0; c < A; ++c) {
+            const float dm = __fsub_rn(dp[c], at[c]);
+            m = __fadd_rn(m, __fmul_rn(dm, dm));
+            if (c < XY) {
+                const float dr = __fsub_rn(prev[c], at[c]);
+                s = __fadd_rn(s, __fmul_rn(dr, dr));
+                prev[c] = at[c];
+            }
+        }
+        route = __fadd_rn(route, __fsqrt_rn(s));
+        maxlen = __fadd_rn(maxlen, __fsqrt_rn(m));
+    }
+    reward[r] = __fadd_rn(__fmul_rn(70.0f, __fmul_rn(inv_n_nodes, visits)), __fmul_rn(30.0f, __fdiv_rn(route, maxlen)));
+}
+
 // ---- pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not hold -----------------
 // kind 0: MUFU (ex2 + rcp alternating, 8 independent chains per thread); kind 1: FP32 FMA (16 chains).
 // [B, N, D] instances (D = 3: x, y, demand; D = 5: x, y, b_tw, e_tw, demand) -> [B, N] float4 (x, y, b_tw, e_tw):

@@ -419,15 +419,19 @@ class VRPTWEnv(_EnvBase):
 
 
 def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
-    """Tour length of a decoded solution, depot=None branch (VRPTW/vrptw_utils.py:397-414, VRP/vrp_utils.py:293-307).
-    sample_solution: list of T tensors [R, >=2] or a tensor [T, R, >=2].  The min_trucks branches are out of scope."""
+    """reward_func of VRPTW/vrptw_utils.py:361-414 and VRP/vrp_utils.py:257-307.
+    sample_solution: list of T tensors [R, A] or a tensor [T, R, A].
+    depot=None: closed tour length over x, y (:397-414).  depot [R, A]: the min_trucks objective (:384-395, 410-412),
+    70/n_nodes x returns to the depot + 30 x route length / sum of the distances to the depot."""
     import torch
-    if depot is not None:
-        raise NotImplementedError("min_trucks reward (depot != None) is outside the rollout path (SURVEY section 8f, N2)")
     sol = sample_solution if isinstance(sample_solution, torch.Tensor) else torch.stack(list(sample_solution), 0)
     sol = sol.to(device="cuda", dtype=torch.float32).contiguous()
     args = dict(task_name="vrp", n_nodes=2, n_cust=1, input_dim=3, embedding_dim=1, hidden_dim=128, decode_len=1, capacity=1.0)
-    return _get_engine(args, _dummy_model_params(args), ("reward",)).reward(sol)
+    eng = _get_engine(args, _dummy_model_params(args), ("reward",))
+    if depot is None:
+        return eng.reward(sol)
+    dep = depot.to(device="cuda", dtype=torch.float32).contiguous()
+    return eng.reward_min_trucks(sol, dep, float(n_nodes))
 
 
 class DataGenerator(object):

@@ -270,6 +270,30 @@ def reward_func(actions: Sequence[np.ndarray], tw: bool) -> np.ndarray:
     return np.sum(np.power(np.sum(np.power(tilted - sol, dt(2)), 2), dt(0.5)), 0)
 
 
+def reward_func_min_trucks(actions: Sequence[np.ndarray], depot: np.ndarray, decode_len: int, n_nodes: float, tw: bool) -> np.ndarray:
+    """``reward_func(sample_solution, decode_len, n_nodes, depot)`` with a depot: 70/n_nodes x (returns to the depot,
+    consecutive stays counted once) + 30 x route length / sum of the distances to the depot
+    (VRPTW/vrptw_utils.py:384-395, 410-412; VRP/vrp_utils.py:275-285, 302-304).
+
+    As written: the depot test compares COLUMN 0 only (``tf.equal(...)[:, 0]``); the normalising length sums over ALL
+    action columns (for VRPTW: x, y, b_tw, e_tw - it is computed before the slice to x, y)."""
+    dt = actions[0].dtype.type
+    counter = np.zeros_like(depot)[:, 0]
+    visits = (actions[0] == depot).astype(dt)[:, 0]
+    for i in range(1, len(actions)):
+        interm = (actions[i] == depot).astype(dt)[:, 0]
+        counter = counter * interm + interm
+        visits = visits + interm * (counter < 1.5).astype(dt)
+    max_length = np.stack([depot for _ in range(decode_len)], 0)
+    sol = np.stack(actions, 0)
+    max_lens = np.sum(np.power(np.sum(np.power(max_length - sol, dt(2)), 2), dt(0.5)), 0)
+    if tw:
+        sol = sol[:, :, :2]
+    tilted = np.concatenate([sol[-1:], sol[:-1]], 0)
+    route = np.sum(np.power(np.sum(np.power(tilted - sol, dt(2)), 2), dt(0.5)), 0)
+    return dt(70.0) * (dt(1.0 / n_nodes) * visits) + dt(30.0) * (route / max_lens)
+
+
 # --------------------------------------------------------------------------- #
 # model pieces
 # --------------------------------------------------------------------------- #

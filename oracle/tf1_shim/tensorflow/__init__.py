@@ -85,6 +85,10 @@ class Tensor:
 def _wrap(x):
     if isinstance(x, Tensor):
         return x
+    if isinstance(x, (list, tuple)) and x and all(isinstance(v, Tensor) for v in x):
+        # TF's constant conversion packs a python list of tensors along a new axis 0 (ops.convert_to_tensor ->
+        # array_ops.stack): reward_func subtracts the LIST sample_solution from a stacked tensor (vrptw_utils.py:394)
+        return Tensor(lambda *vs: np.stack(vs, 0), list(x))
     return Tensor(lambda: x, [], kind="const")
 
 

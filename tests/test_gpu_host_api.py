@@ -170,3 +170,19 @@ def test_evaluate_batch_and_checkpoint_by_name(tmp_path):
     np.testing.assert_allclose(Rg, ref.R, rtol=1e-4)
     np.testing.assert_allclose(Rb, O.best_of_beams(refb.R, 64, 3), rtol=1e-4)
     assert Rb.shape == (64,)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", ["vrp", "vrptw"])
+def test_min_trucks_reward_kernel_matches_reference_fixture(task):
+    """host.reward_func(..., depot) -> vrpb200_reward_min_trucks against the output of the reference's own reward_func
+    (tests/golden/reward_min_trucks.npz); fp32 sums in a different order: 1e-5 relative."""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    pkg = load_pkg()
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    acts = [torch.from_numpy(a).cuda() for a in fx[f"{task}_actions"]]
+    dep = torch.from_numpy(fx[f"{task}_depot"]).cuda()
+    r = pkg.host.reward_func(acts, int(fx[f"{task}_T"]), float(fx[f"{task}_n_nodes"]), dep)
+    np.testing.assert_allclose(r.cpu().numpy(), fx[f"{task}_reward"], rtol=1e-5)

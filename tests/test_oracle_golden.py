@@ -60,3 +60,34 @@ def test_env_matches_reference_code(name, task, W):
         np.testing.assert_array_equal(st.d_sat, fx["d_sat"][t + 1])
         if args["task_name"] == "vrptw":
             np.testing.assert_array_equal(st.time, fx["time"][t + 1])
+
+
+@pytest.mark.parametrize("task,tw", [("vrp", False), ("vrptw", True)])
+def test_min_trucks_reward_matches_reference_code(task, tw):
+    """reward_func with a depot (VRPTW/vrptw_utils.py:384-395, 410-412): the oracle against the output of the reference's
+    own function (tests/golden/make_golden_reward.py), bit for bit."""
+    import os
+    from tests.helpers import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    acts = [a for a in fx[f"{task}_actions"]]
+    r = O.reward_func_min_trucks(acts, fx[f"{task}_depot"], int(fx[f"{task}_T"]), float(fx[f"{task}_n_nodes"]), tw)
+    np.testing.assert_array_equal(r, fx[f"{task}_reward"])
+
+
+def test_min_trucks_reward_known_answer():
+    """Hand-computed.  Depot (0,0); tour depot, depot, (3,4), depot, (1,1).  The reference's counter starts at 0 whatever
+    step 0 is, so the stay at steps 0-1 counts twice (1 for step 0, 1 for step 1 with counter 1 < 1.5), the return at
+    step 3 once: visits = 3.  Route (closed, last -> first): sqrt2 + 0 + 5 + 5 + sqrt2; distances to the depot 0 + 0 + 5 +
+    0 + sqrt2.  A third consecutive depot step would not count (counter 2), and the depot test looks at x only."""
+    dep = np.zeros((1, 2), np.float32)
+    pts = [(0, 0), (0, 0), (3, 4), (0, 0), (1, 1)]
+    acts = [np.array([p], np.float32) for p in pts]
+    r = O.reward_func_min_trucks(acts, dep, len(pts), 4.0, tw=False)
+    s2 = np.sqrt(2.0)
+    np.testing.assert_allclose(r, [70.0 * (3 / 4.0) + 30.0 * ((10 + 2 * s2) / (5 + s2))], rtol=1e-6)
+    # three consecutive depot steps: the third is not a new return; a node sharing the depot's x counts as the depot
+    pts = [(0, 0), (0, 0), (0, 0), (3, 4), (0, 7)]
+    acts = [np.array([p], np.float32) for p in pts]
+    r = O.reward_func_min_trucks(acts, dep, len(pts), 4.0, tw=False)
+    route = 7 + 0 + 0 + 5 + np.hypot(3, 3)
+    np.testing.assert_allclose(r, [70.0 * (3 / 4.0) + 30.0 * (route / (5 + 7))], rtol=1e-6)
