@@ -90,6 +90,48 @@ def create_dataset(task_name: str, n_problems: int, n_cust: int, seed: int, ups:
     return create_vrptw_ups_dataset(n_problems, n_cust, seed) if ups else create_vrptw_dataset(n_problems, n_cust, seed)
 
 
+def dataset_file_name(task_name: str, n_problems: int, n_nodes: int, data_type: str, ups: bool = False) -> str:
+    """File names of the reference's generators: 'vrp-size-{B}-len-{N}-{type}.txt' (VRP/vrp_utils.py:36),
+    'vrptw-size-...' (VRPTW/vrptw_utils.py:38), 'vrp-ups-size-...' / 'vrptw-ups-size-...' (UPS/*_utils.py:34-35)."""
+    return "{}{}-size-{}-len-{}-{}.txt".format(task_name, "-ups" if ups else "", n_problems, n_nodes, data_type)
+
+
+def load_or_create_dataset(task_name: str, n_problems: int, n_cust: int, data_dir: str, seed, data_type: str = "test",
+                           ups: bool = False) -> np.ndarray:
+    """create_VRP_dataset / create_VRPTW_dataset of the reference WITH their on-disk format (VRP/vrp_utils.py:10-53,
+    VRPTW/vrptw_utils.py:10-67, UPS twins): an existing '<task>-size-B-len-N-<type>.txt' is loaded (np.loadtxt, one
+    instance per line, N*D numbers), otherwise the instances are generated and saved with np.savetxt in that layout."""
+    n_nodes = n_cust + 1
+    D = 5 if task_name == "vrptw" else 3
+    fname = os.path.join(data_dir, dataset_file_name(task_name, n_problems, n_nodes, data_type, ups))
+    if os.path.exists(fname):
+        return np.loadtxt(fname, delimiter=" ").reshape(-1, n_nodes, D)
+    data = create_dataset(task_name, n_problems, n_cust, seed, ups=ups)
+    os.makedirs(data_dir, exist_ok=True)
+    np.savetxt(fname, data.reshape(-1, n_nodes * D))
+    return data
+
+
+def write_results(fname: str, all_output, task_name: str, n_nodes: int) -> None:
+    """RLAgent._output_results (model/attention_agent.py:416-459): one line per decoded problem - the visited nodes
+    'x y' (vrp) or 'x y b_tw e_tw' (vrptw) separated by blanks, starting at the depot, cut after the last customer has
+    been seen (a node differs from the depot when |dx| >= 0.001 or |dy| >= 0.001) and closed with the depot - the format
+    evaluation/benchmark reads."""
+    k = 2 if task_name == "vrp" else 4
+    with open(fname, "w") as f:
+        for output in all_output:
+            depot = output[0]
+            nb_stop = 0
+            for node in output:
+                f.write(" ".join(str(v) for v in node[:k]) + " ")
+                if abs(depot[0] - node[0]) >= 0.001 or abs(depot[1] - node[1]) >= 0.001:
+                    nb_stop += 1
+                if nb_stop == n_nodes - 1:
+                    f.write(" ".join(str(v) for v in depot[:k]))
+                    break
+            f.write("\n")
+
+
 def glorot_params(args: dict, seed: int = 1234) -> dict:
     """'random-init' weights: Glorot-uniform kernels and v, zero biases (tf.layers defaults),
     keyed by TF-1 variable name."""

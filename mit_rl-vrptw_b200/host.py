@@ -441,8 +441,12 @@ class DataGenerator(object):
         self.args = args
         self.rnd = np.random.RandomState(seed=args['random_seed'])
         self.n_problems = args['test_size']
-        self.test_data = _data.create_dataset(args['task_name'], self.n_problems, args['n_cust'], args['random_seed'] + 1,
-                                              ups=bool(args.get('ups', False)))
+        if args.get('data_dir'):   # the reference's on-disk test set: loaded if the file exists, else created and saved
+            self.test_data = _data.load_or_create_dataset(args['task_name'], self.n_problems, args['n_cust'], args['data_dir'],
+                                                          args['random_seed'] + 1, 'test', ups=bool(args.get('ups', False)))
+        else:
+            self.test_data = _data.create_dataset(args['task_name'], self.n_problems, args['n_cust'], args['random_seed'] + 1,
+                                                  ups=bool(args.get('ups', False)))
         self.reset()
 
     def reset(self):
@@ -670,20 +674,47 @@ class RLAgent(object):
         return R
 
     def evaluate_single(self, eval_type='greedy'):
-        """attention_agent.py:336-413 (B=1 latency mode): one problem at a time through the same path."""
+        """attention_agent.py:336-413 (B=1 latency mode): one problem at a time through the same path; the decoded routes
+        are written in the reference's result-file format when args['log_dir'] is set (_output_results, :416-471)."""
         import torch
         beam_width = self.args['beam_width'] if eval_type == 'beam_search' else 1
         self.dataGen.reset()
-        rewards = []
+        rewards, all_output = [], []
         start_time = time.time()
         for _ in range(self.dataGen.n_problems):
-            self.env.input_data = torch.as_tensor(np.asarray(self.dataGen.get_test_next(), np.float32))
-            R = self.build_model(eval_type)[0].cpu().numpy()
-            rewards.append(float(np.amin(R.reshape(beam_width, -1), 0)[0]))
+            batch = np.asarray(self.dataGen.get_test_next(), np.float32)
+            self.env.input_data = torch.as_tensor(batch)
+            out = self.build_model(eval_type)
+            R = out[0].cpu().numpy().reshape(beam_width, -1)
+            best = int(np.argmin(R[:, 0]))
+            rewards.append(float(R[best, 0]))
+            actions = out[3]                                              # T x [R, D-1]
+            route = [list(batch[0, self.env.n_nodes - 1, :])]             # "we begin by the depot"
+            for a_t in actions:
+                route.append([float(v) for v in a_t[best * batch.shape[0]].cpu().numpy()])
+            all_output.append(route)
         end_time = time.time() - start_time
         self.prt.print_out('Average of {} in single-mode: {} -- std {} -- time {} s'.format(
             eval_type, np.mean(rewards), np.sqrt(np.var(rewards)), end_time))
+        if self.args.get('log_dir'):
+            self._output_results(all_output, eval_type)
         return np.asarray(rewards)
+
+    def _output_results(self, all_output, eval_type):
+        """attention_agent.py:416-471: '<log_dir>/results/<task>[-ups]-size-B-len-N-results-<eval_type>.txt' (+ a copy of
+        the test set file next to it when args['data_dir'] holds one)."""
+        import shutil
+        a = self.args
+        dir_name = os.path.join(a['log_dir'], 'results')
+        os.makedirs(dir_name, exist_ok=True)
+        ups = bool(a.get('ups', False))
+        stem = '{}{}-size-{}-len-{}'.format(a['task_name'], '-ups' if ups else '', a['test_size'], self.env.n_nodes)
+        _data.write_results(os.path.join(dir_name, stem + '-results-{}.txt'.format(eval_type)), all_output, a['task_name'],
+                            self.env.n_nodes)
+        if a.get('data_dir'):
+            src = os.path.join(a['data_dir'], stem + '-test.txt')
+            if os.path.exists(src):
+                shutil.copyfile(src, os.path.join(dir_name, stem + '-test.txt'))
 
     def inference(self, infer_type='batch'):
         if infer_type == 'batch':

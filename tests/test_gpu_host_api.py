@@ -186,3 +186,33 @@ def test_min_trucks_reward_kernel_matches_reference_fixture(task):
     dep = torch.from_numpy(fx[f"{task}_depot"]).cuda()
     r = pkg.host.reward_func(acts, int(fx[f"{task}_T"]), float(fx[f"{task}_n_nodes"]), dep)
     np.testing.assert_allclose(r.cpu().numpy(), fx[f"{task}_reward"], rtol=1e-5)
+
+
+@pytest.mark.gpu
+def test_evaluate_single_writes_reference_result_files(tmp_path):
+    """evaluate_single (attention_agent.py:336-413) + _output_results (:416-471): one route per problem in the result file,
+    each route a valid VRPTW route over the instance's nodes starting and ending at the depot."""
+    import torch
+    pkg = load_pkg()
+    H = pkg.host
+    args = pkg.task_specific_params.default_args("vrptw10", test_size=5, random_seed=11, beam_width=3)
+    args.update(log_dir=str(tmp_path / "logs"), data_dir=str(tmp_path / "data"), batch_size=1, ups=False)
+    (tmp_path / "logs").mkdir()
+    DataGenerator, Env, reward_func, Actor, Critic = H.load_task_specific_components("vrptw", False)
+    dataGen = DataGenerator(args)
+    assert (tmp_path / "data" / "vrptw-size-5-len-11-test.txt").exists()
+    agent = H.RLAgent(args, None, Env(args), dataGen, reward_func, Actor, Critic, is_train=False, store=H.VariableStore(seed=7))
+    agent.Initialize(None)
+    R = agent.evaluate_single("greedy")
+    assert R.shape == (5,) and np.isfinite(R).all()
+    res = tmp_path / "logs" / "results" / "vrptw-size-5-len-11-results-greedy.txt"
+    assert res.exists() and (tmp_path / "logs" / "results" / "vrptw-size-5-len-11-test.txt").exists()
+    lines = res.read_text().strip().split("\n")
+    assert len(lines) == 5
+    data = dataGen.get_test_all()
+    for b, ln in enumerate(lines):
+        v = np.array([float(t) for t in ln.split(" ")]).reshape(-1, 4)
+        np.testing.assert_allclose(v[0], data[b, -1, :4], rtol=1e-6)       # starts at the depot
+        np.testing.assert_allclose(v[-1], data[b, -1, :4], rtol=1e-6)      # closed with the depot
+        nodes = {tuple(np.round(r, 5)) for r in data[b, :, :4]}
+        assert all(tuple(np.round(r, 5)) in nodes for r in v)

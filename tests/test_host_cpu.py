@@ -130,3 +130,36 @@ def test_sharding_and_cost_gather_two_ranks_gloo(n):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert got == [2.0 * i for i in range(n)]
+
+
+def test_dataset_files_round_trip_in_the_reference_format(tmp_path):
+    """create_VRP(TW)_dataset's on-disk format (VRP/vrp_utils.py:36-53, VRPTW/vrptw_utils.py:38-67): name
+    '<task>-size-B-len-N-<type>.txt', one instance per line; a second call loads the file instead of generating."""
+    pkg = load_pkg()
+    d = pkg.data
+    for task, D in (("vrp", 3), ("vrptw", 5)):
+        a = d.load_or_create_dataset(task, 7, 10, str(tmp_path), seed=5, data_type="test")
+        f = tmp_path / f"{task}-size-7-len-11-test.txt"
+        assert f.exists()
+        rows = f.read_text().strip().split("\n")
+        assert len(rows) == 7 and len(rows[0].split(" ")) == 11 * D
+        b = d.load_or_create_dataset(task, 7, 10, str(tmp_path), seed=999, data_type="test")   # other seed: the FILE wins
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, d.create_dataset(task, 7, 10, 5))
+    assert d.dataset_file_name("vrptw", 3, 101, "test", ups=True) == "vrptw-ups-size-3-len-101-test.txt"
+
+
+def test_result_file_format(tmp_path):
+    """_output_results (model/attention_agent.py:416-459): 'x y b e ' per visited node from the depot on, cut when the
+    last customer has been seen, closed with the depot."""
+    pkg = load_pkg()
+    depot = [0.5, 0.5, 0.0, 8.0]
+    c1, c2 = [0.1, 0.2, 1.0, 2.0], [0.9, 0.8, 3.0, 4.0]
+    route = [depot, c1, depot, c2, depot, depot]          # n_nodes = 3: two customers
+    f = tmp_path / "res.txt"
+    pkg.data.write_results(str(f), [route], "vrptw", 3)
+    toks = f.read_text().strip().split(" ")
+    vals = [float(t) for t in toks]
+    assert vals == depot + c1 + depot + c2 + depot        # stops after the second customer, then the depot once
+    pkg.data.write_results(str(f), [[d[:2] for d in route]], "vrp", 3)
+    assert [float(t) for t in f.read_text().strip().split(" ")] == depot[:2] + c1[:2] + depot[:2] + c2[:2] + depot[:2]
