@@ -83,6 +83,27 @@ def test_fast_path_equals_trace_path(name):
     assert int(fast.steps.max()) <= args["decode_len"]
 
 
+@pytest.mark.parametrize("gemm", ["tc4x", "tc4", "tc4s"])
+@pytest.mark.parametrize("task,B,seed,ups", [("vrptw100", 1500, 21, True), ("vrptw100", 700, 22, False), ("vrptw20", 900, 23, False),
+                                             ("vrp50", 500, 24, False), ("vrp100", 300, 25, True), ("vrptw50", 777, 26, True)])
+def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
+    """The MEASURED path: plain greedy decoding (no log-probabilities, traces or final state requested) runs rollout4's fast
+    per-row tail - arg-max over the item list, exact soft-max only on near-ties, feasibility only for customers with demand
+    left.  It must give bit-identical tours and costs to the exact tail (which the other tests pin against the oracle),
+    in particular on UPS instances, whose saturated logits produce ties and near-ties all the time."""
+    pkg = load_pkg()
+    args = O.default_args(task)
+    params = pkg.data.glorot_params(args, seed=seed)
+    data = pkg.data.create_dataset(args["task_name"], B, args["n_cust"], seed, ups=ups).astype(np.float32)
+    eng, torch = _engine(args, params, gemm=gemm)
+    x = torch.from_numpy(data).cuda()
+    fast = eng.rollout(x, "greedy")
+    exact = eng.rollout(x, "greedy", want_logprobs=True, final_state=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fast.idxs, exact.idxs)
+    assert torch.equal(fast.R, exact.R)
+
+
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
