@@ -277,7 +277,7 @@ def main():
             fp32_ops = 8.0 * H * node_evals + 30.0 * H * gemm_rowsteps
             tensor_flops = 3 * 2.0 * gemm_macs                                           # 3xTF32 split
         elif a.kernel in ("tc4x", "tc4", "tc4s"):
-            fp32_ops = 7.25 * H * node_evals + 46.0 * H * gemm_rowsteps                  # add, clamp, +1, shared-reciprocal algebra
+            fp32_ops = 7.25 * H * node_evals + 46.0 * H * gemm_rowsteps                  # add, clamp, +1, shared-reciprocal algebra (lane-ops; issued as packed FP32x2: 3.25 issue slots + 1 clamp per element)
             tensor_flops = 3 * 2.0 * (gemm_macs + score_macs * 8.0 / 5.0)
         else:
             fp32_ops = 4.0 * H * node_evals + 46.0 * H * gemm_rowsteps                   # tanh/dot epilogue; LSTM epilogue + x part

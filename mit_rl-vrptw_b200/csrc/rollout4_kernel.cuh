@@ -79,6 +79,46 @@ VRP_DEVINL float ldcg_volatile(const float* p) {
     asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
+// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 - two results per issue slot) -------------------------
+#ifndef VRP_EMU_PAIRS
+#define VRP_EMU_PAIRS 0   // pairs (of 4 per group of 8 elements) whose 2^x runs on the FMA pipe; 0 = all on the MUFU pipe
+#endif
+typedef unsigned long long f32x2;
+VRP_DEVINL f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+VRP_DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+VRP_DEVINL f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+VRP_DEVINL f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+VRP_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+// 1 + 2^x for two values on the FMA pipe (no MUFU): x clamped to [-126, 30], n = round(x) through the 1.5 * 2^23 trick,
+// 2^(x - n) by a degree-5 polynomial on [-0.5, 0.5] (max relative error 2.5e-7, the size of ex2.approx's), exponent added
+// to the bit pattern.  14 issue slots per pair against 2 MUFU instructions of 8 clk each.
+VRP_DEVINL f32x2 one_plus_ex2_fma2(float x0, float x1) {
+    x0 = fmaxf(fminf(x0, 30.0f), -126.0f);
+    x1 = fmaxf(fminf(x1, 30.0f), -126.0f);
+    const f32x2 x = pk2(x0, x1);
+    const f32x2 t = add2(x, pk2(12582912.0f, 12582912.0f));
+    const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
+    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), x);
+    f32x2 p = pk2(0.0013400432653725147f, 0.0013400432653725147f);
+    p = fma2(p, f, pk2(0.009676037356257439f, 0.009676037356257439f));
+    p = fma2(p, f, pk2(0.05550327152013779f, 0.05550327152013779f));
+    p = fma2(p, f, pk2(0.2402210682630539f, 0.2402210682630539f));
+    p = fma2(p, f, pk2(0.6931471824645996f, 0.6931471824645996f));
+    p = fma2(p, f, pk2(1.0000001192092896f, 1.0000001192092896f));
+    float p0, p1, t0, t1;
+    upk2(p, p0, p1);
+    upk2(t, t0, t1);
+    const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+    const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+    return add2(pk2(e0, e1), pk2(1.0f, 1.0f));
+}
+// named barrier that also AND-reduces a predicate over its participants (one barrier instead of flags + two barriers)
+VRP_DEVINL int named_bar_and(int id, int nthreads, int pred) {
+    int r;
+    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.and.pred p, %1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(r) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
+    return r;
+}
 VRP_DEVINL float4 ldcg4_volatile(const float4* p) {
     float4 v;
     asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -559,31 +599,37 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         // 32 hidden units of one item: acc += sum_h w_h / (1 + 2^(E_h + base'_h)), w = -2 v, 16 independent elements at a
         // time, ONE reciprocal per 4 elements:  (w0 t1 + w1 t0) t2 t3 + (w2 t3 + w3 t2) t0 t1  over  t0 t1 t2 t3
         // (t = 1 + 2^min(arg, 30) <= 2^30 + 1: the product cannot overflow, and tanh is 1.0f exactly from arg = 26 on)
+        // 8 elements at a time as four pairs P0..P3 = (e0,e1) .. (e6,e7); the two quads that share one reciprocal each are
+        // the .x and the .y lanes of the pairs, so the whole shared-reciprocal algebra is packed FP32x2 arithmetic; the last
+        // pair of every group of eight takes its 2^x from the FMA pipe instead of the MUFU pipe (6 ex2 + 2 rcp per 8 elements)
         auto quarter_arith = [&](const uint32_t (&cur)[32], const float* bq, const float* vq, float& acc0, float& acc1) {
+            f32x2 acc = pk2(acc0, acc1);
+            const f32x2 one = pk2(1.0f, 1.0f);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-                float e[16];
+            for (int g8 = 0; g8 < 4; ++g8) {
+                const float4 ba = *reinterpret_cast<const float4*>(bq + 8 * g8), bb = *reinterpret_cast<const float4*>(bq + 8 * g8 + 4);
+                const float4 va = *reinterpret_cast<const float4*>(vq + 8 * g8), vb = *reinterpret_cast<const float4*>(vq + 8 * g8 + 4);
+                f32x2 P[4];
+                P[0] = add2(pk2(__uint_as_float(cur[8 * g8 + 0]), __uint_as_float(cur[8 * g8 + 1])), pk2(ba.x, ba.y));
+                P[1] = add2(pk2(__uint_as_float(cur[8 * g8 + 2]), __uint_as_float(cur[8 * g8 + 3])), pk2(ba.z, ba.w));
+                P[2] = add2(pk2(__uint_as_float(cur[8 * g8 + 4]), __uint_as_float(cur[8 * g8 + 5])), pk2(bb.x, bb.y));
+                P[3] = add2(pk2(__uint_as_float(cur[8 * g8 + 6]), __uint_as_float(cur[8 * g8 + 7])), pk2(bb.z, bb.w));
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bq + 16 * hf + 4 * k4);
-                    e[4 * k4 + 0] = __uint_as_float(cur[16 * hf + 4 * k4 + 0]) + b4.x;
-                    e[4 * k4 + 1] = __uint_as_float(cur[16 * hf + 4 * k4 + 1]) + b4.y;
-                    e[4 * k4 + 2] = __uint_as_float(cur[16 * hf + 4 * k4 + 2]) + b4.z;
-                    e[4 * k4 + 3] = __uint_as_float(cur[16 * hf + 4 * k4 + 3]) + b4.w;
+                for (int i = 0; i < 4; ++i) {
+                    float x, y;
+                    upk2(P[i], x, y);
+                    if (i >= 4 - VRP_EMU_PAIRS) P[i] = one_plus_ex2_fma2(x, y);
+                    else P[i] = add2(pk2(ex2_approx(fminf(x, 30.0f)), ex2_approx(fminf(y, 30.0f))), one);
                 }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) e[i] = 1.0f + ex2_approx(fminf(e[i], 30.0f));
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                    const float4 v4 = *reinterpret_cast<const float4*>(vq + 16 * hf + 4 * k4);
-                    const float t0 = e[4 * k4], t1 = e[4 * k4 + 1], t2 = e[4 * k4 + 2], t3 = e[4 * k4 + 3];
-                    const float p01 = t0 * t1, p23 = t2 * t3;
-                    const float n01 = fmaf(v4.x, t1, v4.y * t0), n23 = fmaf(v4.z, t3, v4.w * t2);
-                    const float num = fmaf(n01, p23, n23 * p01);
-                    const float r = rcp_approx(p01 * p23);
-                    if (k4 & 1) acc1 = fmaf(num, r, acc1); else acc0 = fmaf(num, r, acc0);
-                }
+                const f32x2 V0 = pk2(va.x, va.y), V1 = pk2(va.z, va.w), V2 = pk2(vb.x, vb.y), V3 = pk2(vb.z, vb.w);
+                const f32x2 p01 = mul2(P[0], P[1]), p23 = mul2(P[2], P[3]);
+                const f32x2 n01 = fma2(V0, P[1], mul2(V1, P[0])), n23 = fma2(V2, P[3], mul2(V3, P[2]));
+                const f32x2 num = fma2(n01, p23, mul2(n23, p01));
+                float dx, dy;
+                upk2(mul2(p01, p23), dx, dy);
+                acc = fma2(num, pk2(rcp_approx(dx), rcp_approx(dy)), acc);
             }
+            upk2(acc, acc0, acc1);
         };
         int r_cur = 0, n_cur = 0, r_nx = 0, n_nx = 0;
         bool v_cur = false, v_nx = false;
@@ -792,6 +838,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
             }
             VRP_CLK(5);
         }
+        int my_done = 1;   // every row of this warp is finished (warps without rows: vacuously)
         if (NSW == 16 ? warp < RB / 4 : warp >= 8) {
             // ================= per-row tail: log-softmax, choice, Env.step, mask, next item list ==========================
             // 8 lanes per row, lane sl owns nodes sl, sl + 8, ...; masked logits and probabilities live in the row's logits
@@ -1187,16 +1234,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 warp_done &= __all_sync(kFull, !live || done_now);
                 VRP_CLK(13);
             }
-            if (lane == 0) done_s[warp] = warp_done;
+            my_done = warp_done;
             VRP_CLK(5);
         }
         load_lstm_consts();
-        named_bar(5, NT);
-        int all_done = 1;
-#pragma unroll
-        for (int w = 0; w < 16; ++w) all_done &= done_s[w];
+        const int all_done = named_bar_and(5, NT, my_done);   // end of the step: one barrier that also tells whether every row is done
         VRP_CLK(6);
-        named_bar(5, NT);
         if (all_done) { ++t; break; }
     }
     if (tid == 0) {
