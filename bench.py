@@ -329,7 +329,7 @@ def main():
                 "e2e": {"value": Bg * world * a.steps / e2e_s, "unit": "instances/s", "h2d_bytes_per_step": Bg * N * D * 4,
                         "d2h_bytes_per_step": Bg * 4 + T * Bg * 4, "api": "vrpb200_rollout_host (pinned host buffers, chunked copy/decode overlap)",
                         "kernel_launches_per_step": e2e_launches},
-                "gpu_launches": a.steps * 1}
+                "gpu_launches": a.steps * (2 if a.kernel.startswith("tc4") else 1)}   # rollout4: feature re-packing kernel + fused rollout kernel per step
         if not a.no_cpu_baseline and world == 1:
             rate, sec = cpu_reference_rate(task, ups, pkg, a.cpu_sample, 1, 1)
             line["cpu_baseline"] = {"value": rate, "unit": "instances/s", "cores": cores, "kind": "port",

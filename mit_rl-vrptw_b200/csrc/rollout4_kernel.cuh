@@ -1,20 +1,22 @@
-// rollout4_kernel: rollout3 with the per-row tail of the decode step (selection, Env.step, mask, item list) taken off
-// the critical path and the pointer-score phase re-built as a real software pipeline.
+// rollout4_kernel: the fused rollout (RLAgent.build_model of model/attention_agent.py:84-240, greedy and stochastic) with
+// the per-step work organised around the two resources that bind it, the MUFU pipe and the issue slots.
 //
-//  * warp specialisation inside the step: compute warps 0..11 (three groups of four) evaluate the pointer scores (C1);
-//    compute warps 12..15 are "row warps": as soon as every tile that holds items of a row has been scored they run
-//    log-softmax, the choice, Env.step, the new mask AND the item list of the next step for that row (8 lanes per row,
-//    16 rows in flight), while the score warps keep the MUFU pipe busy with the tiles of later rows;
-//  * C1 per group: the 128 hidden units of a 128-item tile arrive in four N = 32 quarters that alternate between two
-//    TMEM buffers; a quarter is copied to registers as soon as its MMA has landed, which frees the buffer, so the MMA two
-//    quarters ahead is always in flight behind the arithmetic; the features of the NEXT tile are fetched from L2
-//    (volatile loads, issued before the arithmetic of this tile) and written to the F tile when the last MMA of this tile
-//    has completed; the arithmetic runs on 16 independent elements at a time (v_h comes from the constant bank);
-//  * q^T has its own TMEM columns (192..255), so the first tiles of a step are staged and their MMAs issued while the
-//    query GEMM is still running;
-//  * item lists are per row (node ids, uint8); a tile finds the row of an item with a binary search in the row offsets.
+//  * 16 compute warps + 4 single-thread service warps (weight feeder, LSTM/query MMA issuer, two score-MMA issuers); the
+//    service threads wait on mbarriers with a suspend hint (asleep in hardware, no issue slots);
+//  * pointer scores (C1): 128-item tiles (item = un-masked (row, node)); E = F.Bc on tcgen05 in four N = 32 quarters; per
+//    group 4 TMEM quarter buffers and 2 F tiles, so the MMAs of the NEXT tile are in flight while this one is computed.
+//    Template variants: NSW 16 + SPLIT (default: two groups of 8 warps, the two warps of a TMEM sub-partition share a
+//    tile's items and split the hidden units), NSW 16 (four groups, 2 buffers each, lock-step), NSW 8 (two groups score,
+//    8 row warps stream the per-row tail behind them);
+//  * tanh at 1.25 MUFU per element: four reciprocals share one rcp, evaluated as packed FP32x2 arithmetic;
+//  * per-row item lists (node ids) and lists of the customers with demand left; a tile finds the row of an item with a
+//    binary search in the row offsets; node features are gathered as 16-byte records (repack_features_kernel);
+//  * per-row tail: a warp starts as soon as the tiles of its rows are done (one mbarrier per tile); plain greedy decoding
+//    takes the fast tail (arg-max of the logits, exact soft-max only on near-ties, feasibility only for customers with
+//    demand left), everything else the exact tail (log-softmax, probabilities, sampling, mask counts, traces);
+//  * q^T has its own TMEM columns, so the first tiles of a step are staged while the query GEMM is still running.
 //
-// Greedy and stochastic decoding; beam search stays on rollout3 (rows of one instance compete, no per-row streaming).
+// Beam search stays on rollout3 (rows of one instance compete for the beam slots, no per-row streaming).
 #pragma once
 #include "rollout3_kernel.cuh"
 
@@ -689,7 +691,6 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
 
         if (warp < NSW) {
             // ================= C1: scores =================================================================
-            if (a.tune > 0 && (g & 1)) __nanosleep(a.tune);   // experiment: odd groups start later (warps of one SM sub-partition out of phase)
             if (scoring && !DEEP) {
                 float fn[5];
 #pragma unroll 1

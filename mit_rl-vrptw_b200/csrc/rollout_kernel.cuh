@@ -95,7 +95,6 @@ struct RolloutArgs {
     int use_tanh, mask_pointer;
     float capacity, tanh_C, forget_bias;
     const float4* feat4;     // rollout4: [B, N] (x, y, b_tw, e_tw) re-packed copy of the node features (repack_features_kernel)
-    int tune;                // experiments only (VRPB200_TUNE): start offset in ns of the odd score groups of rollout4
     float sumv;              // rollout4: sum_h v_h of the pointer attention
     float vm2[128];          // rollout4: -2 v_h (read as constant-bank operands)
 };

@@ -545,7 +545,6 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.seed = seed; a.B = B; a.row_base = row_base; a.W = mode == VRPB200_BEAM ? beam_width : 1; a.N = c.n_nodes; a.n_cust = c.n_cust; a.D = c.input_dim; a.T = c.decode_len;
     a.mode = mode; a.use_tanh = c.use_tanh; a.mask_pointer = c.mask_pointer;
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
-    { const char* tv = getenv("VRPB200_TUNE"); a.tune = tv ? atoi(tv) : 0; }
     a.sumv = h->sumv;
     memcpy(a.vm2, h->vm2, sizeof a.vm2);
     if (c.gemm_path >= 4 && mode != VRPB200_BEAM) {   // rollout4 gathers node features as aligned 16-byte records
