@@ -104,6 +104,36 @@ def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
     assert torch.equal(fast.R, exact.R)
 
 
+@pytest.mark.parametrize("gemm", ["tc4x", "tc4", "tc4s"])
+def test_fast_tail_hands_rows_without_unmasked_node_to_the_exact_tail(gemm):
+    """Time windows that close almost immediately: after its first customer a vehicle finds every other customer too late,
+    returns to the depot, and there NO node is un-masked (the depot is masked while demand is left).  The reference then
+    takes the arg-max over logit - 1e5 x mask COUNT (decode_step.py:231-232); the fast tail keeps no counts and must hand
+    such rows to the exact tail (masks recomputed from the row state).  Plain decoding must equal the exact tail, and the
+    situation must actually occur (some instance decodes a node whose mask count is non-zero)."""
+    pkg = load_pkg()
+    args = O.default_args("vrptw20")
+    params = pkg.data.glorot_params(args, seed=31)
+    data = pkg.data.create_dataset("vrptw", 96, args["n_cust"], 32).astype(np.float32)
+    data[:, :-1, 2] = 0.0          # b_tw
+    data[:, :-1, 3] = 0.02         # e_tw: only reachable as the first stop after the (TW-free) initial mask ... never again
+    eng, torch = _engine(args, params, gemm=gemm)
+    x = torch.from_numpy(data).cuda()
+    fast = eng.rollout(x, "greedy")
+    exact = eng.rollout(x, "greedy", want_logprobs=True, trace=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fast.idxs, exact.idxs)
+    assert torch.equal(fast.R, exact.R)
+    # the trace shows rows whose every node is masked at some step, and the chosen node has a non-zero mask count there
+    allmasked = (exact.masks > 0).all(2)                       # [T, R]
+    assert bool(allmasked.any())
+    chosen_mask = torch.gather(exact.masks, 2, exact.idxs.long().unsqueeze(2)).squeeze(2)
+    assert bool((chosen_mask[allmasked] > 0).all())
+    ref = O.rollout(params, args, data.astype(np.float64), "greedy")
+    same = (exact.idxs.cpu().numpy().astype(np.int64) == ref.idxs).all(0)
+    assert same.mean() >= 0.95
+
+
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
