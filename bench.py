@@ -189,7 +189,11 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's own banner must not share stdout with the JSON line
+        # NCCL's own banner ("NCCL version ...", printed on stdout with NCCL_DEBUG=VERSION) must not share stdout with the
+        # JSON line: keep warnings only unless the caller asked for more, and send whatever NCCL prints to stderr
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = pkg.Engine(args, device=local_rank, rows_per_cta=a.rows_per_cta, gemm=a.kernel)
     eng.set_weights(pkg.data.glorot_params(args, seed=1234))
