@@ -95,3 +95,44 @@ def test_greedy_rollout_properties(seed, task, bias):
     for b in range(min(B, 4)):
         pts = [tuple(data[b, i, :2].astype(np.float32)) for i in res.idxs[:, b]]
         assert abs(float(tour_length(pts)) - float(res.R[b])) <= 1e-4 * max(1.0, float(res.R[b]))
+
+
+def _scalar_min_trucks(route, depot, n_nodes, xy):
+    """Independent scalar restatement of reward_func with a depot (VRPTW/vrptw_utils.py:384-395, 410-412), one instance,
+    plain Python floats rounded to fp32 where the reference's fp32 ops round."""
+    f = np.float32
+    counter, visits = f(0), f(1.0 if route[0][0] == depot[0] else 0.0)
+    for p in route[1:]:
+        interm = f(1.0 if p[0] == depot[0] else 0.0)
+        counter = f(f(counter * interm) + interm)
+        visits = f(visits + f(interm * f(1.0 if counter < 1.5 else 0.0)))
+    maxlen, length, prev = f(0), f(0), route[-1]
+    for p in route:
+        m = f(0)
+        for c in range(len(depot)):
+            m = f(m + f(f(depot[c] - p[c]) ** 2))
+        maxlen = f(maxlen + f(np.power(m, f(0.5))))
+        s = f(0)
+        for c in range(xy):
+            s = f(s + f(f(prev[c] - p[c]) ** 2))
+        length = f(length + f(np.power(s, f(0.5))))
+        prev = p
+    return f(f(70.0) * f(f(1.0 / n_nodes) * visits) + f(f(30.0) * f(length / maxlen)))
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 10 ** 6), st.integers(3, 25), st.booleans())
+def test_min_trucks_reward_equals_independent_scalar_restatement(seed, T, tw):
+    rnd = np.random.RandomState(seed)
+    A, N = (4 if tw else 2), 7
+    nodes = np.round(rnd.uniform(0, 1, size=(N, A)), 3).astype(np.float32)
+    depot = nodes[-1]
+    idx = rnd.randint(0, N, size=T)
+    idx[rnd.uniform(size=T) < 0.4] = N - 1
+    route = [nodes[i] for i in idx]
+    if all((p == depot).all() for p in route):
+        route[0] = nodes[0]                       # the reference divides by the summed distance to the depot
+    acts = [p[None, :] for p in route]
+    got = O.reward_func_min_trucks(acts, depot[None, :], T, float(N), tw)[0]
+    want = _scalar_min_trucks(route, depot, float(N), 2)
+    np.testing.assert_allclose(got, want, rtol=3e-6)
