@@ -58,13 +58,12 @@ typedef struct vrpb200_config {
     int32_t mask_glimpses;   /* shared/decode_step.py:222-223 */
     int32_t mask_pointer;    /* shared/decode_step.py:231-232 */
     int32_t rows_per_cta;    /* 0 = choose; else 16/32/48/64 (tuning knob, no effect on results) */
-    int32_t gemm_path;       /* fused kernel variant (every variant gives the same results up to fp32 rounding):
-                                0 = rollout2 (LSTM, query AND pointer scores on tcgen05, 3xTF32 split, TMEM accumulators),
-                                1 = rollout v1, GEMMs on the FP32 pipe, 2 = rollout v1 with tcgen05 LSTM/query GEMMs,
-                                3 = rollout3 (transposed GEMMs, streaming warp; the only variant with fused beam search),
-                                4 = rollout4 lock-step, 5 = rollout4 with 8 row warps, 6 = rollout4 split (default of the
-                                Python host: per-row item lists, fast greedy tail, shared-reciprocal tanh, deep MMA
-                                buffering).  4..6 run beam search on rollout3. */
+    int32_t gemm_path;       /* fused kernel family (every family gives the same results up to fp32 rounding):
+                                0 = default (rollout4; beam search on rollout3),
+                                1 = everything on the FP32 pipe (independent cross-check of the tensor-core kernels),
+                                3 = rollout3 (transposed tcgen05 GEMMs, lock-step phases, fused beam search),
+                                6 = rollout4, split variant (per-row item lists, fast greedy tail, shared-reciprocal
+                                    tanh, deep MMA buffering); runs beam search on rollout3. */
     float capacity;
     float tanh_exploration;  /* C */
     float forget_bias;       /* BasicLSTMCell forget_bias, shared/decode_step.py:175 */

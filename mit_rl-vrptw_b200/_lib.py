@@ -42,24 +42,49 @@ EXPORTS = (
     "vrpb200_pipe_peak",
 )
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+BUILD_DIR = os.path.join(HERE, "build")
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """nvcc -> mit_rl-vrptw_b200/lib/libvrpb200.so (sm_100a only; cross-compiles without a GPU)."""
+def _translation_units():
+    return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def build_library(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = None) -> str:
+    """nvcc -> mit_rl-vrptw_b200/lib/libvrpb200.so (sm_100a only; cross-compiles without a GPU).
+    One object per translation unit of csrc/ (the kernel families compile in parallel), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    out_path = out_path or LIB_PATH
     srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
+    if not force and not extra_flags and os.path.exists(out_path) and all(os.path.getmtime(out_path) >= os.path.getmtime(s) for s in srcs):
+        return out_path
+    os.makedirs(os.path.dirname(out_path), exist_ok=True)
+    tag = "" if out_path == LIB_PATH else "_" + os.path.splitext(os.path.basename(out_path))[0]
+    bdir = BUILD_DIR + tag
+    os.makedirs(bdir, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "vrpb200_api.cu")]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    headers_mtime = max(os.path.getmtime(s) for s in srcs if not s.endswith(".cu"))
+
+    def compile_one(tu):
+        src, obj = os.path.join(CSRC, tu), os.path.join(bdir, tu[:-3] + ".o")
+        if not force and not extra_flags and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), headers_mtime):
+            return obj, ""
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {tu}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, _translation_units()))
     if verbose:
-        print(res.stderr)
-    return LIB_PATH
+        for _, log in results:
+            print(log)
+    res = subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", out_path] + [o for o, _ in results],
+                         capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    return out_path
 
 
 _lib = None

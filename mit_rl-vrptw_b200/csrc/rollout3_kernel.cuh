@@ -11,17 +11,10 @@
 //    q(t) first (the critical path waits for it), then the 512 KB of gates(t+1) in the background of phases C0/C1/C2;
 //  * TMEM: columns 0..255 pointer-score tiles (q^T re-uses 0..63 before them), 256..511 gates^T.
 #pragma once
-#include "rollout2_kernel.cuh"
+#include "common.cuh"
 
 namespace vrpb200 {
 
-constexpr int kV3Threads = 544;
-constexpr int kV3UsesQ = 8;     // 2 k-chunks of W_q^T per 16 KB stage
-#ifdef VRP_EXP_NOGATES   // timing experiment only: drop the gates GEMM (results are wrong)
-constexpr int kV3UsesG = 0;
-#else
-constexpr int kV3UsesG = 32;    // (k-chunk, pair of gate types) per stage
-#endif
 constexpr int kV3GateCol = 256;
 
 struct Smem3 {
@@ -52,70 +45,6 @@ __host__ __device__ inline Smem3 make_layout3(int RB, int IB, int N, int FD, int
     return L;
 }
 
-VRP_DEVINL void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
-VRP_DEVINL void tc_ld4(uint32_t taddr, float (&v)[4]) {
-    uint32_t r0, r1, r2, r3;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
-}
-// TMEM load split into issue + wait so that the load can overlap arithmetic; the wait carries the destination
-// registers as in/out operands, which keeps the compiler from consuming them early
-VRP_DEVINL void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-}
-VRP_DEVINL void tc_ld_wait16(uint32_t (&r)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-                 :
-                 : "memory");
-}
-// 4x4 transpose across the 4 lanes of a quad: in: a[i] = M[lane&3][i]; out: a[i] = M[i][lane&3]
-VRP_DEVINL void transpose4(float (&a)[4], int lane) {
-    const bool b0 = lane & 1, b1 = lane & 2;
-    {
-        const float s0 = b0 ? a[0] : a[1], s1 = b0 ? a[2] : a[3];
-        const float r0 = __shfl_xor_sync(kFull, s0, 1), r1 = __shfl_xor_sync(kFull, s1, 1);
-        if (b0) { a[0] = r0; a[2] = r1; } else { a[1] = r0; a[3] = r1; }
-    }
-    {
-        const float s0 = b1 ? a[0] : a[2], s1 = b1 ? a[1] : a[3];
-        const float r0 = __shfl_xor_sync(kFull, s0, 2), r1 = __shfl_xor_sync(kFull, s1, 2);
-        if (b1) { a[0] = r0; a[1] = r1; } else { a[2] = r0; a[3] = r1; }
-    }
-}
-
-// sum_n exp(logit[n] - max) of one row held by LPR lanes (lane sl owns nodes sl + LPR j), added in ONE fixed order
-// whatever LPR is - the order a full warp would use (node n -> lane n % 32, slots n / 32 in sequence, then the xor
-// butterfly 16, 8, 4, 2, 1) - so that the choice of rows per CTA can never move a near-tie.
-template <int LPR>
-VRP_DEVINL float softmax_denominator(const float (&lg)[128 / LPR], float mx) {
-    constexpr int NQ = 32 / LPR;
-    float P[NQ];
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        float acc = 0.0f;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float u = lg[q + NQ * k];
-            acc = __fadd_rn(acc, (u == -INFINITY) ? 0.0f : expf(u - mx));
-        }
-        P[q] = acc;
-    }
-    float se;
-    if (NQ == 4) se = __fadd_rn(__fadd_rn(P[0], P[2 % NQ]), __fadd_rn(P[1 % NQ], P[3 % NQ]));
-    else if (NQ == 2) se = __fadd_rn(P[0], P[1 % NQ]);
-    else se = P[0];
-#pragma unroll
-    for (int o = LPR / 2; o; o >>= 1) se = __fadd_rn(se, __shfl_xor_sync(kFull, se, o));
-    return se;
-}
 
 template <int RB, bool TW, int STAGES>
 __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutArgs a) {
@@ -190,7 +119,6 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.bar + 120);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
     constexpr uint32_t idescL = tc_idesc(128, RB), idescS = tc_idesc(128, 64);
-#define VRP_XDESC(base, kc) tc_desc((base) + (kc) * 256, 128, 4096)
 
     if (warp == 16) {
         // ============ streaming warp: lane 0 feeds the ring from L2, lane 1 issues every LSTM / query MMA ============
@@ -700,7 +628,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                         if (n < N) dem[lr * NP + n] = dn[j];
                     }
                 }
-                const int done_now = (!a.full && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
+                const int done_now = (!a.full && a.mask_pointer && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
                 if (rvalid && sl == 0) {
                     rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
                     if (t == 0) { rs[4] = 0.0f; rs[5] = sx; rs[6] = sy; }
@@ -834,7 +762,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             }
 #pragma unroll
             for (int o = LPR / 2; o; o >>= 1) sumdem += __shfl_xor_sync(kFull, sumdem, o);
-            const int done_now = (!a.full && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
+            const int done_now = (!a.full && a.mask_pointer && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
             if (live && sl == 0) {
                 rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
                 if (t == 0) { rs[5] = sx; rs[6] = sy; }

@@ -18,11 +18,10 @@
 //
 // Beam search stays on rollout3 (rows of one instance compete for the beam slots, no per-row streaming).
 #pragma once
-#include "rollout3_kernel.cuh"
+#include "common.cuh"
 
 namespace vrpb200 {
 
-constexpr int kV4Threads = 640;   // 16 compute warps + weight feeder warp + LSTM/query MMA issuer warp + 2 score-MMA issuer warps
 
 struct Smem4 {
     int ring, X, qq, F, logits, items, alive, bc, vsm, psum, dem, mask, rs, meta, bar, total, stages;
@@ -53,80 +52,6 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
     return L;
 }
 
-VRP_DEVINL void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-VRP_DEVINL void tc_ld_wait32(uint32_t (&r)[32]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                   "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
-                   "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
-                   "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-VRP_DEVINL void mbar_arrive_n(uint32_t bar, uint32_t n) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
-}
-VRP_DEVINL float ldcg_volatile(const float* p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-// ---- packed FP32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 - two results per issue slot) -------------------------
-#ifndef VRP_EMU_PAIRS
-#define VRP_EMU_PAIRS 0   // pairs (of 4 per group of 8 elements) whose 2^x runs on the FMA pipe; 0 = all on the MUFU pipe
-#endif
-typedef unsigned long long f32x2;
-VRP_DEVINL f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-VRP_DEVINL void upk2(f32x2 v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-VRP_DEVINL f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-VRP_DEVINL f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-VRP_DEVINL f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-// 1 + 2^x for two values on the FMA pipe (no MUFU): x clamped to [-126, 30], n = round(x) through the 1.5 * 2^23 trick,
-// 2^(x - n) by a degree-5 polynomial on [-0.5, 0.5] (max relative error 2.5e-7, the size of ex2.approx's), exponent added
-// to the bit pattern.  14 issue slots per pair against 2 MUFU instructions of 8 clk each.
-VRP_DEVINL f32x2 one_plus_ex2_fma2(float x0, float x1) {
-    x0 = fmaxf(fminf(x0, 30.0f), -126.0f);
-    x1 = fmaxf(fminf(x1, 30.0f), -126.0f);
-    const f32x2 x = pk2(x0, x1);
-    const f32x2 t = add2(x, pk2(12582912.0f, 12582912.0f));
-    const f32x2 n = add2(t, pk2(-12582912.0f, -12582912.0f));
-    const f32x2 f = fma2(n, pk2(-1.0f, -1.0f), x);
-    f32x2 p = pk2(0.0013400432653725147f, 0.0013400432653725147f);
-    p = fma2(p, f, pk2(0.009676037356257439f, 0.009676037356257439f));
-    p = fma2(p, f, pk2(0.05550327152013779f, 0.05550327152013779f));
-    p = fma2(p, f, pk2(0.2402210682630539f, 0.2402210682630539f));
-    p = fma2(p, f, pk2(0.6931471824645996f, 0.6931471824645996f));
-    p = fma2(p, f, pk2(1.0000001192092896f, 1.0000001192092896f));
-    float p0, p1, t0, t1;
-    upk2(p, p0, p1);
-    upk2(t, t0, t1);
-    const float e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-    const float e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-    return add2(pk2(e0, e1), pk2(1.0f, 1.0f));
-}
-// named barrier that also AND-reduces a predicate over its participants (one barrier instead of flags + two barriers)
-VRP_DEVINL int named_bar_and(int id, int nthreads, int pred) {
-    int r;
-    asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.b32 q, %3, 0;\n\tbar.red.and.pred p, %1, %2, q;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                 : "=r"(r) : "r"(id), "r"(nthreads), "r"(pred) : "memory");
-    return r;
-}
-VRP_DEVINL float4 ldcg4_volatile(const float4* p) {
-    float4 v;
-    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-VRP_DEVINL int lds_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
 
 // NSW = number of score warps:
 //   16 -> every warp scores (4 groups, 2 TMEM quarter buffers each, the MMAs are issued by a thread of the group), then
@@ -620,8 +545,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 for (int i = 0; i < 4; ++i) {
                     float x, y;
                     upk2(P[i], x, y);
-                    if (i >= 4 - VRP_EMU_PAIRS) P[i] = one_plus_ex2_fma2(x, y);
-                    else P[i] = add2(pk2(ex2_approx(fminf(x, 30.0f)), ex2_approx(fminf(y, 30.0f))), one);
+                    P[i] = add2(pk2(ex2_approx(fminf(x, 30.0f)), ex2_approx(fminf(y, 30.0f))), one);
                 }
                 const f32x2 V0 = pk2(va.x, va.y), V1 = pk2(va.z, va.w), V2 = pk2(vb.x, vb.y), V3 = pk2(vb.z, vb.w);
                 const f32x2 p01 = mul2(P[0], P[1]), p23 = mul2(P[2], P[3]);
@@ -1185,7 +1109,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     if (d_idx != 0.0f && d_new == 0.0f) nz -= 1.0f;
                     if (live && sl == 0) drow[idx] = d_new;
                     __syncwarp();
-                    done_now = (!a.full && idx == n_cust && nz == 0.0f) ? 1 : 0;
+                    done_now = (!a.full && a.mask_pointer && idx == n_cust && nz == 0.0f) ? 1 : 0;
                     if (live && sl == 0) {
                         rs[0] = nload; rs[1] = ntime; rs[2] = sx; rs[3] = sy;
                         if (t == 0) { rs[5] = sx; rs[6] = sy; }

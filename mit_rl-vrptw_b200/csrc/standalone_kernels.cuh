@@ -4,7 +4,7 @@
 // caller can drive the reference's step-by-step protocol against device state, and so that the fused
 // kernel can be cross-checked on the GPU against an independent formulation.
 #pragma once
-#include "rollout_kernel.cuh"
+#include "common.cuh"
 
 namespace vrpb200 {
 

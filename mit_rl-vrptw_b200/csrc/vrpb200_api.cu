@@ -14,10 +14,7 @@
 #include <vector>
 
 #include <cstdlib>
-#include "rollout_kernel.cuh"
-#include "rollout2_kernel.cuh"
-#include "rollout3_kernel.cuh"
-#include "rollout4_kernel.cuh"
+#include "launchers.h"
 #include "standalone_kernels.cuh"
 
 using namespace vrpb200;
@@ -38,7 +35,6 @@ struct vrpb200_handle {
     // offsets (in floats) into the blob
     const float* Wg = nullptr;
     const float* bg = nullptr;
-    const float* WgTc = nullptr;
     const float *WgT3 = nullptr, *WxT = nullptr, *bgT = nullptr;
     const float* WqTc[8] = {nullptr};
     AttWeights att[8];
@@ -131,7 +127,8 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path < 0 || c.gemm_path > 6) return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0..6");
+    if (c.gemm_path != 0 && c.gemm_path != 1 && c.gemm_path != 3 && c.gemm_path != 6)
+        return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (default), 1 (FP32 pipe), 3 (rollout3) or 6 (rollout4)");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -220,7 +217,6 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     // layout [slab s][kk 8][uh 2][part 2][lane 32][gate 4], unit = uh*64 + 2*lane + part, k = 8 s + kk.
     const size_t oWg = reserve((size_t)kGateSlabs * kSlabFloats);
     const size_t obg = reserve(4 * H);
-    const size_t oWgTc = reserve((size_t)kTcUsesA * kSlabFloats);
     const size_t oWgT3 = reserve((size_t)kV3UsesG * kSlabFloats), oWxT = reserve(16 * H), obgT = reserve(4 * H);
     {
         std::vector<double> Wx((size_t)D1 * 4 * H, 0.0), bx(4 * H, 0.0);
@@ -270,22 +266,6 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                 for (int cc = 0; cc < 4; ++cc)
                     blob[oWxT + (cc * 4 + m) * H + unit] = cc < D1 ? (float)Wx[(size_t)cc * 4 * H + m * H + unit] : 0.0f;
             }
-        // tcgen05 path: per (k-chunk, N-half) stage a hi tile and a lo tile, [N=256][K=8] canonical K-major no-swizzle
-        // ([n/8][k/4][n%8][k%4]); n = 4*unit_local + gate, unit = 64*half + unit_local
-        for (int u = 0; u < kTcUsesA; ++u) {
-            const int kc = u >> 1, half = u & 1;
-            for (int n = 0; n < 256; ++n)
-                for (int kl = 0; kl < 8; ++kl) {
-                    const int unit = half * 64 + n / 4, g = n % 4, k = kc * 8 + kl, col = g * H + unit;
-                    float val = 0.0f;
-                    if (k < H) val = lstm_k[(size_t)(E + k) * 4 * H + col];
-                    else if (k - H < D1) val = (float)Wx[(size_t)(k - H) * 4 * H + col];
-                    const float hi = tf32_round(val), lo = tf32_round(val - hi);
-                    const size_t o = (size_t)(n / 8) * 64 + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
-                    blob[oWgTc + (size_t)u * kSlabFloats + o] = hi;
-                    blob[oWgTc + (size_t)u * kSlabFloats + 2048 + o] = lo;
-                }
-        }
     }
     struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc; };
     std::vector<AttOff> ao(natt);
@@ -295,8 +275,8 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         o.Wq = put(r.pq_k, (size_t)H * H);   // [k][unit] row-major == 4 slabs of 32 k-rows
         o.bq = reserve(H); o.A = reserve(4 * H); o.gd = reserve(H); o.gl = reserve(H); o.gt = reserve(H);
         o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H);
-        o.WqTc = reserve((size_t)kTcUsesB * kSlabFloats);
-        for (int u = 0; u < kTcUsesB; ++u)
+        o.WqTc = reserve((size_t)kV3UsesQ * kSlabFloats);
+        for (int u = 0; u < kV3UsesQ; ++u)
             for (int kk = 0; kk < 2; ++kk)
                 for (int n = 0; n < H; ++n)
                     for (int kl = 0; kl < 8; ++kl) {
@@ -356,7 +336,6 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     const float* d = h->d_blob;
     h->Wg = d + oWg;
     h->bg = d + obg;
-    h->WgTc = d + oWgTc;
     h->WgT3 = d + oWgT3; h->WxT = d + oWxT; h->bgT = d + obgT;
     for (int a = 0; a < natt; ++a) {
         h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
@@ -390,120 +369,54 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
 
 namespace {
 
-template <int RB, bool TW, bool TC>
-int launch_rollout_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout_kernel<RB, TW, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout_kernel<RB, TW, TC><<<grid, TC ? 512 : RB * 8, smem, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
-    return 0;
-}
-
-template <int RB, bool TW>
-int launch_rollout2_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout2_kernel<RB, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout2_kernel<RB, TW><<<grid, 512, smem, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
-    return 0;
-}
-
-template <int RB, bool TW, int STAGES>
-int launch_rollout3_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout3_kernel<RB, TW, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout3_kernel<RB, TW, STAGES><<<grid, kV3Threads, smem, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
-    return 0;
-}
-
-template <int RB, bool TW, int STAGES, int NSW, bool SPLIT = false>
-int launch_rollout4_t(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    CUDA_TRY(h, cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, NSW, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    rollout4_kernel<RB, TW, STAGES, NSW, SPLIT><<<grid, kV4Threads, smem, st>>>(a);
-    CUDA_TRY(h, cudaGetLastError());
-    return 0;
-}
-
-template <int RB>
-int launch_rollout4_any(vrpb200_handle* h, const RolloutArgs& a, int grid, int smem, cudaStream_t st, int stages, int nsw) {
-    if constexpr (RB <= 48) {
-#define V4(TWv, STv, NSv) launch_rollout4_t<RB, TWv, STv, NSv>(h, a, grid, smem, st)
-        if (nsw == 17) return h->tw ? (stages == 3 ? launch_rollout4_t<RB, true, 3, 16, true>(h, a, grid, smem, st) : launch_rollout4_t<RB, true, 2, 16, true>(h, a, grid, smem, st))
-                                    : (stages == 3 ? launch_rollout4_t<RB, false, 3, 16, true>(h, a, grid, smem, st) : launch_rollout4_t<RB, false, 2, 16, true>(h, a, grid, smem, st));
-        if (nsw == 8) return h->tw ? (stages == 3 ? V4(true, 3, 8) : V4(true, 2, 8)) : (stages == 3 ? V4(false, 3, 8) : V4(false, 2, 8));
-        return h->tw ? (stages == 3 ? V4(true, 3, 16) : V4(true, 2, 16)) : (stages == 3 ? V4(false, 3, 16) : V4(false, 2, 16));
-#undef V4
-    } else {
-        return fail(h, VRPB200_E_ARG, "rollout4 supports rows_per_cta <= 48");
-    }
-}
+// gemm_path -> kernel family.  0 picks the default (rollout4 split; beam search on rollout3).
+enum Family { kFamFfma = 1, kFamV3 = 3, kFamV4 = 6 };
 
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
-    const bool v4 = c.gemm_path >= 4 && a.mode != 2;             // rollout4: greedy / stochastic; beam search stays on rollout3
-    const int nsw = c.gemm_path == 5 ? 8 : c.gemm_path == 6 ? 17 : 16;   // 5: eight row warps stream the per-row tail; 6 (17): split variant
-    const bool v3 = c.gemm_path == 3 || (c.gemm_path >= 4 && !v4);
-    const bool v2 = c.gemm_path == 0, tc = c.gemm_path != 1;
-    int stages3 = 2;
+    int fam = c.gemm_path == 0 ? kFamV4 : c.gemm_path;
+    if (fam == kFamV4 && a.mode == 2) fam = kFamV3;              // beam search: rollout3
+    int stages = 2;
     auto smem_of = [&](int rb) {
-        if (v4) {
-            if (rb > 48) return 1 << 30;                        // TMEM: q^T and the score buffers need their own columns
-            stages3 = make_layout4(rb, c.n_nodes, 3, nsw).total <= h->max_smem_optin ? 3 : 2;
-            return make_layout4(rb, c.n_nodes, stages3, nsw).total;
-        }
-        if (v3) {
-            if (rb < a.W) return 1 << 30;                       // every beam of an instance lives in one CTA
-            const int ib = rb / a.W, np = (c.n_nodes + 3) / 4 * 4;
-            if (a.W > 1 && 1024 + rb * (np * 4 + np + kRowState * 4) > 8 * kC1TileBytes) return 1 << 30;   // beam gather scratch
-            stages3 = make_layout3(rb, ib, c.n_nodes, FD, 3).total <= h->max_smem_optin ? 3 : 2;
-            return make_layout3(rb, ib, c.n_nodes, FD, stages3).total;
-        }
-        if (v2) return layout2_fits_U(rb, c.n_nodes) ? make_layout2(rb, rb, c.n_nodes, FD).total : (1 << 30);
-        return make_layout(rb, rb, c.n_nodes, FD, tc).total;
+        if (fam == kFamV4) return smem_rollout4(rb, c.n_nodes, h->max_smem_optin, &stages);
+        if (fam == kFamV3) return smem_rollout3(rb, rb / a.W, c.n_nodes, FD, a.W, h->max_smem_optin, &stages);
+        return smem_ffma(rb, rb, c.n_nodes, FD);
     };
-    // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks,
-    // else the smallest (more, lighter CTAs for small batches)
+    // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks; when no candidate
+    // fills the device twice, the smallest one that fits (more, lighter CTAs for small batches; with beam search the
+    // smallest block that still holds every beam of an instance)
     const int cand[4] = {64, 48, 32, 16};
     int RB = 0;
     if (c.rows_per_cta) {
         RB = c.rows_per_cta;
-        if (v4 && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
+        if (fam == kFamV4 && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
     } else {
+        int smallest_fit = 0;
         for (int i = 0; i < 4 && !RB; ++i) {
             const int rb = cand[i];
             if (smem_of(rb) > h->max_smem_optin) continue;
-            if ((a.B * a.W + rb - 1) / rb >= 2LL * h->num_sms || rb == 16) RB = rb;
+            smallest_fit = rb;
+            if ((a.B * a.W + rb - 1) / rb >= 2LL * h->num_sms) RB = rb;
         }
+        if (!RB) RB = smallest_fit;
     }
-    if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory");
+    if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory (n_nodes %d, beam_width %d)", c.n_nodes, a.W);
     a.IB = RB / a.W;
     const int total = smem_of(RB);
     if (total > h->max_smem_optin)
         return fail(h, VRPB200_E_ARG, "rows_per_cta %d needs %d B shared memory (> %d)", RB, total, h->max_smem_optin);
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
-    h->last_launch[0] = (int)grid; h->last_launch[1] = v4 ? kV4Threads : v3 ? kV3Threads : tc ? 512 : RB * 8; h->last_launch[2] = total; h->last_launch[3] = RB;
-    h->last_launch[4] = 1; h->last_launch[5] = c.gemm_path;
-    int rc = 0;
-#define DISPATCH(rb)                                                                                   \
-    case rb:                                                                                           \
-        if (v4) { rc = launch_rollout4_any<rb>(h, a, (int)grid, total, st, stages3, nsw); }                     \
-        else if (v3) { if (stages3 == 3) rc = h->tw ? launch_rollout3_t<rb, true, 3>(h, a, (int)grid, total, st)    \
-                                               : launch_rollout3_t<rb, false, 3>(h, a, (int)grid, total, st);  \
-                  else rc = h->tw ? launch_rollout3_t<rb, true, 2>(h, a, (int)grid, total, st)                 \
-                                  : launch_rollout3_t<rb, false, 2>(h, a, (int)grid, total, st); }             \
-        else if (v2) rc = h->tw ? launch_rollout2_t<rb, true>(h, a, (int)grid, total, st)                   \
-                           : launch_rollout2_t<rb, false>(h, a, (int)grid, total, st);                 \
-        else if (tc) rc = h->tw ? launch_rollout_t<rb, true, true>(h, a, (int)grid, total, st)         \
-                                : launch_rollout_t<rb, false, true>(h, a, (int)grid, total, st);       \
-        else    rc = h->tw ? launch_rollout_t<rb, true, false>(h, a, (int)grid, total, st)             \
-                           : launch_rollout_t<rb, false, false>(h, a, (int)grid, total, st);           \
-        break;
-    switch (RB) {
-        DISPATCH(64) DISPATCH(48) DISPATCH(32) DISPATCH(16)
-        default: return fail(h, VRPB200_E_ARG, "bad rows_per_cta");
-    }
-#undef DISPATCH
-    return rc;
+    h->last_launch[0] = (int)grid;
+    h->last_launch[1] = fam == kFamV4 ? kV4Threads : fam == kFamV3 ? kV3Threads : RB * 8;
+    h->last_launch[2] = total; h->last_launch[3] = RB; h->last_launch[4] = 1; h->last_launch[5] = fam;
+    cudaError_t e;
+    if (fam == kFamV4) e = launch_rollout4(a, RB, h->tw, stages, (int)grid, total, st);
+    else if (fam == kFamV3) e = launch_rollout3(a, RB, h->tw, stages, (int)grid, total, st);
+    else e = launch_ffma(a, RB, h->tw, (int)grid, total, st);
+    if (e != cudaSuccess) return fail(h, VRPB200_E_CUDA, "rollout launch (family %d, rows_per_cta %d): %s", fam, RB, cudaGetErrorString(e));
+    return 0;
 }
 
 }  // namespace
@@ -519,9 +432,8 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     if (!d_input || !d_cost || !d_idx) return fail(h, VRPB200_E_ARG, "d_input, d_idx and d_cost are required");
     if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
     if (mode != VRPB200_GREEDY && mode != VRPB200_STOCHASTIC && mode != VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "bad mode %d", mode);
-    if (mode == VRPB200_BEAM && h->cfg.gemm_path < 3) return fail(h, VRPB200_E_ARG, "beam search needs the rollout3 kernel (gemm_path 3 or 4)");
+    if (mode == VRPB200_BEAM && h->cfg.gemm_path == 1) return fail(h, VRPB200_E_ARG, "beam search is not implemented by the FP32-pipe cross-check kernel");
     if (mode == VRPB200_BEAM && (beam_width < 1 || beam_width > 64)) return fail(h, VRPB200_E_ARG, "beam_width outside [1,64]");
-    if (mode == VRPB200_BEAM && trace && (trace->d_logits || trace->d_probs || trace->d_masks) && false) return VRPB200_E_ARG;
     if (h->cfg.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "n_glimpses > 0 is not implemented by the fused kernel yet (use decode_step)");
     if (mode == VRPB200_STOCHASTIC && ((d_uniforms == nullptr) != (d_uniforms_retry == nullptr)))
         return fail(h, VRPB200_E_ARG, "pass both uniform buffers or neither");
@@ -530,7 +442,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     RolloutArgs a;
     memset(&a, 0, sizeof a);
     a.input = d_input; a.Wg = h->Wg; a.bg = h->bg; a.att = h->att[c.n_glimpses];
-    a.WgTc = h->WgTc; a.WqTc = h->WqTc[c.n_glimpses];
+    a.WqTc = h->WqTc[c.n_glimpses];
     a.WgT3 = h->WgT3; a.WxT = h->WxT; a.bgT = h->bgT;
     a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
     a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
@@ -547,7 +459,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
     a.sumv = h->sumv;
     memcpy(a.vm2, h->vm2, sizeof a.vm2);
-    if (c.gemm_path >= 4 && mode != VRPB200_BEAM) {   // rollout4 gathers node features as aligned 16-byte records
+    if ((c.gemm_path == 0 || c.gemm_path == 6) && mode != VRPB200_BEAM) {   // rollout4 gathers node features as aligned 16-byte records
         const int slot = h->ws_slot;
         const long long nn = (long long)B * c.n_nodes;
         int rc = ensure(h, &h->ws_feat4[slot], &h->ws_feat4_bytes[slot], (size_t)nn * sizeof(float4));

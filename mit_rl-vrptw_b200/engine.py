@@ -48,17 +48,21 @@ class RolloutOutput:
     stats: Optional[torch.Tensor] = None     # [4] int64 work counters: node evals, live row-steps, block-steps*rows, blocks
 
 
+# fused-kernel families (vrpb200_config.gemm_path): the default, the FP32-pipe cross-check, rollout3, rollout4 (split)
+GEMM_PATHS = {"auto": 0, "ffma": 1, "tc3": 3, "tc4x": 6}
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
 class Engine:
-    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0, gemm: str = "tc4x"):
+    def __init__(self, args: dict, device: int = 0, rows_per_cta: int = 0, gemm: str = "auto"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise VrpB200Error("no CUDA device: the rollout path has no CPU implementation")
         self.args = dict(args)
-        self.cfg = config_from_args(args, rows_per_cta, {"tc2": 0, "ffma": 1, "tc": 2, "tc3": 3, "tc4": 4, "tc4s": 5, "tc4x": 6}[gemm])
+        self.cfg = config_from_args(args, rows_per_cta, GEMM_PATHS[gemm])
         self.device = torch.device("cuda", device)
         self.handle = C.c_void_p()
         rc = self.lib.vrpb200_create(C.byref(self.cfg), device, C.byref(self.handle))

@@ -105,7 +105,8 @@ def reset_default_store(seed: int = 1234) -> VariableStore:
 _engine_cache: Dict[tuple, object] = {}
 
 
-def _get_engine(args: dict, params: Dict[str, np.ndarray], version_key, device: int = 0):
+def _get_engine(args: dict, params, version_key, device: int = 0):
+    """params: the variable dict, or a callable that builds it (only called when the engine is not cached yet)."""
     from .engine import Engine
     key = (tuple(sorted((k, str(v)) for k, v in args.items() if k in (
         "task_name", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
@@ -115,7 +116,7 @@ def _get_engine(args: dict, params: Dict[str, np.ndarray], version_key, device: 
         if len(_engine_cache) > 8:
             _engine_cache.clear()
         eng = Engine(args, device=device)
-        eng.set_weights(params)
+        eng.set_weights(params() if callable(params) else params)
         _engine_cache[key] = eng
     return eng
 
@@ -165,9 +166,11 @@ class LinearEmbedding(Embedding):
         task_name = "vrptw" if d1 == 4 else "vrp"
         args = dict(task_name=task_name, n_nodes=x.shape[-2], n_cust=x.shape[-2] - 1, input_dim=d1 + 1,
                     embedding_dim=self.embedding_dim, hidden_dim=128, decode_len=1, capacity=1.0)
-        params = _dummy_model_params(args)
-        params['Actor/Embedding/conv1d/kernel'] = self.store.vars[self.scope + '/kernel']
-        params['Actor/Embedding/conv1d/bias'] = self.store.vars[self.scope + '/bias']
+        def params():
+            p = _dummy_model_params(args)
+            p['Actor/Embedding/conv1d/kernel'] = self.store.vars[self.scope + '/kernel']
+            p['Actor/Embedding/conv1d/bias'] = self.store.vars[self.scope + '/bias']
+            return p
         eng = _get_engine(args, params, ("emb", self.store.uid, self.store.version, self.scope))
         out = eng.embed(x)
         self.total_time += time.time() - t0
@@ -214,9 +217,11 @@ class _AttentionActorBase(object):
         args = dict(task_name="vrptw" if self.TW else "vrp", n_nodes=N, n_cust=N - 1, input_dim=5 if self.TW else 3,
                     embedding_dim=E, hidden_dim=self.dim, decode_len=1, capacity=1.0, use_tanh=self.use_tanh,
                     tanh_exploration=float(self.C))
-        params = _dummy_model_params(args)
-        for k in self.variable_names():
-            params['Actor/Decoder/Attention' + k[len(self.prefix):]] = self.store.vars[k]
+        def params():
+            p = _dummy_model_params(args)
+            for k in self.variable_names():
+                p['Actor/Decoder/Attention' + k[len(self.prefix):]] = self.store.vars[k]
+            return p
         eng = _get_engine(args, params, ("att", self.store.uid, self.store.version, self.prefix))
         return eng.attention(-1, query, ref, env.demand, env.load, env.time if self.TW else None)
 
@@ -318,7 +323,7 @@ class RNNDecodeStep(DecodeStep):
                     hidden_dim=self.hidden_dim, decode_len=1, capacity=float(getattr(Env, "capacity", 1.0)),
                     n_glimpses=self.n_glimpses, use_tanh=self.use_tanh, tanh_exploration=float(self.tanh_exploration),
                     mask_glimpses=self.mask_glimpses, mask_pointer=self.mask_pointer, forget_bias=float(self.forget_bias))
-        return _get_engine(args, self.model_params(args=args), ("dec", self.store.uid, self.store.version, self._scope))
+        return _get_engine(args, lambda: self.model_params(args=args), ("dec", self.store.uid, self.store.version, self._scope))
 
     def step(self, decoder_inp, context, Env, decoder_state=None, *args, **kwargs):
         """decoder_inp [R,1,E], context [R,N,E], decoder_state = (c, h) each [R,H] (LSTMStateTuple order)
@@ -378,7 +383,7 @@ class _EnvBase(object):
             self.previous_x, self.previous_y = x[:, self.n_nodes - 1, 0:1], x[:, self.n_nodes - 1, 1:2]
 
     def _eng(self):
-        return _get_engine(self._eargs, _dummy_model_params(self._eargs), ("env",))
+        return _get_engine(self._eargs, lambda: _dummy_model_params(self._eargs), ("env",))
 
     def _publish(self, st, d_sat):
         import torch
@@ -427,7 +432,7 @@ def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
     sol = sample_solution if isinstance(sample_solution, torch.Tensor) else torch.stack(list(sample_solution), 0)
     sol = sol.to(device="cuda", dtype=torch.float32).contiguous()
     args = dict(task_name="vrp", n_nodes=2, n_cust=1, input_dim=3, embedding_dim=1, hidden_dim=128, decode_len=1, capacity=1.0)
-    eng = _get_engine(args, _dummy_model_params(args), ("reward",))
+    eng = _get_engine(args, lambda: _dummy_model_params(args), ("reward",))
     if depot is None:
         return eng.reward(sol)
     dep = depot.to(device="cuda", dtype=torch.float32).contiguous()
@@ -538,11 +543,11 @@ class RLAgent(object):
     def engine(self):
         eargs = dict(self.args)
         eargs.setdefault('task_name', 'vrptw' if self.env.TW else 'vrp')
-        return _get_engine(eargs, self.model_params(), ("agent", self.store.uid, self.store.version), self.device)
+        return _get_engine(eargs, self.model_params, ("agent", self.store.uid, self.store.version), self.device)
 
     # -- the rollout -----------------------------------------------------------------------------
     def build_model(self, decode_type="greedy", uniforms=None, uniforms_retry=None, seed=0, want_probs=False,
-                    backend="auto"):
+                    backend="auto", want_logprobs=True):
         """attention_agent.py:84-272.  backend 'fused' = the persistent rollout kernel, 'stepwise' = the reference's
         loop over RNNDecodeStep.step / Env.step on device state (beam search and glimpses take this route in this
         round), 'auto' picks."""
@@ -555,8 +560,10 @@ class RLAgent(object):
                 raise NotImplementedError("fused kernel: greedy / stochastic / beam search without glimpses")
             W = self.args['beam_width'] if decode_type == 'beam_search' else 1
             self.beam_width = W
+            # the per-step log-probabilities are only computed on request: without them plain greedy decoding runs the
+            # kernel's fast per-row tail (evaluate_batch / evaluate_single never read them)
             out = self.engine().rollout(self.env.input_data, decode_type, beam_width=W, uniforms=uniforms,
-                                        uniforms_retry=uniforms_retry, seed=seed, want_logprobs=True)
+                                        uniforms_retry=uniforms_retry, seed=seed, want_logprobs=want_logprobs)
             idx = out.idxs.long()                                      # [T, R]
             T, R = idx.shape
             pnt = self.env.input_pnt                                    # [B, N, D-1]
@@ -572,9 +579,18 @@ class RLAgent(object):
                     bt[k] = actions[k][ind]
                     ind = (inst + B * par[k])[ind]
                 actions = torch.stack(bt)
+            R_out = self._reward(list(actions), pnt, W) if self.args.get('min_trucks') else out.R
             v = torch.zeros((), device=idx.device)
-            return (out.R, v, list(out.logprobs), list(actions), [i[:, None] for i in idx], pnt, None)
+            return (R_out, v, list(out.logprobs) if want_logprobs else None, list(actions), [i[:, None] for i in idx], pnt, None)
         return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs)
+
+    def _reward(self, actions, input_pnt, beam_width):
+        """attention_agent.py:236-240: the tour length, or with args['min_trucks'] the depot form of reward_func on the
+        (back-tracked) actions with the depot coordinates tiled over the beams."""
+        if self.args.get('min_trucks'):
+            depot = input_pnt[:, self.env.n_nodes - 1, :].repeat(beam_width, 1)
+            return self.reward_func(actions, self.args['decode_len'], self.args['n_nodes'] - 1, depot)
+        return self.reward_func(actions)
 
     def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs):
         """The reference loop, line for line, on device tensors (attention_agent.py:89-240)."""
@@ -650,7 +666,7 @@ class RLAgent(object):
         else:
             actions = actions_tmp
         self.last_beam_path = beam_path
-        R = self.reward_func(actions)                                                      # :236-240
+        R = self._reward(actions, input_pnt, beam_width)                                   # :236-240
         v = torch.zeros((), device=dev)
         return (R, v, logprobs, actions, idxs, input_pnt, probs if want_probs else None)
 
@@ -663,7 +679,7 @@ class RLAgent(object):
         self.env.input_data = torch.as_tensor(np.asarray(data, np.float32))
         torch.cuda.synchronize()
         start_time = time.time()
-        R, v, logprobs, actions, idxs, batch, _ = self.build_model(eval_type, backend=backend)
+        R, v, logprobs, actions, idxs, batch, _ = self.build_model(eval_type, backend=backend, want_logprobs=False)
         R = R.cpu().numpy()
         R = np.concatenate(np.split(np.expand_dims(R, 1), beam_width, axis=0), 1)
         R = np.amin(R, 1, keepdims=False)
@@ -684,7 +700,7 @@ class RLAgent(object):
         for _ in range(self.dataGen.n_problems):
             batch = np.asarray(self.dataGen.get_test_next(), np.float32)
             self.env.input_data = torch.as_tensor(batch)
-            out = self.build_model(eval_type)
+            out = self.build_model(eval_type, want_logprobs=False)
             R = out[0].cpu().numpy().reshape(beam_width, -1)
             best = int(np.argmin(R[:, 0]))
             rewards.append(float(R[best, 0]))

@@ -216,3 +216,78 @@ def test_evaluate_single_writes_reference_result_files(tmp_path):
         np.testing.assert_allclose(v[-1], data[b, -1, :4], rtol=1e-6)      # closed with the depot
         nodes = {tuple(np.round(r, 5)) for r in data[b, :, :4]}
         assert all(tuple(np.round(r, 5)) in nodes for r in v)
+
+
+@pytest.mark.parametrize("decode_type,W", [("greedy", 1), ("beam_search", 3)])
+def test_build_model_min_trucks_reward(decode_type, W):
+    """args['min_trucks'] switches build_model's R to reward_func(actions, decode_len, n_nodes-1, depot tiled over the
+    beams) (attention_agent.py:236-238) - on the fused and on the step-wise route, with back-tracked beam actions."""
+    args = O.default_args("vrptw10", beam_width=W, min_trucks=True)
+    params = O.init_params(args, seed=41, bias_scale=0.2)
+    agent, env, torch, H = _agent(args, params)
+    data = O.create_dataset("vrptw10", 24, seed=6)
+    env.input_data = torch.from_numpy(data.astype(np.float32))
+    ref = O.rollout(params, args, data, decode_type)
+    depot = np.tile(data[:, -1, :4].astype(np.float32), [W, 1])
+    want = O.reward_func_min_trucks(list(ref.actions), depot, args["decode_len"], args["n_nodes"] - 1, True)
+    for backend in ("fused", "stepwise"):
+        out = agent.build_model(decode_type, backend=backend)
+        idx = torch.stack(out[4])[:, :, 0].cpu().numpy()
+        same = (idx == ref.idxs).all(0)
+        if decode_type == "beam_search":      # twin beams may swap slots: compare per-instance multisets
+            np.testing.assert_allclose(np.sort(out[0].cpu().numpy().reshape(W, -1), 0), np.sort(want.reshape(W, -1), 0), rtol=2e-5)
+        else:
+            assert same.mean() >= 0.95
+            np.testing.assert_allclose(out[0].cpu().numpy()[same], want[same], rtol=2e-5)
+    plain = dict(args, min_trucks=False)
+    agent2, env2, _, _ = _agent(plain, params)
+    env2.input_data = env.input_data
+    assert not np.allclose(agent2.build_model(decode_type)[0].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("W,B", [(20, 1), (20, 100), (64, 1), (64, 100), (17, 1500)])
+def test_wide_beams_pick_a_block_size(W, B):
+    """beam_width in [17, 64] on small and medium batches: the automatic rows-per-CTA choice falls back to the smallest
+    block that holds every beam of an instance (it used to find none; evaluate_single with beam_width 20 is B = 1).
+    With more beams than finite candidates the reference's top_k picks -inf entries too (masked nodes, probability 0),
+    so the comparison is with the oracle, not with a feasibility replay."""
+    import torch
+    pkg = load_pkg()
+    args = O.default_args("vrptw20", beam_width=W)
+    params = O.init_params(args, seed=5, bias_scale=0.1)
+    data = O.create_dataset("vrptw20", B, seed=9)
+    eng = pkg.Engine(args)
+    eng.set_weights(params)
+    x = torch.from_numpy(data.astype(np.float32)).cuda()
+    out = eng.rollout(x, "beam_search", beam_width=W)
+    torch.cuda.synchronize()
+    assert eng.last_launch()["rows_per_cta"] >= W
+    ref = O.rollout(params, args, data, "beam_search")
+    best, ref_best = out.R.cpu().numpy().reshape(W, B).min(0), O.best_of_beams(ref.R, B, W)
+    assert np.isclose(best, ref_best, rtol=1e-4).mean() >= 0.9
+    same = (out.idxs.cpu().numpy() == ref.idxs).all(0) & (out.beam_parents.cpu().numpy() == ref.beam_parents).all(0)
+    assert same.reshape(W, B).all(0).mean() >= 0.8
+
+
+@pytest.mark.parametrize("task", ["vrptw20", "vrp20"])
+@pytest.mark.parametrize("gemm", ["auto", "tc3", "ffma"])
+def test_mask_pointer_false_matches_oracle(task, gemm):
+    """mask_pointer=False (decode_step.py:231-232 skipped): logits are not masked, a served row keeps moving for all T
+    steps instead of being frozen at the depot, every node is evaluated at every step."""
+    import torch
+    pkg = load_pkg()
+    args = O.default_args(task, mask_pointer=False)
+    params = O.init_params(args, seed=8, bias_scale=0.3)
+    data = O.create_dataset(task, 96, seed=4)
+    eng = pkg.Engine(args, gemm=gemm)
+    eng.set_weights(params)
+    out = eng.rollout(torch.from_numpy(data.astype(np.float32)).cuda(), "greedy", want_logprobs=True, final_state=True, want_steps=True)
+    torch.cuda.synchronize()
+    ref = O.rollout(params, args, data, "greedy")
+    idx = out.idxs.cpu().numpy().astype(np.int64)
+    same = (idx == ref.idxs).all(0)
+    assert same.mean() >= 0.95
+    assert int(out.steps.min()) == args["decode_len"]          # no early exit without the pointer mask
+    np.testing.assert_allclose(out.R.cpu().numpy()[same], ref.R[same], rtol=1e-4)
+    np.testing.assert_allclose(out.logprobs.cpu().numpy()[:, same], ref.logprobs[:, same], rtol=2e-4, atol=2e-5)
+    np.testing.assert_array_equal(out.final_demand.cpu().numpy()[same], ref.final_state.demand[same])
