@@ -185,7 +185,7 @@ class Engine:
     def last_launch(self) -> dict:
         arr = (C.c_int32 * 8)()
         self._check(self.lib.vrpb200_last_launch(self.handle, arr), "last_launch")
-        return dict(grid=arr[0], block=arr[1], smem=arr[2], rows_per_cta=arr[3], kernels=arr[4])
+        return dict(grid=arr[0], block=arr[1], smem=arr[2], rows_per_cta=arr[3], kernels=arr[4], family=arr[5])
 
     # -- Env -------------------------------------------------------------------------------------
     def env_reset(self, input_data: torch.Tensor, beam_width: int = 1):

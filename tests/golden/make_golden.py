@@ -61,10 +61,17 @@ _stub("shared.graph_embedding.full_graph_learning", FullGraphEmbedding=_Dummy)
 from model.attention_agent import RLAgent  # noqa: E402
 
 
-def components(task_name):
-    if task_name == "vrp":
+def components(task_name, ups=False):
+    """main.py:17-53 (load_task_specific_components): the UPS twins when args['ups'] is set."""
+    if task_name == "vrp" and ups:
+        from UPS.vrp_ups_utils import Env, reward_func
+        from UPS.vrp_ups_attention import AttentionVRP_UPS_Actor as A, AttentionVRP_UPS_Critic as C
+    elif task_name == "vrp":
         from VRP.vrp_utils import Env, reward_func
         from VRP.vrp_attention import AttentionVRPActor as A, AttentionVRPCritic as C
+    elif ups:
+        from UPS.vrptw_ups_utils import Env, reward_func
+        from UPS.vrptw_ups_attention import AttentionVRPTW_UPS_Actor as A, AttentionVRPTW_UPS_Critic as C
     else:
         from VRPTW.vrptw_utils import Env, reward_func
         from VRPTW.vrptw_attention import AttentionVRPTWActor as A, AttentionVRPTWCritic as C
@@ -87,7 +94,7 @@ def run_reference(args, params, data, decode_type, uniforms=None, uniforms_retry
     """Build the reference graph for ``decode_type`` and evaluate it on ``data``."""
     tf.reset_shim()
     tf.VARIABLE_STORE.update(params)
-    Env, reward_func, Actor, Critic = components(args["task_name"])
+    Env, reward_func, Actor, Critic = components(args["task_name"], bool(args.get("ups")))
     a = dict(args)
     a["log_dir"] = tempfile.mkdtemp()
     env = Env(a)
@@ -165,15 +172,34 @@ CASES = [
     ("vrptw10_stochastic", "vrptw10", "stochastic", 16, {}, 16, 0.3),
     ("vrptw20_glimpse_tanh", "vrptw20", "greedy", 8, {"n_glimpses": 1, "use_tanh": True}, 17, 0.3),
     ("vrptw10_small_dims", "vrptw10", "greedy", 8, {"hidden_dim": 128, "embedding_dim": 8}, 18, 0.3),
+    # round 2: the sizes and classes of the headline configs, run through the reference's own code as well
+    ("vrptw50_greedy", "vrptw50", "greedy", 4, {}, 21, 0.0),
+    ("vrptw100_greedy", "vrptw100", "greedy", 4, {}, 22, 0.0),                       # extrapolated task
+    ("ups_vrptw100_greedy", "vrptw100", "greedy", 4, {"ups": True}, 23, 0.0),        # UPS/vrptw_ups_utils.Env + UPS actor, GMM instances
+    ("ups_vrptw20_stochastic", "vrptw20", "stochastic", 8, {"ups": True}, 26, 0.2),
+    ("ups_vrp20_greedy", "vrp20", "greedy", 8, {"ups": True}, 27, 0.2),              # UPS/vrp_ups_utils.Env + UPS actor
+    ("vrptw20_tanh", "vrptw20", "greedy", 8, {"use_tanh": True}, 24, 0.3),           # C tanh(u) without glimpses
+    ("vrptw10_nomaskptr", "vrptw10", "greedy", 8, {"mask_pointer": False}, 25, 0.3),
 ]
 
 
 def main():
+    import json
+    only = set(sys.argv[1:])
     index = {}
+    if only and os.path.exists(os.path.join(HERE, "index.json")):
+        with open(os.path.join(HERE, "index.json")) as f:
+            index = json.load(f)
     for name, task, dtype_, B, over, seed, bscale in CASES:
+        if only and name not in only:
+            continue
         args = O.default_args(task, **over)
         params = O.init_params(args, seed=seed, bias_scale=bscale)
-        data = O.create_dataset(task, B, seed=1000 + seed)
+        if over.get("ups"):   # the UPS generators (GMM samples), restated in the product package's data module
+            import importlib
+            data = importlib.import_module("mit_rl-vrptw_b200.data").create_dataset(args["task_name"], B, args["n_cust"], 1000 + seed, ups=True)
+        else:
+            data = O.create_dataset(task, B, seed=1000 + seed)
         T = args["decode_len"]
         W = args["beam_width"] if dtype_ == "beam_search" else 1
         rnd = np.random.RandomState(seed)
@@ -197,6 +223,8 @@ def main():
 
     # Env driven directly: random feasible-ish action sequences incl. repeated depot visits and beams
     for name, task, W in [("env_vrptw10", "vrptw10", 1), ("env_vrp10", "vrp10", 1), ("env_vrptw10_beam", "vrptw10", 3)]:
+        if only and name not in only:
+            continue
         args = O.default_args(task)
         B, T = 12, 24
         data = O.create_dataset(task, B, seed=77)
@@ -212,7 +240,6 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(f"{name}: mask max {out['mask'].max()}  load min {out['load'].min()}")
 
-    import json
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(index, f, indent=1, sort_keys=True)
 

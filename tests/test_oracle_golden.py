@@ -91,3 +91,25 @@ def test_min_trucks_reward_known_answer():
     r = O.reward_func_min_trucks(acts, dep, len(pts), 4.0, tw=False)
     route = 7 + 0 + 0 + 5 + np.hypot(3, 3)
     np.testing.assert_allclose(r, [70.0 * (3 / 4.0) + 30.0 * (route / (5 + 7))], rtol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["ups_vrptw100", "uniform_vrptw100", "vrptw50"])
+def test_committed_oracle_tours_are_reproducible(name):
+    """tests/golden/oracle_tours_*.npz (fp32 and fp64 greedy tours of the oracle at the headline sizes): the first
+    instances regenerate bit-for-bit from the seeds, in both precisions."""
+    import importlib
+    import os
+    from tests.helpers import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, f"oracle_tours_{name}.npz"))
+    data_mod = importlib.import_module("mit_rl-vrptw_b200.data")
+    args = O.default_args(str(fx["task"]))
+    params = data_mod.glorot_params(args, seed=int(fx["weight_seed"]))
+    data = data_mod.create_dataset(args["task_name"], int(fx["B"]), args["n_cust"], int(fx["data_seed"]), ups=bool(fx["ups"]))
+    assert int(np.abs(data).sum() * 1e6) % (1 << 40) == int(fx["data_crc"])
+    n = 6
+    for tag, dt in (("32", np.float32), ("64", np.float64)):
+        r = O.rollout(params, args, data[:n], "greedy", dtype=dt)
+        np.testing.assert_array_equal(r.idxs, fx["idx" + tag][:, :n].astype(np.int64))
+        np.testing.assert_allclose(r.R, fx["R" + tag][:n], rtol=1e-6)
+    if name == "ups_vrptw100":   # saturated tanh: fp32 rounding alone moves tours - the reason for the fp64 adjudication
+        assert (fx["idx32"] == fx["idx64"]).all(0).mean() < 0.99
