@@ -245,20 +245,22 @@ def test_build_model_min_trucks_reward(decode_type, W):
     assert not np.allclose(agent2.build_model(decode_type)[0].cpu().numpy(), want)
 
 
-@pytest.mark.parametrize("W,B", [(20, 1), (20, 100), (64, 1), (64, 100), (17, 1500)])
-def test_wide_beams_pick_a_block_size(W, B):
+@pytest.mark.parametrize("task,W,B", [("vrptw20", 20, 1), ("vrptw20", 20, 100), ("vrptw50", 40, 1), ("vrptw50", 48, 24), ("vrptw20", 17, 1500)])
+def test_wide_beams_pick_a_block_size(task, W, B):
     """beam_width in [17, 64] on small and medium batches: the automatic rows-per-CTA choice falls back to the smallest
     block that holds every beam of an instance (it used to find none; evaluate_single with beam_width 20 is B = 1).
     With more beams than finite candidates the reference's top_k picks -inf entries too (masked nodes, probability 0),
     so the comparison is with the oracle, not with a feasibility replay."""
     import torch
     pkg = load_pkg()
-    args = O.default_args("vrptw20", beam_width=W)
+    args = O.default_args(task, beam_width=W)
     params = O.init_params(args, seed=5, bias_scale=0.1)
-    data = O.create_dataset("vrptw20", B, seed=9)
+    data = O.create_dataset(task, B, seed=9)
     eng = pkg.Engine(args)
     eng.set_weights(params)
     x = torch.from_numpy(data.astype(np.float32)).cuda()
+    with pytest.raises(pkg.VrpB200Error, match="exceeds n_nodes"):     # top_k(k > candidates) is an error in the reference too
+        eng.rollout(x, "beam_search", beam_width=args["n_nodes"] + 1)
     out = eng.rollout(x, "beam_search", beam_width=W)
     torch.cuda.synchronize()
     assert eng.last_launch()["rows_per_cta"] >= W

@@ -65,14 +65,18 @@ FUSED_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
 
 @pytest.mark.parametrize("name", FUSED_CASES)
 @pytest.mark.parametrize("rows_per_cta", [0, 64])
-@pytest.mark.parametrize("gemm", ["tc4x", "tc3", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
 def test_rollout_matches_reference_fixture(name, rows_per_cta, gemm):
     fx, args, params = load_golden(name)
     meta = GOLDEN_INDEX[name]
     eng, torch = _engine(args, params, rows_per_cta=rows_per_cta, gemm=gemm)
     x = torch.from_numpy(fx["data"].astype(np.float32)).cuda()
-    out = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"),
-                      want_logprobs=True, trace=True)
+    try:
+        out = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"),
+                          want_logprobs=True, trace=True)
+    except load_pkg().VrpB200Error as e:      # 64 rows per CTA do not fit shared memory at N = 101
+        assert "shared memory" in str(e) and rows_per_cta == 64 and args["n_nodes"] > 51
+        return
     torch.cuda.synchronize()
     _compare_trace(out, fx, args, meta["decode_type"])
 
@@ -95,7 +99,7 @@ def test_fast_path_equals_trace_path(name):
     assert int(fast.steps.max()) <= args["decode_len"]
 
 
-@pytest.mark.parametrize("gemm", ["tc4x"])
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x"])
 @pytest.mark.parametrize("task,B,seed,ups", [("vrptw100", 1500, 21, True), ("vrptw100", 700, 22, False), ("vrptw20", 900, 23, False),
                                              ("vrp50", 500, 24, False), ("vrp100", 300, 25, True), ("vrptw50", 777, 26, True)])
 def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
@@ -116,7 +120,7 @@ def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
     assert torch.equal(fast.R, exact.R)
 
 
-@pytest.mark.parametrize("gemm", ["tc4x"])
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x"])
 def test_fast_tail_hands_rows_without_unmasked_node_to_the_exact_tail(gemm):
     """Time windows that close almost immediately: after its first customer a vehicle finds every other customer too late,
     returns to the depot, and there NO node is un-masked (the depot is masked while demand is left).  The reference then
@@ -149,7 +153,7 @@ def test_fast_tail_hands_rows_without_unmasked_node_to_the_exact_tail(gemm):
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
-@pytest.mark.parametrize("gemm", ["tc4x", "tc3", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
 def test_greedy_vs_oracle_seeded(task, B, seed, bias, gemm):
     """Ragged batch sizes, every task size; per-instance comparison up to the first near-tie."""
     args = O.default_args(task)
@@ -234,7 +238,7 @@ def test_host_entry_point_equals_device_entry_point():
     np.testing.assert_array_equal(cost_h, out.R.cpu().numpy())
 
 
-@pytest.mark.parametrize("gemm", ["tc4x", "tc3"])
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3"])
 def test_tensor_core_path_equals_fp32_path_up_to_near_ties(gemm):
     """The tcgen05 (3xTF32 split) GEMMs against the FP32-pipe GEMMs of the same kernel: logits within 2e-6,
     identical tours except at near-ties, every rows_per_cta."""

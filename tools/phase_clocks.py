@@ -6,14 +6,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = importlib.import_module("mit_rl-vrptw_b200")
 L = pkg._lib
-so = os.path.join(ROOT, "gpurun_out", "libvrpb200_clk.so")
-os.makedirs(os.path.dirname(so), exist_ok=True)
-subprocess.run(["/usr/local/cuda/bin/nvcc"] + L.NVCC_FLAGS + ["-DVRPB200_PHASE_CLOCKS"] + sys.argv[5:] + ["-o", so, os.path.join(L.CSRC, "vrpb200_api.cu")], check=True)
+so = os.path.join(L.LIB_DIR, "libvrpb200_clk.so")   # prebuilt on the CPU box (travels with the snapshot): python tools/phase_clocks.py --build
+if "--build" in sys.argv or not os.path.exists(so):
+    L.build_library(force=True, extra_flags=["-DVRPB200_PHASE_CLOCKS"], out_path=so)
+    if "--build" in sys.argv:
+        sys.exit(0)
 L.LIB_PATH = so
 L._lib = None
 _ = 0
 task, B, gemm, rb = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0
-extra = sys.argv[5:]
 args = pkg.task_specific_params.default_args(task)
 eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))
@@ -30,6 +31,18 @@ blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
 names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epilogue", "C1 scores", "C2 select/env"] if gemm == "tc3" else
          ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"])
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
+if gemm == "tc5":
+    sn = ["(loop)", "T0 -> offsets + first tiles staged", "wait q", "q epilogue + barrier", "C1: tile end / loop", "C1: wait MMA", "C1: TMEM load, free", "C1: arithmetic", "C1: psum / logits / next F", "after last tile"]
+    an = ["(wait T0)", "prefix + prefetch + wait tiles", "choice", "Env.step", "next mask + item list", "chunk barrier", "wait gates MMA", "LSTM epilogue chunk", "step end (done flags, arrive)"]
+    print("  score warp 2")
+    for n, v in zip(sn, s[4:4 + len(sn)]):
+        print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
+    print(f"    total {s[4:16].sum() / blocksteps:.0f} clk/step")
+    print("  aux warp 16")
+    for n, v in zip(an, s[16:16 + len(an)]):
+        print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
+    print(f"    total {s[16:25].sum() / blocksteps:.0f} clk/step;  near-tie softmax visits (row-steps of this warp): {s[26]}")
+    sys.exit(0)
 if gemm in ("tc4", "tc4s", "tc4x"):
     names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
              "end-of-step barrier", "C1: wait MMA", "C1: next F tile + group barrier", "C1: TMEM load, free, issue", "C1: arithmetic", "C1: tile end / loop", "rows: wait for logits", "rows: processing (rest)", "rows fast: prefetch issue", "rows fast: arg-max + merge", "rows fast: Env.step", "rows fast: feasibility + lists"]
