@@ -91,6 +91,9 @@ VRP_DEVINL void mbar_init(uint32_t bar, uint32_t count) {
 VRP_DEVINL void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef VRP_SUSPEND_NS
+#define VRP_SUSPEND_NS 0x989680u
+#endif
 // try_wait with a suspend-time hint: the waiting thread sleeps in hardware until the phase completes instead of
 // spinning through the loop (a spinning waiter takes issue slots from the warps that do the arithmetic)
 VRP_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -100,7 +103,7 @@ VRP_DEVINL void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
         "@P1 bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(VRP_SUSPEND_NS) : "memory");
 }
 VRP_DEVINL void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -231,6 +234,7 @@ constexpr int kV3UsesG = 32;                // W_h^T: (k-chunk, pair of gate typ
 #define VRP_XDESC(base, kc) tc_desc((base) + (kc) * 256, 128, 4096)
 
 VRP_DEVINL void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+VRP_DEVINL void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 VRP_DEVINL void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 VRP_DEVINL void tc_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r0, r1, r2, r3;

@@ -210,10 +210,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
+#ifndef VRP_NO_THROTTLE_GATES
                     if (u > 0) {   // throttle: this GEMM has a whole step of slack, the score MMAs of C1 queue behind it
                         const uint32_t cp = c - 1;
                         mbar_wait(bar_empty + 8 * (cp % STAGES), (cp / STAGES) & 1);
                     }
+#endif
                     tc_fence_after();
                     const int kc = u >> 1, mp = u & 1;
                     const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);

@@ -1,39 +1,38 @@
 // rollout5_kernel: the fused rollout (RLAgent.build_model of model/attention_agent.py:84-240, greedy and stochastic) as a
-// warp-specialised pipeline in which the MUFU-bound score phase never waits for the latency-bound rest of a decode step.
+// warp-specialised pipeline in which the MUFU-bound score phase does not wait for the latency-bound rest of a decode step.
 //
-//   warps  0..15  score warps   pointer scores u[n] = sum_h v_h tanh(.) (VRPTW/vrptw_attention.py:77) over 128-item tiles
-//                               (item = un-masked (row, node)): E = F.Bc on tcgen05 (3xTF32), tanh at 1.25 MUFU per element
-//                               (four reciprocals share one rcp, packed FP32x2 algebra); two groups of 8 warps, the two
-//                               warps of a TMEM sub-partition share a tile's items and split the hidden units; they also
-//                               run the query epilogue (base' = 2log2e (q + b + load g_ld + time g_t))
-//   warps 16..19  aux warps     everything that is a long dependent chain per row, STREAMED behind the score tiles: as soon
-//                               as the tiles holding a row's items are done, one warp runs the row's tail - choice (arg-max,
-//                               exact soft-max on near-ties, or sampling), Env.step (VRPTW/vrptw_utils.py:254-358), the
-//                               feasibility mask and the item list of the next step - and every four rows the four warps
-//                               run the LSTM epilogue of those rows for the NEXT step (gates^T from TMEM + x part -> c, h';
-//                               shared/decode_step.py:211-214), so that at the end of the score phase only the last rows'
-//                               tail and one 4-row epilogue chunk are exposed
+//   warps  0..15  score warps   per decode step: (1) Env mask -> item lists of the step (vrptw_utils.py:328-348; one warp per
+//                               row, 4 nodes per lane, hidden behind the query GEMM), (2) query epilogue, (3) pointer scores
+//                               u[n] = sum_h v_h tanh(.) (VRPTW/vrptw_attention.py:77) over 128-item tiles (item = un-masked
+//                               (row, node)): E = F.Bc on tcgen05 (3xTF32), tanh at 1.25 MUFU per element (four reciprocals
+//                               share one rcp, packed FP32x2 algebra); two groups of 8 warps, the two warps of a TMEM
+//                               sub-partition share a tile's items and split the hidden units; (4) BETWEEN tiles, the LSTM
+//                               epilogue of the next step (gates^T from TMEM + x part -> c, h'; shared/decode_step.py:211-214)
+//                               for every 4-row chunk whose rows have moved
+//   warps 16..19  aux warps     the per-row tail, STREAMED behind the score tiles: as soon as the tiles holding a row's items
+//                               are done, one warp picks the row's node (arg-max with exact soft-max on near-ties, or sampling;
+//                               attention_agent.py:146-167) and runs Env.step (vrptw_utils.py:254-325); four rows = one chunk
 //   warp  20      weight feeder (cp.async.bulk ring from L2: W_q^T, then W_h^T for the next step's gates)
 //   warp  21      LSTM / query MMA issuer (transposed GEMMs, M = 128 units, N = rows, TMEM accumulators)
 //   warps 22, 23  score-MMA issuers of the two groups (a rotating ring of three 32-column TMEM buffers per group)
 //
-// Registers are re-distributed with setmaxnreg inside the CTA's own pool of 768 x 80 (score warps 96, aux warps 72,
-// service warps 24: 16 x 32 x 96 + 4 x 32 x 72 + 4 x 32 x 24 = 768 x 80 exactly - an increase can only be served from what the
-// other warps have released).  The LSTM cell state lives
-// in TMEM (lane = unit, one column per row) because the aux warp that owns a unit serves every row of the block.
-// One synchronisation point per decode step: T0 = "h'(t) is in the X tiles and the item lists of step t are final"
-// (mbarrier bar_x, arrived by the four aux warps); both GEMMs of the step are issued at T0, the gates GEMM (whose result
-// is needed one step later) in the background of the score phase.
+// At the end of the score phase only the tail of the last rows and one LSTM chunk are exposed.  Registers are re-distributed
+// with setmaxnreg inside the CTA's own pool of 768 x 80 (score warps 96, aux warps 72, service warps 24: an increase can only
+// be served from what the other warps of the CTA have released).  The LSTM cell state lives in TMEM (lane = unit, one column
+// per row).  Long waits of many warps are hardware barriers (bar.sync), never polling mbarrier waits: 16 polling warps take
+// the issue slots of the warps they wait for.
+// One synchronisation point per decode step: T0 = "h'(t) is in the X tiles and every row has moved"; both GEMMs of the step
+// are issued at T0, the gates GEMM (whose result is needed one step later) in the background of the score phase.
 #pragma once
 #include "common.cuh"
 
 namespace vrpb200 {
 
 constexpr int kV5Threads = 768;   // 16 score warps + 4 aux warps + 4 service warps
-constexpr int kRS5 = 20;          // floats of row state
+constexpr int kRS5 = 18;          // floats of row state
 
 struct Smem5 {
-    int ring, X, qq, F, logits, items, bc, vsm, psum, dem, mask, rs, ibits, meta, bar, total, stages;
+    int ring, X, qq, F, logits, items, bc, vsm, psum, dem, mask, rs, ibits, wx, meta, bar, total, stages;
 };
 
 __host__ __device__ inline Smem5 make_layout5(int RB, int N, int stages) {
@@ -52,8 +51,9 @@ __host__ __device__ inline Smem5 make_layout5(int RB, int N, int stages) {
     L.psum = off;   off += 2 * 2 * 128 * 4;                    // partial score sums, [group][tile parity][item]
     L.dem = off;    off += RB * NP * 4;
     L.mask = off;   off += align_up(RB * NP, 16);              // mask counts (exact tail only)
-    L.rs = off;     off += RB * kRS5 * 4;
+    L.rs = off;     off += align_up(RB * kRS5 * 4, 16);
     L.ibits = off;  off += RB * 16;                            // per row: 128-bit set of the nodes that are items
+    L.wx = off;     off += 20 * kH * 4;                        // x part of the LSTM gates: W_x^T [4 features][4 gates][128] + bias [4][128]
     L.meta = off;   off += align_up((RB + 68 + RB + 8) * 4, 16);   // nact[RB], off[<=65 (+pad)], flags[RB], stop, t_end
     L.bar = off;    off += 320 + 64 * 8;
     L.total = off;
@@ -65,6 +65,13 @@ VRP_DEVINL void tc_st4(uint32_t taddr, const float (&v)[4]) {
                  "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                  : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// non-blocking test of an mbarrier phase
+VRP_DEVINL bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
 }
 
 // row state: 0 load, 1 time, 2-3 position, 4 tour length so far, 5-6 first node visited, 7 depot x, 8 done (int),
@@ -92,13 +99,15 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
     unsigned char* maskb = smem + L.mask;
     float* rowst = reinterpret_cast<float*>(smem + L.rs);
     unsigned* ibits = reinterpret_cast<unsigned*>(smem + L.ibits);
+    const float* wxs = reinterpret_cast<const float*>(smem + L.wx);   // [(feature 4 + gate)][unit], then bias [gate][unit] at 16 * kH
     int* nact_s = reinterpret_cast<int*>(smem + L.meta);
-    int* off_s = nact_s + RB;            // [RB + 1] exclusive prefix of nact (this step; score warps only)
+    int* off_s = nact_s + RB;            // [RB + 1] exclusive prefix of nact (this step)
     int* flag_s = off_s + 68;            // [RB] every node of the row is an item (the mask COUNTS decide the choice)
     volatile int* stop_s = flag_s + RB;
     volatile int* tend_s = stop_s + 1;
     const uint32_t bar0 = smem_u32(smem + L.bar);
-    const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, tmem_slot = bar0 + 120,
+    const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, bar_items = bar0 + 88,
+                   tmem_slot = bar0 + 120,
                    bar_grp = bar0 + 128,   // group g at + 64 g: full[3] (MMA commit), free[3] (4 warps copied the buffer), F ready[2]
                    bar_psum = bar0 + 256, bar_pack = bar0 + 272, bar_tile = bar0 + 320;
     const uint32_t ring_u32 = smem_u32(smem + L.ring), bc_u32 = smem_u32(smem + L.bc);
@@ -115,15 +124,14 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(bar0 + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        mbar_init(bar_q, 1); mbar_init(bar_g, 1);
-        mbar_init(bar_x, 4);                                     // the four aux warps
+        mbar_init(bar_q, 1); mbar_init(bar_g, 1); mbar_init(bar_x, 1); mbar_init(bar_items, 1);
         for (int g = 0; g < NG; ++g) {
             for (int b = 0; b < 3; ++b) { mbar_init(bar_grp + 64 * g + 8 * b, 1); mbar_init(bar_grp + 64 * g + 24 + 8 * b, 4); }
             mbar_init(bar_grp + 64 * g + 48, 4); mbar_init(bar_grp + 64 * g + 56, 4);
             mbar_init(bar_psum + 8 * g, 4);    // the partial sums of a tile are in place
             mbar_init(bar_pack + 8 * g, 4);    // ... and have been consumed (the producing half runs at most one tile ahead)
         }
-        for (int i = 0; i < 64; ++i) mbar_init(bar_tile + 8 * i, 4);   // 4 arrivals per step: the 4 warps that finish the tile
+        for (int i = 0; i < 64; ++i) mbar_init(bar_tile + 8 * i, 4);    // 4 arrivals per step: the 4 warps that finish the tile
         *stop_s = 0;
         *tend_s = 0;
         fence_mbar_init();
@@ -141,6 +149,8 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
         *reinterpret_cast<float*>(smem + L.bc + 4096 + o) = lo;
     }
     if (tid < 128) vsm[tid] = a.vm2[tid];
+    for (int i = tid; i < 20 * kH; i += kV5Threads)
+        reinterpret_cast<float*>(smem + L.wx)[i] = i < 16 * kH ? a.WxT[i] : a.bgT[i - 16 * kH];
     for (int i = tid; i < IBv * N; i += kV5Threads) {
         const int lb = i / N, n = i - lb * N;
         dem[lb * NP + n] = a.input[((b0 + lb) * N + n) * D + D - 1];
@@ -152,19 +162,42 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
     constexpr uint32_t idescL = tc_idesc(128, RB), idescQ = tc_idesc(128, 32);
     const bool tracing = a.tr_logits || a.tr_probs || a.tr_masks;
-    // the fast per-row tail serves plain greedy decoding when nobody reads probabilities, log-probabilities or masks
+    // the fast per-row path serves plain greedy decoding when nobody reads probabilities, log-probabilities or masks
     const bool fastk = a.mode == 0 && !a.full && a.mask_pointer && !a.use_tanh && a.logprob_out == nullptr && a.fin_mask == nullptr && !tracing;
+    const unsigned ltm = (1u << lane) - 1;
+
+    // 128-bit node set -> the row's item list (ascending node ids), the set itself, count and "all nodes" flag
+    auto publish_items = [&](int lr, unsigned (&bits)[4], bool on) {
+        int nit = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
+        int fl = 0;
+        if (on && (a.full || nit == 0 || !a.mask_pointer)) {   // every node is evaluated (the mask counts decide)
+            fl = 1; nit = N;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) bits[k] = (N - 32 * k >= 32) ? kFull : (N - 32 * k > 0 ? ((1u << (N - 32 * k)) - 1) : 0u);
+        }
+        if (!on) { nit = 0; bits[0] = bits[1] = bits[2] = bits[3] = 0u; }
+        unsigned char* it = items + lr * NP;
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if ((bits[k] >> lane) & 1) it[base + __popc(bits[k] & ltm)] = (unsigned char)(lane + 32 * k);
+            base += __popc(bits[k]);
+        }
+        if (lane < 4) ibits[lr * 4 + lane] = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
+        if (lane == 0) { nact_s[lr] = nit; flag_s[lr] = fl; }
+        return fl;
+    };
 
     // ---- Env.reset (vrptw_utils.py:199-252) + prologue (attention_agent.py:126-134): one warp per row, lane owns nodes lane + 32 k
     if (warp < 16) {
         for (int lr = warp; lr < RB; lr += 16) {
             float* rs = rowst + lr * kRS5;
+            unsigned bits[4] = {0u, 0u, 0u, 0u};
             if (lr >= IBv) {   // no instance behind this row slot: finished from the start, no items
-                if (lane == 0) { nact_s[lr] = 0; flag_s[lr] = 0; reinterpret_cast<int*>(rs)[8] = 1; rs[9] = rs[10] = rs[11] = rs[12] = 0.0f; rs[0] = rs[1] = 0.0f; }
-                if (lane < 4) ibits[lr * 4 + lane] = 0;
+                if (lane == 0) { reinterpret_cast<int*>(rs)[8] = 1; rs[9] = rs[10] = rs[11] = rs[12] = 0.0f; rs[0] = rs[1] = 0.0f; }
+                publish_items(lr, bits, false);
                 continue;
             }
-            unsigned bits[4];
             int nzc = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -174,18 +207,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 bits[k] = __ballot_sync(kFull, has);
                 nzc += __popc(bits[k]);
             }
-            int nit = nzc, fl = 0;
-            if (a.full || nit == 0 || !a.mask_pointer) {   // every node is evaluated
-                fl = 1; nit = N;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) bits[k] = (N - 32 * k >= 32) ? kFull : (N - 32 * k > 0 ? ((1u << (N - 32 * k)) - 1) : 0u);
-            }
-            int base = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if ((bits[k] >> lane) & 1) items[lr * NP + base + __popc(bits[k] & ((1u << lane) - 1))] = (unsigned char)(lane + 32 * k);
-                base += __popc(bits[k]);
-            }
+            publish_items(lr, bits, true);
             const float4 fdep = __ldcg(gfeat4 + (size_t)lr * N + n_cust);
             if (lane == 0) {
                 rs[0] = a.capacity; rs[1] = 0.0f; rs[2] = fdep.x; rs[3] = fdep.y; rs[4] = 0.0f; rs[5] = 0.0f; rs[6] = 0.0f;
@@ -193,9 +215,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 reinterpret_cast<int*>(rs)[8] = 0;
                 rs[9] = fdep.x; rs[10] = fdep.y; rs[11] = TW ? fdep.z : 0.0f; rs[12] = TW ? fdep.w : 0.0f;
                 rs[13] = (float)nzc; rs[15] = 0.0f;
-                nact_s[lr] = nit; flag_s[lr] = fl;
             }
-            if (lane < 4) ibits[lr * 4 + lane] = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
         }
     }
     __syncthreads();
@@ -256,10 +276,12 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
+#ifdef VRP_THROTTLE_GATES
                     if (u > 0) {   // throttle: one ring stage in the tensor-pipe queue, the score MMAs queue behind it
                         const uint32_t cp = c - 1;
                         mbar_wait(bar_empty + 8 * (cp % STAGES), (cp / STAGES) & 1);
                     }
+#endif
                     tc_fence_after();
                     const int kc = u >> 1, mp = u & 1;
                     const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
@@ -305,87 +327,21 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
         }
         __syncwarp();
     } else if (warp >= 16) {
-        // ============ aux warps: per-row tails streamed behind the score tiles + LSTM epilogue of the next step ==========
+        // ============ aux warps: the per-row tail (choice + Env.step), streamed behind the score tiles ====================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        const int ax = warp - 16;                                // = TMEM sub-partition of this warp; rows ax, ax + 4, ...
-        const int unit = 32 * ax + lane;
-        float wx[4][4], bgt[4];                                  // x part of the LSTM gates (rank D-1 through the embedding) + biases
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-            bgt[m] = __ldg(a.bgT + m * kH + unit);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) wx[k][m] = __ldg(a.WxT + (k * 4 + m) * kH + unit);
-        }
-        // LSTM epilogue of the rows 4j .. 4j+3: gates = gates^T(TMEM, h part) + x part + bias; c, h'; h' -> X (hi | lo)
-        auto lstm_chunk = [&](int j, bool first) {
-            const int r0 = 4 * j;
-            float g[4][4], cc[4];
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-                if (!first) tc_ld4(tmem_lane + kGCol + RB * m + r0, g[m]);
-                else { g[m][0] = g[m][1] = g[m][2] = g[m][3] = 0.0f; }
-            }
-            if (!first) tc_ld4(tmem_lane + kCCol + r0, cc);
-            else { cc[0] = cc[1] = cc[2] = cc[3] = 0.0f; }
-            float hi[4], lo[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float* rs = rowst + (r0 + i) * kRS5;
-                const float xf[4] = {rs[9], rs[10], rs[11], rs[12]};
-                float gg[4];
-#pragma unroll
-                for (int m = 0; m < 4; ++m) {
-                    float s = bgt[m];
-#pragma unroll
-                    for (int k = 0; k < FD; ++k) s = fmaf(xf[k], wx[k][m], s);
-                    gg[m] = g[m][i] + s;
-                }
-                const float cn = __fadd_rn(__fmul_rn(cc[i], sigmoid_fast(gg[2] + a.forget_bias)),
-                                           __fmul_rn(sigmoid_fast(gg[0]), tanh_fast(gg[1])));
-                cc[i] = cn;
-                const float hn = __fmul_rn(tanh_fast(cn), sigmoid_fast(gg[3]));
-                hi[i] = tf32_rna(hn);
-                lo[i] = hn - hi[i];
-            }
-            tc_st4(tmem_lane + kCCol + r0, cc);
-            transpose4(hi, lane);
-            transpose4(lo, lane);
-            const int rr = r0 + (lane & 3);
-            const int off = (rr >> 3) * 4096 + (unit >> 2) * 128 + (rr & 7) * 16;
-            *reinterpret_cast<float4*>(xt + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<float4*>(xt + RB * kH * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        };
-        // step 0: h_0 = c_0 = 0, decoder input = the depot (attention_agent.py:126-134)
-        for (int j = 0; j < NCH; ++j) lstm_chunk(j, true);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_x);
-
+        const int ax = warp - 16;                                // rows ax, ax + 4, ...: one row of every 4-row chunk
         unsigned long long n_rowsteps = 0;
 #ifdef VRPB200_PHASE_CLOCKS
-        long long pc_[12], pc_last_ = clock64();
-        for (int i = 0; i < 12; ++i) pc_[i] = 0;
+        long long pc_[8], pc_last_ = clock64();
+        for (int i = 0; i < 8; ++i) pc_[i] = 0;
 #endif
         int t = 0;
 #pragma unroll 1
         for (;; ++t) {
-            mbar_wait(bar_x, t & 1);                             // every aux warp has finished step t - 1: nact / items are final
+            mbar_wait(bar_x, t & 1);                             // T0 of step t
             if (*stop_s) break;
+            mbar_wait(bar_items, t & 1);                         // item lists, item sets and row offsets of step t are published
             VRP_CLK(0);
-            // exclusive prefix of the item counts (registers: lane l holds rows l and l + 32)
-            int ex0, ex1;
-            {
-                const int n0 = (lane < RB) ? nact_s[lane] : 0, n1 = (lane + 32 < RB) ? nact_s[lane + 32] : 0;
-                int s0 = n0, s1 = n1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t0 = __shfl_up_sync(kFull, s0, o), t1 = __shfl_up_sync(kFull, s1, o);
-                    if (lane >= o) { s0 += t0; s1 += t1; }
-                }
-                const int tot0 = __shfl_sync(kFull, s0, 31);
-                ex0 = s0 - n0; ex1 = tot0 + s1 - n1;
-            }
 #pragma unroll 1
             for (int j = 0; j < NCH; ++j) {
                 const int lr = 4 * j + ax;
@@ -393,44 +349,38 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 float* rs = rowst + lr * kRS5;
                 const long long row = b0 + lr;
                 const bool was_done = reinterpret_cast<int*>(rs)[8] != 0;
-                const bool live = rvalid && !was_done;
                 if (rvalid && was_done && lane == 0) {
                     a.idx_out[(long long)t * R + row] = n_cust;
                     if (a.logprob_out) a.logprob_out[(long long)t * R + row] = 0.0f;
                 }
-                if (live) {
-                    // ================= per-row tail ======================================================================
+                if (rvalid && !was_done) {
                     if (lane == 0) ++n_rowsteps;
                     const float load = rs[0], time = TW ? rs[1] : 0.0f;
                     const float4* frow = gfeat4 + (size_t)lr * N;
                     float* drow = dem + lr * NP;
                     float* ulog = logits + lr * NP;
-                    unsigned char* mk = maskb + lr * NP;
-                    unsigned char* it = items + lr * NP;
+                    const unsigned char* mk = maskb + lr * NP;
+                    const unsigned char* it = items + lr * NP;
                     const int fl = flag_s[lr], na = nact_s[lr];
                     const bool fast = fastk && fl == 0;
-                    // (0) this lane's nodes: demand, and the features of the customers that may matter for the next mask -
-                    //     issued before the wait for the logits, used after the choice
+                    // (0) the records of this lane's items (the chosen node is one of them): issued before the wait for the
+                    //     logits, used after the choice
                     float dk[4];
                     float4 fk[4];
-                    bool has[4];
+                    bool isit[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const int n = lane + 32 * k;
+                        isit[k] = (ibits[lr * 4 + k] >> lane) & 1;
                         dk[k] = (n < N) ? drow[n] : 0.0f;
-                        has[k] = n < n_cust && dk[k] != 0.0f;
                         fk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (n < n_cust && (has[k] || !fast)) fk[k] = ldcg4_volatile(frow + n);
+                        if (isit[k] && n < n_cust) fk[k] = ldcg4_volatile(frow + n);
                     }
-                    {   // wait for every tile that holds items of this row
-                        const int i0 = lr < 32 ? __shfl_sync(kFull, ex0, lr) : __shfl_sync(kFull, ex1, lr - 32);
-                        if (na > 0) {
-                            const int tl = (i0 + na - 1) >> 7;
-                            for (int tile = i0 >> 7; tile <= tl; ++tile) mbar_wait(bar_tile + 8 * tile, t & 1);
-                        }
+                    if (na > 0) {   // wait for every tile that holds items of this row
+                        const int i0 = off_s[lr], tl = (i0 + na - 1) >> 7;
+                        for (int tile = i0 >> 7; tile <= tl; ++tile) mbar_wait(bar_tile + 8 * tile, t & 1);
                     }
                     VRP_CLK(1);
-                    const unsigned ltm = (1u << lane) - 1;
                     int idx;
                     float psel = 1.0f;
                     if (fast) {
@@ -442,8 +392,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                         int mxi = 0x7fffffff;
 #pragma unroll
                         for (int k = 0; k < 4; ++k) {
-                            const bool isit = (ibits[lr * 4 + k] >> lane) & 1;
-                            u[k] = isit ? ulog[lane + 32 * k] : -INFINITY;
+                            u[k] = isit[k] ? ulog[lane + 32 * k] : -INFINITY;
                             if (u[k] > mx) { second = mx; mx = u[k]; mxi = lane + 32 * k; }
                             else second = fmaxf(second, u[k]);
                         }
@@ -456,10 +405,10 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                             if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                         }
                         if (second > mx - 1e-5f) {
-                            // near-tie: exact probabilities, summed in the fixed order of the exact tail (lane = node % 32 adds its
+                            // near-tie: exact probabilities, summed in the fixed order of the exact path (lane = node % 32 adds its
                             // nodes in sequence, then the xor butterfly); masked nodes have probability exactly 0
 #ifdef VRPB200_PHASE_CLOCKS
-                            pc_[10] += 1;
+                            pc_[7] += 1;
 #endif
                             float se = 0.0f;
 #pragma unroll
@@ -485,20 +434,8 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                         idx = mxi;
                     } else {
                         // ---- exact choice: masked logits (decode_step.py:231-232), log-softmax / probabilities (:125-126), greedy
-                        //      arg-max of the probabilities or inverse-CDF sampling (attention_agent.py:146-167), traces
-                        if (fastk) {   // handed over by the fast tail, which keeps no mask counts: recompute them from the state
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-                                const int n = lane + 32 * k;
-                                if (n < N) {
-                                    int mm;
-                                    if (t == 0) mm = (n == n_cust) ? 1 : (dk[k] == 0.0f ? 1 : 0);
-                                    else mm = node_mask<TW>(n, n_cust, dk[k], rs[0], TW ? rs[1] : 0.0f, rs[2], rs[3], fk[k].x, fk[k].y, fk[k].w, rs[15], rs[13]);
-                                    mk[n] = (unsigned char)mm;
-                                }
-                            }
-                            __syncwarp();
-                        }
+                        //      arg-max of the probabilities or inverse-CDF sampling (attention_agent.py:146-167), traces.  The mask
+                        //      counts of the row were written by the score warp that built its item list.
                         const long long tro = ((long long)t * R + row) * N;
                         float u[4];
                         float mx = -INFINITY, second = -INFINITY;
@@ -600,20 +537,20 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                         }
                     }
                     VRP_CLK(2);
-                    // ---- Env.step (vrptw_utils.py:254-358): the record of the chosen node comes from the lane that owns it
-                    //      (every item is a customer with demand left, whose record was fetched above, or the depot)
+                    // ---- Env.step (vrptw_utils.py:254-325): the record of the chosen node comes from the lane that owns it
+                    //      (a chosen customer is an item, whose record was fetched above; the depot's is part of the row state)
                     float sx, sy, sb, se_tw, d_idx;
                     {
                         const int ko = idx >> 5, lo = idx & 31;
                         const float4 fo = ko == 0 ? fk[0] : ko == 1 ? fk[1] : ko == 2 ? fk[2] : fk[3];
                         const float dko = ko == 0 ? dk[0] : ko == 1 ? dk[1] : ko == 2 ? dk[2] : dk[3];
-                        const bool hko = ko == 0 ? has[0] : ko == 1 ? has[1] : ko == 2 ? has[2] : has[3];
+                        const bool iko = ko == 0 ? isit[0] : ko == 1 ? isit[1] : ko == 2 ? isit[2] : isit[3];
                         sx = __shfl_sync(kFull, fo.x, lo); sy = __shfl_sync(kFull, fo.y, lo);
                         sb = __shfl_sync(kFull, fo.z, lo); se_tw = __shfl_sync(kFull, fo.w, lo);
                         d_idx = __shfl_sync(kFull, dko, lo);
-                        const int have = __shfl_sync(kFull, (int)(hko || (!fast && idx < n_cust)), lo);
+                        const int have = __shfl_sync(kFull, (int)iko, lo);
                         if (idx == n_cust) { sx = rs[7]; sy = rs[14]; sb = rs[16]; se_tw = rs[17]; }
-                        else if (!have) {   // (a customer without demand can only be chosen when every node is masked)
+                        else if (!have) {   // (a node that is not an item can only be chosen when every node is masked)
                             const float4 fv = __ldcg(frow + idx);
                             sx = fv.x; sy = fv.y; sb = fv.z; se_tw = fv.w;
                         }
@@ -644,74 +581,16 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                         if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
                     }
                     VRP_CLK(3);
-                    // ---- mask of the next step (vrptw_utils.py:328-348) -> 128-bit item set, item list, count
-                    const bool on = !done_now;
-                    unsigned bits[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int n = lane + 32 * k;
-                        const float dn = (n == idx) ? d_new : dk[k];
-                        bool um = false;
-                        if (n < N) {
-                            if (fastk) {   // un-masked / masked only (the counts are recomputed if a row ever needs them)
-                                if (n < n_cust) {
-                                    um = dn != 0.0f && nload != 0.0f;
-                                    if (TW && um) um = !(__fadd_rn(ntime, dist_rn(sx, sy, fk[k].x, fk[k].y)) > fk[k].w);
-                                } else um = !(nz > 0.0f && dep != 0.0f);
-                            } else {
-                                const int mm = node_mask<TW>(n, n_cust, dn, nload, ntime, sx, sy, fk[k].x, fk[k].y, fk[k].w, dep, nz);
-                                mk[n] = (unsigned char)mm;
-                                um = mm == 0;
-                            }
-                        }
-                        bits[k] = __ballot_sync(kFull, um && on);
-                    }
-                    int nit = __popc(bits[0]) + __popc(bits[1]) + __popc(bits[2]) + __popc(bits[3]);
-                    int flv = 0;
-                    if (on && (a.full || nit == 0 || !a.mask_pointer)) {   // every node is evaluated (the mask counts decide)
-                        flv = 1; nit = N;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) bits[k] = (N - 32 * k >= 32) ? kFull : (N - 32 * k > 0 ? ((1u << (N - 32 * k)) - 1) : 0u);
-                    }
-                    int base = 0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if ((bits[k] >> lane) & 1) it[base + __popc(bits[k] & ltm)] = (unsigned char)(lane + 32 * k);
-                        base += __popc(bits[k]);
-                    }
-                    if (lane < 4) ibits[lr * 4 + lane] = lane == 0 ? bits[0] : lane == 1 ? bits[1] : lane == 2 ? bits[2] : bits[3];
-                    if (lane == 0) { nact_s[lr] = nit; flag_s[lr] = flv; }
-                    VRP_CLK(4);
                 }
-                // ---- the four rows of chunk j have moved: LSTM epilogue of those rows for the next step
-                named_bar(6, 128);
-                VRP_CLK(5);
-                if (j == 0) {
-                    mbar_wait(bar_g, t & 1);                     // gates^T(t+1) = W_h^T h'(t)^T is complete (and X is no longer read)
-                    tc_fence_after();
-                    VRP_CLK(6);
-                }
-                lstm_chunk(j, false);
-                VRP_CLK(7);
+                VRP_CLK(4);
             }
-            fence_proxy_async();
-            tc_fence_before();
-            named_bar(6, 128);                                   // every row's "done" flag is final
-            {
-                const int d0 = (lane < IBv) ? reinterpret_cast<const int*>(rowst + lane * kRS5)[8] : 1;
-                const int d1 = (lane + 32 < IBv) ? reinterpret_cast<const int*>(rowst + (lane + 32) * kRS5)[8] : 1;
-                const bool all_done = __all_sync(kFull, d0 && d1);
-                if (ax == 0 && lane == 0 && (all_done || t == T - 1)) { *tend_s = t + 1; *stop_s = 1; }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_x);                   // T0 of the next step
-            VRP_CLK(8);
+            named_bar_arrive(7, 640);                            // every row of this warp has moved (the score warps are parked there)
         }
         if (a.stats) {
             if (lane == 0 && n_rowsteps) atomicAdd(a.stats + 1, n_rowsteps);
 #ifdef VRPB200_PHASE_CLOCKS
             if (tid == 16 * 32)
-                for (int i = 0; i < 12; ++i) atomicAdd(a.stats + 16 + i, (unsigned long long)pc_[i]);
+                for (int i = 0; i < 8; ++i) atomicAdd(a.stats + 20 + i, (unsigned long long)pc_[i]);
 #endif
         }
     } else {
@@ -721,22 +600,146 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
         const int g = warp >> 3;                                         // score group
         const int half = ub & 1;                                         // hidden units 64 half .. 64 half + 63 (quarters half, half + 2)
         const int m = 32 * sp + lane;                                    // item of the tile
-        const int unit = 32 * sp + lane;                                 // hidden unit in the query epilogue
+        const int unit = 32 * sp + lane;                                 // hidden unit in the LSTM / query epilogues
         unsigned char* fgrp = ftile + g * 4 * kC1TileBytes;
         const uint32_t bfull = bar_grp + 64 * g, bfree = bfull + 24, bfrdy = bfull + 48, bpsum = bar_psum + 8 * g, bpack = bar_pack + 8 * g;
         float* ps = psum + g * 256;
         uint32_t c1_nq = 0;                                              // tiles of this group so far (all steps)
         unsigned long long n_eval = 0;
 #ifdef VRPB200_PHASE_CLOCKS
-        long long pc_[12], pc_last_ = clock64();
-        for (int i = 0; i < 12; ++i) pc_[i] = 0;
+        long long pc_[16], pc_last_ = clock64();
+        for (int i = 0; i < 16; ++i) pc_[i] = 0;
 #endif
+        // LSTM epilogue of the rows 4j .. 4j+3 (this warp: units 32 sp .. 32 sp + 31; chunk j belongs to team j % 4 = ub):
+        // gates = gates^T(TMEM, h part) + x part + bias; c, h'; h' -> X (hi | lo)
+        auto lstm_chunk = [&](int j, bool first) {
+            const int r0 = 4 * j;
+            float gt[4][4], cc[4];
+#pragma unroll
+            for (int mm = 0; mm < 4; ++mm) {
+                if (!first) tc_ld4(tmem_lane + kGCol + RB * mm + r0, gt[mm]);
+                else { gt[mm][0] = gt[mm][1] = gt[mm][2] = gt[mm][3] = 0.0f; }
+            }
+            if (!first) tc_ld4(tmem_lane + kCCol + r0, cc);
+            else { cc[0] = cc[1] = cc[2] = cc[3] = 0.0f; }
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float* rs = rowst + (r0 + i) * kRS5;
+                const float xf[4] = {rs[9], rs[10], rs[11], rs[12]};
+                float gg[4];
+#pragma unroll
+                for (int mm = 0; mm < 4; ++mm) {
+                    float s = wxs[(16 + mm) * kH + unit];
+#pragma unroll
+                    for (int k = 0; k < FD; ++k) s = fmaf(xf[k], wxs[(k * 4 + mm) * kH + unit], s);
+                    gg[mm] = gt[mm][i] + s;
+                }
+                const float cn = __fadd_rn(__fmul_rn(cc[i], sigmoid_fast(gg[2] + a.forget_bias)),
+                                           __fmul_rn(sigmoid_fast(gg[0]), tanh_fast(gg[1])));
+                cc[i] = cn;
+                const float hn = __fmul_rn(tanh_fast(cn), sigmoid_fast(gg[3]));
+                hi[i] = tf32_rna(hn);
+                lo[i] = hn - hi[i];
+            }
+            tc_st4(tmem_lane + kCCol + r0, cc);
+            transpose4(hi, lane);
+            transpose4(lo, lane);
+            const int rr = r0 + (lane & 3);
+            const int off = (rr >> 3) * 4096 + (unit >> 2) * 128 + (rr & 7) * 16;
+            *reinterpret_cast<float4*>(xt + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(xt + RB * kH * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        };
+        // Env mask of a row after its last move (vrptw_utils.py:328-348) -> 128-bit item set, item list, count; one warp per
+        // row, lane owns nodes lane + 32 k.  Plain greedy decoding keeps no mask counts (un-masked / masked only) unless a row
+        // has no un-masked node left; then (and in every other mode) the counts are written for the aux warps.
+        // One code path, kept small: this runs once per step and must not evict the score loop from the instruction cache.
+        auto build_masks = [&](int lr, const float4 (&fk)[4], bool exact) {
+            const float* rs = rowst + lr * kRS5;
+            const bool on = lr < IBv && reinterpret_cast<const int*>(rs)[8] == 0;
+            const float nload = rs[0], ntime = TW ? rs[1] : 0.0f, sx = rs[2], sy = rs[3], nz = rs[13], dep = rs[15];
+            const float* drow = dem + lr * NP;
+            unsigned char* mk = maskb + lr * NP;
+            unsigned bits[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = lane + 32 * k;
+                int mm = 1;
+                if (n < N && on) {
+                    if (n == n_cust) mm = (nz > 0.0f && dep != 0.0f) ? 1 : 0;
+                    else {
+                        mm = (drow[n] == 0.0f) + (nload == 0.0f);
+                        if (TW && (exact || mm == 0)) mm += (__fadd_rn(ntime, dist_rn(sx, sy, fk[k].x, fk[k].y)) > fk[k].w);
+                    }
+                    if (exact) mk[n] = (unsigned char)mm;
+                }
+                bits[k] = __ballot_sync(kFull, mm == 0);
+            }
+            return publish_items(lr, bits, on);
+        };
+        float4 fnext[4];                                                 // mask records of the warp's next row (software pipeline)
+        // the records a row's time-window test can need: its customers with demand left (a superset: demand only decreases)
+        auto mask_records = [&](int lr, float4 (&fk)[4], bool all) {
+            const bool on = lr < IBv && reinterpret_cast<const int*>(rowst + lr * kRS5)[8] == 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int n = lane + 32 * k;
+                fk[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (TW && on && lr < RB && n < n_cust && (all || dem[lr * NP + n] != 0.0f)) fk[k] = ldcg4_volatile(gfeat4 + (size_t)lr * N + n);
+            }
+        };
         int t = 0;
 #pragma unroll 1
         for (;; ++t) {
-            mbar_wait(bar_x, t & 1);                                     // T0: item lists of this step are final
-            if (*stop_s) break;
+            // ================= T0': every row has made its move of step t - 1 (the aux warps arrive on this barrier) =========
+            if (t > 0) named_bar(7, 640);
+            {
+                const int d0 = (lane < IBv) ? reinterpret_cast<const int*>(rowst + lane * kRS5)[8] : 1;
+                const int d1 = (lane + 32 < IBv) ? reinterpret_cast<const int*>(rowst + (lane + 32) * kRS5)[8] : 1;
+                const bool stop = t > 0 && (__all_sync(kFull, d0 && d1) || t == T);   // (the same in every warp)
+                if (stop) {
+                    if (tid == 0) {
+                        *tend_s = t; *stop_s = 1;
+                        __threadfence_block();
+                        mbar_arrive(bar_x);                              // feeder, MMA issuer and aux warps leave
+                    }
+                    break;
+                }
+            }
             VRP_CLK(0);
+            if (t > 0) mask_records(warp, fnext, !fastk);                // in flight during the LSTM epilogue
+            // ================= LSTM epilogue -> h'(t) (step 0: h_0 = c_0 = 0, decoder input = the depot, attention_agent.py:126-134)
+            if (t > 0) {
+                mbar_wait(bar_g, (t - 1) & 1);                           // gates^T(t) = W_h^T h'(t-1)^T: issued a whole step ago
+                tc_fence_after();
+            }
+#pragma unroll 1
+            for (int j = ub; j < NCH; j += 4) lstm_chunk(j, t == 0);
+            fence_proxy_async();
+            tc_fence_before();
+            named_bar(5, 512);
+            if (tid == 0) mbar_arrive(bar_x);                            // T0: h'(t) is in place - feeder, MMA issuer, aux warps
+            VRP_CLK(1);
+            // ================= Env mask -> item lists of this step (the query GEMM is running) ============================
+            if (t > 0) {
+                bool exact = !fastk;
+#pragma unroll 1
+                for (int lr = warp; lr < RB;) {
+                    float4 fk[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) fk[k] = fnext[k];
+                    if (!exact || !fastk) mask_records(lr + 16, fnext, !fastk);   // the next row's records, in flight during this row
+                    const int fl = build_masks(lr, fk, exact);
+                    // no un-masked node: the mask COUNTS decide the choice - the same row once more, exactly (rare)
+                    if (fastk && fl && !exact) { exact = true; mask_records(lr, fnext, true); }
+                    else {
+                        if (fastk && exact) mask_records(lr + 16, fnext, false);
+                        exact = !fastk; lr += 16;
+                    }
+                }
+            }
+            VRP_CLK(9);
+            named_bar(5, 512);                                           // item lists final
             // ================= row offsets of this step's item lists (every warp, redundantly; warp 0 publishes them) ======
             int m_tot;
             {
@@ -757,6 +760,8 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 if (tid < 64 && tid >= ((m_tot + 127) >> 7)) mbar_arrive_n(bar_tile + 8 * tid, 4);   // tiles that do not exist in this step
             }
             named_bar(5, 512);                                           // off_s is in place
+            VRP_CLK(15);
+            if (tid == 0) mbar_arrive(bar_items);                        // the aux warps may look at item lists and offsets
             const int ntiles = (m_tot + 127) >> 7;
             // item `it` of the step -> (row, node): binary search in the row offsets, then the row's node list
             auto load_item = [&](int tile, int& r, int& n, bool& valid, float (&f)[5], bool feats) {
@@ -844,10 +849,11 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                     }
                 }
             }
-            VRP_CLK(1);
+            VRP_CLK(11);
             // ================= query epilogue: base'[row][unit] = 2log2e (q + b + load g_ld + time g_t) ===================
             const float bqv = __ldg(a.att.bq + unit), glv = __ldg(a.att.gl + unit), gtv = __ldg(a.att.gt + unit);
-            mbar_wait(bar_q, t & 1);
+            if (warp == 0) mbar_wait(bar_q, t & 1);                      // one warp polls, the others are parked
+            named_bar(5, 512);
             tc_fence_after();
             VRP_CLK(2);
 #pragma unroll 1
@@ -867,7 +873,7 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
             named_bar(5, 512);
             tc_fence_after();
             VRP_CLK(3);
-            // ================= C1: scores ==============================================================================
+            // ================= C1: scores (the aux warps stream the per-row tails behind the tiles) ========================
             // c1_nq counts the tiles of this group (all steps): tile k uses F tile k & 1; its quarter q is the (4k + q)-th use of
             // the group's TMEM buffers, which rotate over three.  Warps of half 0 gather the items, write F and take quarters 0, 2;
             // warps of half 1 take quarters 1, 3 of the same items and hand their partial sum over through shared memory.
@@ -877,66 +883,65 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 float fn[5];
 #pragma unroll 1
                 for (int tile = g; tile < ntiles; tile += NG) {
-                    const float* brow = qq + r_cur * kH;
-                    const uint32_t par = c1_nq & 1;
-                    float acc0 = 0.0f, acc1 = 0.0f;
+                const float* brow = qq + r_cur * kH;
+                const uint32_t par = c1_nq & 1;
+                float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-                    for (int qi = 0; qi < 2; ++qi) {
-                        const int q = 2 * qi + half;
-                        const uint32_t cq = 4 * c1_nq + q, buf = cq % 3, bpar = (cq / 3) & 1;
-                        VRP_CLK(4);
-                        mbar_wait(bfull + 8 * buf, bpar);
-                        tc_fence_after();
-                        VRP_CLK(5);
-                        uint32_t cur[32];
-                        tc_ld32_issue(tmem_lane + 96 * g + 32 * buf, cur);
-                        tc_ld_wait32(cur);
-                        tc_fence_before();
-                        if (lane == 0) mbar_arrive(bfree + 8 * buf);     // the issuer may send another quarter here
+                for (int qi = 0; qi < 2; ++qi) {
+                    const int q = 2 * qi + half;
+                    const uint32_t cq = 4 * c1_nq + q, buf = cq % 3, bpar = (cq / 3) & 1;
+                    VRP_CLK(4);
+                    mbar_wait(bfull + 8 * buf, bpar);
+                    tc_fence_after();
+                    VRP_CLK(5);
+                    uint32_t cur[32];
+                    tc_ld32_issue(tmem_lane + 96 * g + 32 * buf, cur);
+                    tc_ld_wait32(cur);
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive(bfree + 8 * buf);     // the issuer may send another quarter here
+                    __syncwarp();
+                    VRP_CLK(6);
+                    // the items two tiles ahead: row look-up and feature loads are scheduled into the arithmetic below
+                    if (qi == 0) load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn, half == 0);
+                    quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
+                    VRP_CLK(7);
+                }
+                if (half == 1) {
+                    if (c1_nq > 0) mbar_wait(bpack, (c1_nq - 1) & 1);   // the other half has taken the previous tile's sums
+                    ps[par * 128 + m] = acc0 + acc1;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bpsum);
+                } else {
+                    mbar_wait(bpsum, par);      // (also: quarters 1 and 3 of this tile have been read, its F tile is free)
+                    const float psv = ps[par * 128 + m];
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bpack);
+                    // u = sum_h v_h tanh(.) = sum_h v_h - sum_h 2 v_h / (1 + 2^arg)
+                    if (v_cur) logits[r_cur * NP + n_cur] = (a.sumv + (acc0 + acc1)) + psv;
+                    n_eval += v_cur ? 1 : 0;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished (release: logits visible)
+                    if (tile + 2 * NG < ntiles) {
+                        store_F(fgrp + par * 2 * kC1TileBytes, fn);
                         __syncwarp();
-                        VRP_CLK(6);
-                        // the items two tiles ahead: row look-up and feature loads are scheduled into the arithmetic below
-                        if (qi == 0) load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn, half == 0);
-                        quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
-                        VRP_CLK(7);
+                        if (lane == 0) mbar_arrive(bfrdy + 8 * par);
                     }
-                    if (half == 1) {
-                        if (c1_nq > 0) mbar_wait(bpack, (c1_nq - 1) & 1);   // the other half has taken the previous tile's sums
-                        ps[par * 128 + m] = acc0 + acc1;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bpsum);
-                    } else {
-                        mbar_wait(bpsum, par);      // (also: quarters 1 and 3 of this tile have been read, its F tile is free)
-                        const float psv = ps[par * 128 + m];
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bpack);
-                        // u = sum_h v_h tanh(.) = sum_h v_h - sum_h 2 v_h / (1 + 2^arg)
-                        if (v_cur) logits[r_cur * NP + n_cur] = (a.sumv + (acc0 + acc1)) + psv;
-                        n_eval += v_cur ? 1 : 0;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished (release: logits visible)
-                        if (tile + 2 * NG < ntiles) {
-                            store_F(fgrp + par * 2 * kC1TileBytes, fn);
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bfrdy + 8 * par);
-                        }
-                    }
-                    VRP_CLK(8);
-                    ++c1_nq;
-                    r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
-                    r_nx = r_n2; n_nx = n_n2; v_nx = v_n2;
+                }
+                VRP_CLK(8);
+                ++c1_nq;
+                r_cur = r_nx; n_cur = n_nx; v_cur = v_nx;
+                r_nx = r_n2; n_nx = n_n2; v_nx = v_n2;
                 }
             }
-            VRP_CLK(9);
+            VRP_CLK(10);
         }
         // wake the score-MMA issuers (they wait for the F tile of the group's next tile)
-        named_bar(5, 512);
         if (half == 0 && lane == 0) mbar_arrive(bfrdy + 8 * (c1_nq & 1));
         if (a.stats) {
             if (n_eval) atomicAdd(a.stats + 0, n_eval);
 #ifdef VRPB200_PHASE_CLOCKS
             if (tid == 64)
-                for (int i = 0; i < 12; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)pc_[i]);
+                for (int i = 0; i < 16; ++i) atomicAdd(a.stats + 4 + i, (unsigned long long)pc_[i]);
 #endif
         }
     }
@@ -956,7 +961,11 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
             if (lane == 0) a.cost_out[row] = __fadd_rn(rs[4], dist_rn(rs[2], rs[3], rs[5], rs[6]));
             for (int n = lane; n < N; n += 32) {
                 if (a.fin_demand) a.fin_demand[row * N + n] = dem[lr * NP + n];
-                if (a.fin_mask) a.fin_mask[row * N + n] = (float)maskb[lr * NP + n];
+                if (a.fin_mask) {   // Env.mask after the last move (vrptw_utils.py:328-348)
+                    float nx = 0.f, ny = 0.f, ne = 0.f;
+                    if (TW && n < n_cust) { const float4 fv = __ldcg(gfeat4 + (size_t)lr * N + n); nx = fv.x; ny = fv.y; ne = fv.w; }
+                    a.fin_mask[row * N + n] = (float)node_mask<TW>(n, n_cust, dem[lr * NP + n], rs[0], TW ? rs[1] : 0.0f, rs[2], rs[3], nx, ny, ne, rs[15], rs[13]);
+                }
             }
             if (lane == 0) {
                 if (a.fin_load) a.fin_load[row] = rs[0];

@@ -32,16 +32,17 @@ names = (["wait gates MMA", "LSTM epilogue + masks", "C0 items + wait q", "q epi
          ["A: wait MMA (TMA+tcgen05)", "A: LSTM epilogue + sync", "B: wait MMA", "B: q epilogue + sync", "C: rows", "C: step barrier wait"])
 print(task, B, gemm, eng.last_launch(), "block-steps", blocksteps)
 if gemm == "tc5":
-    sn = ["(loop)", "T0 -> offsets + first tiles staged", "wait q", "q epilogue + barrier", "C1: tile end / loop", "C1: wait MMA", "C1: TMEM load, free", "C1: arithmetic", "C1: psum / logits / next F", "after last tile"]
-    an = ["(wait T0)", "prefix + prefetch + wait tiles", "choice", "Env.step", "next mask + item list", "chunk barrier", "wait gates MMA", "LSTM epilogue chunk", "step end (done flags, arrive)"]
+    sn = {0: "T0' barrier (wait for the aux warps)", 1: "LSTM epilogue + barrier", 15: "offsets + barrier", 11: "first tiles staged", 2: "wait q", 3: "q epilogue + barrier",
+          4: "C1: (loop top)", 5: "C1: wait MMA", 6: "C1: TMEM load, free", 7: "C1: arithmetic", 8: "C1: psum / logits / next F", 10: "after the last tile"}
+    an = {0: "wait T0 + item lists", 1: "prefetch + wait tiles", 2: "choice", 3: "Env.step", 5: "next mask + item list", 4: "row end"}
     print("  score warp 2")
-    for n, v in zip(sn, s[4:4 + len(sn)]):
-        print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
-    print(f"    total {s[4:16].sum() / blocksteps:.0f} clk/step")
+    for i in (0, 1, 15, 11, 2, 3, 4, 5, 6, 7, 8, 10):
+        print(f"    {sn[i]:40s} {s[4 + i] / blocksteps:10.0f} clk/step")
+    print(f"    total {s[4:20].sum() / blocksteps:.0f} clk/step")
     print("  aux warp 16")
-    for n, v in zip(an, s[16:16 + len(an)]):
-        print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
-    print(f"    total {s[16:25].sum() / blocksteps:.0f} clk/step;  near-tie softmax visits (row-steps of this warp): {s[26]}")
+    for i in (0, 1, 2, 3, 5, 4):
+        print(f"    {an[i]:40s} {s[20 + i] / blocksteps:10.0f} clk/step")
+    print(f"    total {s[20:27].sum() / blocksteps:.0f} clk/step;  near-tie softmax visits (row-steps of this warp): {s[27]}")
     sys.exit(0)
 if gemm in ("tc4", "tc4s", "tc4x"):
     names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
