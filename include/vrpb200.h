@@ -171,6 +171,11 @@ int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t
 int vrpb200_reward_min_trucks(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
                               float n_nodes, float* d_reward, void* stream);
 
+/* reward_func with a depot, UPS VRPTW form (UPS/vrptw_ups_utils.py:387-419): 100 x returns to the depot (a stay counts
+ * once, column 0 is compared) + closed route length over x, y.  d_actions [T, R, A], d_depot [R, A] -> d_reward [R]. */
+int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
+                                  float* d_reward, void* stream);
+
 /* Measured throughput of one SM pipe on the handle's device, for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: kind 0 = MUFU (ex2/rcp, ops/s), 1 = FP32 FMA (FMA/s, 2 flop each).
  * Runs a register-only micro-benchmark on every SM for ~`iters` x 4096 ops per thread.  Synchronous. */

@@ -283,8 +283,10 @@ __global__ void reward_kernel(const float* __restrict__ actions, long long T, lo
 // ---- reward_func with a depot ("min_trucks": VRPTW/vrptw_utils.py:384-395, 410-412; VRP/vrp_utils.py:275-285, 302-304):
 // 70/n_nodes x returns to the depot (a stay counts once; the test compares column 0 only, as the reference does)
 // + 30 x route length (first XY columns) / sum over steps of the distance to the depot over ALL A action columns
+// ups != 0: the UPS VRPTW form (UPS/vrptw_ups_utils.py:387-419): 100 x returns to the depot + route length (its great-circle
+// normaliser is computed by the reference but not used in the reward)
 __global__ void reward_min_trucks_kernel(const float* __restrict__ actions, const float* __restrict__ depot, long long T, long long R,
-                                         int A, int XY, float inv_n_nodes, float* reward) {
+                                         int A, int XY, float inv_n_nodes, int ups, float* reward) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     const float* dp = depot + r * A;
@@ -313,7 +315,8 @@ __global__ void reward_min_trucks_kernel(const float* __restrict__ actions, cons
         route = __fadd_rn(route, __fsqrt_rn(s));
         maxlen = __fadd_rn(maxlen, __fsqrt_rn(m));
     }
-    reward[r] = __fadd_rn(__fmul_rn(70.0f, __fmul_rn(inv_n_nodes, visits)), __fmul_rn(30.0f, __fdiv_rn(route, maxlen)));
+    reward[r] = ups ? __fadd_rn(__fmul_rn(100.0f, visits), route)
+                    : __fadd_rn(__fmul_rn(70.0f, __fmul_rn(inv_n_nodes, visits)), __fmul_rn(30.0f, __fdiv_rn(route, maxlen)));
 }
 
 // ---- pipe micro-benchmarks: the roofline denominators MEASURED_PEAKS.json does not hold -----------------

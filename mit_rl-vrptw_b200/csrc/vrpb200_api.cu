@@ -682,7 +682,17 @@ int vrpb200_reward_min_trucks(vrpb200_handle* h, const float* d_actions, const f
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int XY = A > 2 ? 2 : A;   // VRPTW slices the actions to x, y for the route length; VRP actions are x, y already
     reward_min_trucks_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, d_depot, T, R, A, XY,
-                                                                                           (float)(1.0 / (double)n_nodes), d_reward);
+                                                                                           (float)(1.0 / (double)n_nodes), 0, d_reward);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
+                                  float* d_reward, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_actions || !d_depot || !d_reward || T < 1 || R < 1 || A < 2 || A > 4) return fail(h, VRPB200_E_ARG, "reward_min_trucks_ups: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    reward_min_trucks_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, d_depot, T, R, A, 2, 0.0f, 1, d_reward);
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }

@@ -423,7 +423,7 @@ class VRPTWEnv(_EnvBase):
     TW = True
 
 
-def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
+def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None, _ups=False):
     """reward_func of VRPTW/vrptw_utils.py:361-414 and VRP/vrp_utils.py:257-307.
     sample_solution: list of T tensors [R, A] or a tensor [T, R, A].
     depot=None: closed tour length over x, y (:397-414).  depot [R, A]: the min_trucks objective (:384-395, 410-412),
@@ -436,7 +436,13 @@ def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
     if depot is None:
         return eng.reward(sol)
     dep = depot.to(device="cuda", dtype=torch.float32).contiguous()
-    return eng.reward_min_trucks(sol, dep, float(n_nodes))
+    return eng.reward_min_trucks(sol, dep, float(n_nodes), ups=_ups)
+
+
+def reward_func_vrptw_ups(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
+    """reward_func of UPS/vrptw_ups_utils.py:362-422: the tour length, or with a depot 100 x returns to the depot + the
+    tour length (the great-circle normaliser of :399-402 is computed by the reference but does not enter the reward)."""
+    return reward_func(sample_solution, decode_len, n_nodes, depot, _ups=True)
 
 
 class DataGenerator(object):
@@ -479,7 +485,8 @@ def load_task_specific_components(task, ups=False):
     if task == 'vrp':
         return (DataGenerator, VRPEnv, reward_func, AttentionVRP_UPS_Actor if ups else AttentionVRPActor, AttentionVRPCritic)
     if task == 'vrptw':
-        return (DataGenerator, VRPTWEnv, reward_func, AttentionVRPTW_UPS_Actor if ups else AttentionVRPTWActor, AttentionVRPTWCritic)
+        return (DataGenerator, VRPTWEnv, reward_func_vrptw_ups if ups else reward_func,
+                AttentionVRPTW_UPS_Actor if ups else AttentionVRPTWActor, AttentionVRPTWCritic)
     raise Exception('Task is not implemented')
 
 

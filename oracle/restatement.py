@@ -294,6 +294,23 @@ def reward_func_min_trucks(actions: Sequence[np.ndarray], depot: np.ndarray, dec
     return dt(70.0) * (dt(1.0 / n_nodes) * visits) + dt(30.0) * (route / max_lens)
 
 
+def reward_func_min_trucks_ups(actions: Sequence[np.ndarray], depot: np.ndarray) -> np.ndarray:
+    """``reward_func`` with a depot of the UPS VRPTW twin (UPS/vrptw_ups_utils.py:387-419): 100 x (returns to the depot,
+    consecutive stays counted once, column 0 compared) + the closed route length over x, y.  The great-circle distance to the
+    depot (:399-402) is computed by the reference but never used in the returned value."""
+    dt = actions[0].dtype.type
+    counter = np.zeros_like(depot)[:, 0]
+    visits = (actions[0] == depot).astype(dt)[:, 0]
+    for i in range(1, len(actions)):
+        interm = (actions[i] == depot).astype(dt)[:, 0]
+        counter = counter * interm + interm
+        visits = visits + interm * (counter < 1.5).astype(dt)
+    sol = np.stack(actions, 0)[:, :, :2]
+    tilted = np.concatenate([sol[-1:], sol[:-1]], 0)
+    route = np.sum(np.power(np.sum(np.power(tilted - sol, dt(2)), 2), dt(0.5)), 0)
+    return dt(100.0) * visits + route
+
+
 # --------------------------------------------------------------------------- #
 # model pieces
 # --------------------------------------------------------------------------- #

@@ -21,9 +21,10 @@ import tensorflow as tf  # noqa: E402  (the shim)
 from oracle import restatement as O  # noqa: E402
 
 
-def make(task, n_cust, R, T, seed):
+def make(task, n_cust, R, T, seed, ups=False):
     from VRP.vrp_utils import reward_func as rf_vrp
     from VRPTW.vrptw_utils import reward_func as rf_tw
+    from UPS.vrptw_ups_utils import reward_func as rf_tw_ups
     rnd = np.random.RandomState(seed)
     data = O.create_dataset(f"{task}{n_cust}", R, seed=seed).astype(np.float32)
     pnt = data[:, :, :-1]                                    # input_pnt: x, y (, b_tw, e_tw)
@@ -34,7 +35,7 @@ def make(task, n_cust, R, T, seed):
     actions = [pnt[np.arange(R), idx[t]] for t in range(T)]
     depot = pnt[:, n_cust]
     tf.reset_shim()
-    rf = rf_tw if task == "vrptw" else rf_vrp
+    rf = rf_tw_ups if ups else (rf_tw if task == "vrptw" else rf_vrp)
     out = rf([tf.constant(a) for a in actions], T, float(N), tf.constant(depot))
     ref = tf.Session().run(out)
     return dict(actions=np.stack(actions), depot=depot, reward=np.asarray(ref, np.float32), T=T, n_nodes=N, idx=idx)
@@ -45,5 +46,7 @@ if __name__ == "__main__":
     for task, n_cust, R, T, seed in (("vrp", 10, 64, 20, 101), ("vrptw", 20, 64, 40, 102)):
         for k, v in make(task, n_cust, R, T, seed).items():
             fx[f"{task}_{k}"] = v
+    for k, v in make("vrptw", 20, 64, 40, 103, ups=True).items():    # the UPS VRPTW form: 100 x visits + route length
+        fx[f"vrptwups_{k}"] = v
     np.savez_compressed(os.path.join(HERE, "reward_min_trucks.npz"), **fx)
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in fx.items()})

@@ -189,6 +189,23 @@ def test_min_trucks_reward_kernel_matches_reference_fixture(task):
 
 
 @pytest.mark.gpu
+def test_min_trucks_reward_ups_kernel_matches_reference_fixture():
+    """load_task_specific_components('vrptw', ups=True) hands out the UPS reward (UPS/vrptw_ups_utils.py:387-419:
+    100 x returns to the depot + route length) -> vrpb200_reward_min_trucks_ups against the reference's own output."""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    pkg = load_pkg()
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    rf = pkg.host.load_task_specific_components("vrptw", True)[2]
+    acts = [torch.from_numpy(a).cuda() for a in fx["vrptwups_actions"]]
+    dep = torch.from_numpy(fx["vrptwups_depot"]).cuda()
+    r = rf(acts, int(fx["vrptwups_T"]), float(fx["vrptwups_n_nodes"]), dep)
+    np.testing.assert_allclose(r.cpu().numpy(), fx["vrptwups_reward"], rtol=1e-5)
+    np.testing.assert_allclose(rf(acts).cpu().numpy(), pkg.host.reward_func(acts).cpu().numpy(), rtol=0)   # no depot: tour length
+
+
+@pytest.mark.gpu
 def test_evaluate_single_writes_reference_result_files(tmp_path):
     """evaluate_single (attention_agent.py:336-413) + _output_results (:416-471): one route per problem in the result file,
     each route a valid VRPTW route over the instance's nodes starting and ending at the depot."""

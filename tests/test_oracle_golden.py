@@ -74,6 +74,17 @@ def test_min_trucks_reward_matches_reference_code(task, tw):
     np.testing.assert_array_equal(r, fx[f"{task}_reward"])
 
 
+def test_min_trucks_reward_ups_form_matches_reference_code():
+    """reward_func with a depot of the UPS VRPTW twin (UPS/vrptw_ups_utils.py:387-419, 100 x visits + route length): the
+    oracle against the output of the reference's own function, bit for bit."""
+    import os
+    from tests.helpers import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    r = O.reward_func_min_trucks_ups([a for a in fx["vrptwups_actions"]], fx["vrptwups_depot"])
+    np.testing.assert_array_equal(r, fx["vrptwups_reward"])
+    assert (r >= 100.0).all()        # every route starts at ... or at least returns once to the depot in these fixtures
+
+
 def test_min_trucks_reward_known_answer():
     """Hand-computed.  Depot (0,0); tour depot, depot, (3,4), depot, (1,1).  The reference's counter starts at 0 whatever
     step 0 is, so the stay at steps 0-1 counts twice (1 for step 0, 1 for step 1 with counter 1 < 1.5), the return at
