@@ -39,6 +39,11 @@ extern "C" {
 #define VRPB200_TASK_VRP 0      /* input_dim 3: x, y, demand            (VRP/vrp_utils.py) */
 #define VRPB200_TASK_VRPTW 1    /* input_dim 5: x, y, b_tw, e_tw, demand (VRPTW/vrptw_utils.py, UPS twin) */
 
+#define VRPB200_PHYSICS_EUCLID 0  /* travel time = Euclidean distance (VRP, VRPTW and UPS Env) */
+#define VRPB200_PHYSICS_UPS_OLD 1 /* UPS_old/vrptw_ups_utils.py:321-361, 416-424: x, y = latitude, longitude in radians;
+                                     equirectangular km x (100/13 * 1.2) clicks per km, 1.5 clicks of service per package;
+                                     the tour length (reward_func) is in km.  VRPTW only. */
+
 #define VRPB200_GREEDY 0        /* model/attention_agent.py:146-147 */
 #define VRPB200_STOCHASTIC 1    /* model/attention_agent.py:148-167 */
 #define VRPB200_BEAM 2          /* model/attention_agent.py:169-205 */
@@ -71,6 +76,7 @@ typedef struct vrpb200_config {
     float capacity;
     float tanh_exploration;  /* C */
     float forget_bias;       /* BasicLSTMCell forget_bias, shared/decode_step.py:175 */
+    int32_t physics;         /* VRPB200_PHYSICS_*: Env.step / mask / reward_func arithmetic (Env, env_step, reward, rollout) */
 } vrpb200_config;
 
 typedef struct vrpb200_handle vrpb200_handle;

@@ -26,7 +26,7 @@ class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "task", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
         "use_tanh", "mask_glimpses", "mask_pointer", "rows_per_cta", "gemm_path")] + [
-        ("capacity", C.c_float), ("tanh_exploration", C.c_float), ("forget_bias", C.c_float)]
+        ("capacity", C.c_float), ("tanh_exploration", C.c_float), ("forget_bias", C.c_float), ("physics", C.c_int32)]
 
 
 class Trace(C.Structure):

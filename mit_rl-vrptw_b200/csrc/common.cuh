@@ -40,6 +40,10 @@ struct AttWeights {
     const float* v;    // [128]
     const float* Au;   // [4][128]  W_emb . W_ref (unscaled, glimpse read-out)
     const float* ce;   // [128]     b_emb . W_ref + b_ref
+    // glimpse modules only: the query of the NEXT module as a function of the glimpse read-out.  hy = sum_n p[n] e[n,:] =
+    // pf . Au + ce with pf = sum_n p[n] feat[n], so  hy . W_q' + b'  =  pf . Mq + cq
+    const float* Mq;   // [4][128]  Au . W_q(next module)
+    const float* cq;   // [128]     ce . W_q(next module) + bq(next module)   (bq = every constant of that module)
 };
 
 struct RolloutArgs {
@@ -79,6 +83,12 @@ struct RolloutArgs {
     const float4* feat4;     // rollout4: [B, N] (x, y, b_tw, e_tw) re-packed copy of the node features (repack_features_kernel)
     float sumv;              // rollout4: sum_h v_h of the pointer attention
     float vm2[128];          // rollout4: -2 v_h (read as constant-bank operands)
+    // FP32-pipe kernel only (the tensor-core kernels are not launched with these set):
+    const AttWeights* gatt;  // [n_glimpses] glimpse modules (device array), shared/decode_step.py:218-227
+    const float* q_Wq;       // W_q / bias of the module that takes the LSTM output as its query (glimpse 0, else the pointer)
+    const float* q_bq;
+    int n_glimpses, mask_glimpses;
+    int physics;             // 0: VRP / VRPTW / UPS Env (Euclidean travel time); 1: UPS_old/vrptw_ups_utils.py:321-361
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -170,6 +180,23 @@ VRP_DEVINL float dist_rn(float ax, float ay, float bx, float by) {
     return __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
 }
 
+// UPS_old/vrptw_ups_utils.py:321-322, 359-360, 421-423: x = latitude, y = longitude (radians);
+// d = 6371 * sqrt(square((by - ay) * cos(0.5 * (bx + ax))) + square(bx - ax)) km (the same value whichever point is "a":
+// the differences are squared and the sum is commutative); travel time = (100/13 * 1.2) * d clicks, 1.5 clicks per package.
+constexpr float kGeoRadius = 6371.0f;
+constexpr float kGeoClicksPerKm = (float)((100.0 / 13.0) * 1.2);
+constexpr float kGeoService = 1.5f;
+VRP_DEVINL float geo_km_rn(float ax, float ay, float bx, float by) {
+    const float interm = __fmul_rn(__fsub_rn(by, ay), cosf(__fmul_rn(0.5f, __fadd_rn(bx, ax))));
+    const float dx = __fsub_rn(bx, ax);
+    return __fmul_rn(kGeoRadius, __fsqrt_rn(__fadd_rn(__fmul_rn(interm, interm), __fmul_rn(dx, dx))));
+}
+// length of a move (what reward_func adds up) and its travel time, by Env physics
+VRP_DEVINL float move_len(int physics, float ax, float ay, float bx, float by) {
+    return physics ? geo_km_rn(ax, ay, bx, by) : dist_rn(ax, ay, bx, by);
+}
+VRP_DEVINL float travel_time(int physics, float len) { return physics ? __fmul_rn(kGeoClicksPerKm, len) : len; }
+
 VRP_DEVINL float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
@@ -214,10 +241,10 @@ VRP_DEVINL float counter_uniform(unsigned long long seed, unsigned t, unsigned l
 // Env mask of one node after a step (VRPTW/vrptw_utils.py:328-348, VRP/vrp_utils.py:228-247), as a count 0..3.
 template <bool TW>
 VRP_DEVINL int node_mask(int n, int n_cust, float dem_n, float load, float time, float px, float py, float nx,
-                         float ny, float e_tw, float dep, float sumdem) {
+                         float ny, float e_tw, float dep, float sumdem, int physics = 0) {
     if (n == n_cust) return (sumdem > 0.0f && dep != 0.0f) ? 1 : 0;
     int m = (dem_n == 0.0f) + (load == 0.0f);
-    if (TW) m += (__fadd_rn(time, dist_rn(px, py, nx, ny)) > e_tw);
+    if (TW) m += (__fadd_rn(time, travel_time(physics, move_len(physics, px, py, nx, ny))) > e_tw);
     return m;
 }
 

@@ -9,6 +9,9 @@
 //            (vrptw_attention.py:77, SURVEY App. C collapse), mask (decode_step.py:231-232),
 //            log_softmax/exp (decode_step.py:125-126), selection (attention_agent.py:146-167),
 //            Env.step (VRPTW/vrptw_utils.py:254-358), tour-length accumulation (vrptw_utils.py:397-414).
+//            Glimpses (shared/decode_step.py:218-227) run inside the same per-row pass: scores of the glimpse module,
+//            softmax, read-out hy = sum_n p[n] e[n,:] collapsed to pf = sum_n p[n] feat[n] (rank D-1), and
+//            the next module's query pf . Mq + cq - no second GEMM, no extra launch.  UPS_old physics: a.physics.
 // Node features, demand, masks and the LSTM state stay in shared memory / registers for the whole
 // rollout; HBM sees the instance once on the way in and T int32 indices + one cost on the way out.
 // The weight matrices of phases A and B (387 KB fp32) do not fit next to the instances, so they are
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
 
     // ownership: (rows 8rg..8rg+7) x (units u0, u0+1); the LSTM cell state c lives in registers for all T steps
     const int u0 = uh * 64 + 2 * lane;
-    const float2 bq2 = __ldg(reinterpret_cast<const float2*>(a.att.bq + u0));
+    const float2 bq2 = __ldg(reinterpret_cast<const float2*>(a.q_bq + u0));
     constexpr int NCST = 16;
     float cst[NCST];
 #pragma unroll
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
                 for (int s = 0; s < kStages; ++s) {
                     const uint32_t st = (slabcnt + s) % kStages;
                     mbar_expect_tx(bar0 + 8 * st, kSlabBytes);
-                    bulk_g2s(ring_u32 + st * kSlabBytes, a.att.Wq + (size_t)s * kSlabFloats, kSlabBytes, bar0 + 8 * st);
+                    bulk_g2s(ring_u32 + st * kSlabBytes, a.q_Wq + (size_t)s * kSlabFloats, kSlabBytes, bar0 + 8 * st);
                 }
             }
             // BasicLSTMCell (TF-1 rnn_cell_impl): c' = c*sig(f+fb) + sig(i)*tanh(j); h' = tanh(c')*sig(o)
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
                 __syncthreads();
                 if (tid == 0 && s + kStages < kQSlabs) {
                     mbar_expect_tx(bar0 + 8 * st, kSlabBytes);
-                    bulk_g2s(ring_u32 + st * kSlabBytes, a.att.Wq + (size_t)(s + kStages) * kSlabFloats, kSlabBytes, bar0 + 8 * st);
+                    bulk_g2s(ring_u32 + st * kSlabBytes, a.q_Wq + (size_t)(s + kStages) * kSlabFloats, kSlabBytes, bar0 + 8 * st);
                 }
                 ++slabcnt;
             }
@@ -248,23 +251,25 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
         VRP_CLK(3);
 
         // ================= phase C: one warp per row ====================================================
-        // pointer-attention constants of this lane's 4 hidden units h = 4*lane .. 4*lane+3
+        // attention constants of this lane's 4 hidden units h = 4*lane .. 4*lane+3, per module (glimpses, then the pointer)
         float cA[FD][4], cgd[4], cv[4], cgl[4], cgt[4];
+        auto load_att = [&](const AttWeights& w) {
 #pragma unroll
-        for (int k = 0; k < FD; ++k) {
-            const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.att.A + k * kH) + lane);
-            cA[k][0] = t4.x; cA[k][1] = t4.y; cA[k][2] = t4.z; cA[k][3] = t4.w;
-        }
-        {
-            float4 t4 = __ldg(reinterpret_cast<const float4*>(a.att.gd) + lane);
+            for (int k = 0; k < FD; ++k) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(w.A + k * kH) + lane);
+                cA[k][0] = t4.x; cA[k][1] = t4.y; cA[k][2] = t4.z; cA[k][3] = t4.w;
+            }
+            float4 t4 = __ldg(reinterpret_cast<const float4*>(w.gd) + lane);
             cgd[0] = t4.x; cgd[1] = t4.y; cgd[2] = t4.z; cgd[3] = t4.w;
-            t4 = __ldg(reinterpret_cast<const float4*>(a.att.v) + lane);
+            t4 = __ldg(reinterpret_cast<const float4*>(w.v) + lane);
             cv[0] = t4.x; cv[1] = t4.y; cv[2] = t4.z; cv[3] = t4.w;
-            t4 = __ldg(reinterpret_cast<const float4*>(a.att.gl) + lane);
+            t4 = __ldg(reinterpret_cast<const float4*>(w.gl) + lane);
             cgl[0] = t4.x; cgl[1] = t4.y; cgl[2] = t4.z; cgl[3] = t4.w;
-            t4 = __ldg(reinterpret_cast<const float4*>(a.att.gt) + lane);
+            t4 = __ldg(reinterpret_cast<const float4*>(w.gt) + lane);
             cgt[0] = t4.x; cgt[1] = t4.y; cgt[2] = t4.z; cgt[3] = t4.w;
-        }
+        };
+        const int G = a.n_glimpses;
+        if (G == 0) load_att(a.att);
         int warp_done = 1;
         for (;;) {   // rows are handed out dynamically: their cost varies with the number of un-masked nodes
             int lr = 0;
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
                 mcnt[j] = (n < N) ? mk[n] : 255;
                 nun += __popc(__ballot_sync(kFull, mcnt[j] == 0));
             }
-            const bool all_nodes = a.full || nun == 0 || !a.mask_pointer;
+            const bool all_nodes = a.full || nun == 0 || !a.mask_pointer || (G > 0 && !a.mask_glimpses);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int n = lane + 32 * j;
@@ -312,50 +317,99 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
             if (lane < npad - nact) list[nact + lane] = 0;   // padding entries: node 0, result ignored
             __syncwarp();
 
-            // --- u[n] = sum_h v_h tanh(q_h + e[n,h] + d[n,h] + ld[n,h] + t_h), all pre-scaled by 2 log2 e
-            float base[4];
+            // --- u[n] = sum_h v_h tanh(q_h + e[n,h] + d[n,h] + ld[n,h] + t_h), all pre-scaled by 2 log2 e; once per glimpse
+            //     module (query = LSTM output for the first one) and once for the pointer
+            float qv[4];
             {
                 const float4 q4 = *reinterpret_cast<const float4*>(qq + lr * kH + 4 * lane);
-                const float qv[4] = {q4.x, q4.y, q4.z, q4.w};
+                qv[0] = q4.x; qv[1] = q4.y; qv[2] = q4.z; qv[3] = q4.w;
+            }
+#pragma unroll 1
+            for (int mod = 0; mod <= G; ++mod) {
+                if (G > 0) load_att(mod < G ? a.gatt[mod] : a.att);
+                float base[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     float s = fmaf(load, cgl[j], qv[j]);
                     if (TW) s = fmaf(time, cgt[j], s);
                     base[j] = s * kTwoLog2e;
                 }
-            }
-            for (int c0 = 0; c0 < npad; c0 += 8) {
-                const uint2 ids = *reinterpret_cast<const uint2*>(list + c0);
-                float part[8];
+                for (int c0 = 0; c0 < npad; c0 += 8) {
+                    const uint2 ids = *reinterpret_cast<const uint2*>(list + c0);
+                    float part[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int n = ((e < 4 ? ids.x : ids.y) >> (8 * (e & 3))) & 0xff;
-                    float f[FD];
-                    if (TW) {
-                        const float4 f4 = *reinterpret_cast<const float4*>(frow + n * 4);
-                        f[0] = f4.x; f[1] = f4.y; f[FD - 2] = f4.z; f[FD - 1] = f4.w;
-                    } else {
-                        const float2 f2 = *reinterpret_cast<const float2*>(frow + n * 2);
-                        f[0] = f2.x; f[1] = f2.y;
+                    for (int e = 0; e < 8; ++e) {
+                        const int n = ((e < 4 ? ids.x : ids.y) >> (8 * (e & 3))) & 0xff;
+                        float f[FD];
+                        if (TW) {
+                            const float4 f4 = *reinterpret_cast<const float4*>(frow + n * 4);
+                            f[0] = f4.x; f[1] = f4.y; f[FD - 2] = f4.z; f[FD - 1] = f4.w;
+                        } else {
+                            const float2 f2 = *reinterpret_cast<const float2*>(frow + n * 2);
+                            f[0] = f2.x; f[1] = f2.y;
+                        }
+                        const float dn = drow[n];
+                        float p = 0.0f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float x = base[j];
+#pragma unroll
+                            for (int k = 0; k < FD; ++k) x = fmaf(f[k], cA[k][j], x);
+                            x = fmaf(dn, cgd[j], x);
+                            const float rr = rcp_approx(1.0f + ex2_approx(x));
+                            p = fmaf(cv[j], fmaf(-2.0f, rr, 1.0f), p);
+                        }
+                        part[e] = p;
                     }
-                    const float dn = drow[n];
-                    float p = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float x = base[j];
-#pragma unroll
-                        for (int k = 0; k < FD; ++k) x = fmaf(f[k], cA[k][j], x);
-                        x = fmaf(dn, cgd[j], x);
-                        const float rr = rcp_approx(1.0f + ex2_approx(x));
-                        p = fmaf(cv[j], fmaf(-2.0f, rr, 1.0f), p);
-                    }
-                    part[e] = p;
+                    const float tot = reduce8(part, lane);
+                    const int pos = c0 + (lane >> 2);
+                    if ((lane & 3) == 0 && pos < nact) ulog[list[pos]] = tot;
                 }
-                const float tot = reduce8(part, lane);
-                const int pos = c0 + (lane >> 2);
-                if ((lane & 3) == 0 && pos < nact) ulog[list[pos]] = tot;
+                __syncwarp();
+                if (mod == G) break;
+                // --- glimpse (shared/decode_step.py:218-227): prob = softmax(logit - 1e5 mask); hy = prob . e  ->  the next
+                //     module's query q' = hy . W_q' + b' = pf . Mq + cq with pf = sum_n prob[n] feat[n]
+                float gl_[4], gmx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = lane + 32 * j;
+                    float u = -INFINITY;
+                    if ((actbits[j] >> lane) & 1) {
+                        u = ulog[n];
+                        if (a.mask_glimpses) u = __fsub_rn(u, __fmul_rn(kBig, (float)mcnt[j]));
+                    }
+                    gl_[j] = u;
+                    gmx = fmaxf(gmx, u);
+                }
+                gmx = warp_max(gmx);
+                float gse = 0.0f, pf[FD];
+#pragma unroll
+                for (int k = 0; k < FD; ++k) pf[k] = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int n = lane + 32 * j;
+                    const float ev = (gl_[j] == -INFINITY) ? 0.0f : expf(gl_[j] - gmx);
+                    gse += ev;
+                    if (ev != 0.0f) {
+#pragma unroll
+                        for (int k = 0; k < FD; ++k) pf[k] = fmaf(ev, frow[n * FD + k], pf[k]);
+                    }
+                }
+                gse = warp_sum(gse);
+                const float ginv = 1.0f / gse;
+#pragma unroll
+                for (int k = 0; k < FD; ++k) pf[k] = warp_sum(pf[k]) * ginv;
+                const AttWeights& gw = a.gatt[mod];
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(gw.cq) + lane);
+                qv[0] = c4.x; qv[1] = c4.y; qv[2] = c4.z; qv[3] = c4.w;
+#pragma unroll
+                for (int k = 0; k < FD; ++k) {
+                    const float4 m4 = __ldg(reinterpret_cast<const float4*>(gw.Mq + k * kH) + lane);
+                    qv[0] = fmaf(pf[k], m4.x, qv[0]); qv[1] = fmaf(pf[k], m4.y, qv[1]);
+                    qv[2] = fmaf(pf[k], m4.z, qv[2]); qv[3] = fmaf(pf[k], m4.w, qv[3]);
+                }
+                __syncwarp();
             }
-            __syncwarp();
 
             // --- mask, log_softmax, exp (shared/decode_step.py:231-232, 125-126)
             float lg[4], pr[4];
@@ -449,9 +503,12 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
             __syncwarp();
             const float d_sat = fminf(d_idx, load);
             float nload = __fsub_rn(load, d_sat);
-            const float ts = dist_rn(px, py, sx, sy);
+            const float ts = move_len(a.physics, px, py, sx, sy);   // what reward_func adds up; its travel time below
             float ntime = 0.0f;
-            if (TW) ntime = fmaxf(__fadd_rn(time, ts), fsel[2]);
+            if (TW) {
+                ntime = fmaxf(__fadd_rn(time, travel_time(a.physics, ts)), fsel[2]);
+                if (a.physics) ntime = __fadd_rn(ntime, __fmul_rn(kGeoService, d_sat));   // UPS_old/vrptw_ups_utils.py:332-333
+            }
             const float dep = (idx == n_cust) ? 1.0f : 0.0f;
             nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, a.capacity));
             if (TW) ntime = __fmul_rn(ntime, 1.0f - dep);
@@ -475,7 +532,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
                         nx = f4.x; ny = f4.y; ne = f4.w;
                     }
                     maskb[lr * NP + n] =
-                        (unsigned char)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem);
+                        (unsigned char)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, nx, ny, ne, dep, sumdem, a.physics);
                 }
             }
             const int done_now = (!a.full && a.mask_pointer && idx == n_cust && sumdem == 0.0f) ? 1 : 0;
@@ -511,7 +568,7 @@ __global__ void __launch_bounds__(RB * 8, 1) rollout_ffma_kernel(const RolloutAr
             if (a.logprob_out) a.logprob_out[(long long)tt * R + row] = 0.0f;
         }
         const float* rs = rowst + lr * kRowState;
-        if (lane == 0) a.cost_out[row] = __fadd_rn(rs[4], dist_rn(rs[2], rs[3], rs[5], rs[6]));   // + |a_0 - a_{T-1}|
+        if (lane == 0) a.cost_out[row] = __fadd_rn(rs[4], move_len(a.physics, rs[2], rs[3], rs[5], rs[6]));   // + |a_0 - a_{T-1}|
         for (int n = lane; n < N; n += 32) {
             if (a.fin_demand) a.fin_demand[row * N + n] = dem[lr * NP + n];
             if (a.fin_mask) a.fin_mask[row * N + n] = (float)maskb[lr * NP + n];

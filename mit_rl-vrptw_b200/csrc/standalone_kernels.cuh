@@ -37,7 +37,7 @@ __global__ void env_step_kernel(const float* __restrict__ input, long long B, in
                                 const long long* __restrict__ idx, const long long* __restrict__ parent,
                                 const float* demand_in, const float* load_in, const float* time_in,
                                 const float* prev_in, float* demand, float* load, float* time, float* mask,
-                                float* prev_xy, float* d_sat_out) {
+                                float* prev_xy, float* d_sat_out, int physics) {
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= B * W) return;
@@ -55,8 +55,9 @@ __global__ void env_step_kernel(const float* __restrict__ input, long long B, in
     if (TW) {
         px = prev_in[src * 2 + 0];
         py = prev_in[src * 2 + 1];
-        const float ts = dist_rn(px, py, sx, sy);
+        const float ts = travel_time(physics, move_len(physics, px, py, sx, sy));
         ntime = fmaxf(__fadd_rn(time_in[src], ts), in[id * D + 2]);
+        if (physics) ntime = __fadd_rn(ntime, __fmul_rn(kGeoService, d_sat));   // UPS_old/vrptw_ups_utils.py:332-333
     }
     const float dep = (id == n_cust) ? 1.0f : 0.0f;
     nload = __fadd_rn(__fmul_rn(nload, 1.0f - dep), __fmul_rn(dep, capacity));
@@ -82,7 +83,7 @@ __global__ void env_step_kernel(const float* __restrict__ input, long long B, in
             float e_tw = 0.f;
             if (TW) e_tw = in[n * D + 3];
             mask[row * N + n] = (float)node_mask<TW>(n, n_cust, dn[j], nload, ntime, sx, sy, in[n * D + 0],
-                                                     in[n * D + 1], e_tw, dep, sumdem);
+                                                     in[n * D + 1], e_tw, dep, sumdem, physics);
         }
     }
     if (lane == 0) {
@@ -266,14 +267,15 @@ __global__ void decode_step_kernel(RawModel mdl, int N, int E, const float* dec_
 }
 
 // ---- reward_func, depot=None branch (VRPTW/vrptw_utils.py:397-414, VRP/vrp_utils.py:293-307) ---------
-__global__ void reward_kernel(const float* __restrict__ actions, long long T, long long R, int A, float* cost) {
+// physics 1: the km length of UPS_old/vrptw_ups_utils.py:416-424
+__global__ void reward_kernel(const float* __restrict__ actions, long long T, long long R, int A, float* cost, int physics) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     float px = actions[((T - 1) * R + r) * A + 0], py = actions[((T - 1) * R + r) * A + 1];
     float s = 0.0f;
     for (long long t = 0; t < T; ++t) {
         const float x = actions[(t * R + r) * A + 0], y = actions[(t * R + r) * A + 1];
-        s = __fadd_rn(s, dist_rn(px, py, x, y));
+        s = __fadd_rn(s, move_len(physics, px, py, x, y));
         px = x;
         py = y;
     }

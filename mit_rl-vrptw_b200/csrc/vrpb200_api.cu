@@ -38,6 +38,7 @@ struct vrpb200_handle {
     const float *WgT3 = nullptr, *WxT = nullptr, *bgT = nullptr;
     const float* WqTc[8] = {nullptr};
     AttWeights att[8];
+    AttWeights* d_gatt = nullptr;   // device copy of att[0..n_glimpses-1]
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
     // staging of the *_host call: kChunks in-flight chunks, one stream each
@@ -129,6 +130,8 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
     if (c.gemm_path != 0 && c.gemm_path != 1 && c.gemm_path != 3 && c.gemm_path != 6 && c.gemm_path != 7)
         return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (default), 1 (FP32 pipe), 3 (rollout3), 6 (rollout4) or 7 (rollout5)");
+    if (c.physics != VRPB200_PHYSICS_EUCLID && c.physics != VRPB200_PHYSICS_UPS_OLD) return fail(nullptr, VRPB200_E_ARG, "physics must be 0 (Euclidean) or 1 (UPS_old)");
+    if (c.physics == VRPB200_PHYSICS_UPS_OLD && c.task != VRPB200_TASK_VRPTW) return fail(nullptr, VRPB200_E_ARG, "UPS_old physics is a VRPTW environment");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
         return fail(nullptr, VRPB200_E_ARG, "rows_per_cta must be 0, 16, 32, 48 or 64");
     int ndev = 0;
@@ -155,6 +158,7 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (!h) return VRPB200_OK;
     cudaSetDevice(h->device);
     if (h->d_blob) cudaFree(h->d_blob);
+    if (h->d_gatt) cudaFree(h->d_gatt);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
         if (h->dev_idx[i]) cudaFree(h->dev_idx[i]);
@@ -267,14 +271,15 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                     blob[oWxT + (cc * 4 + m) * H + unit] = cc < D1 ? (float)Wx[(size_t)cc * 4 * H + m * H + unit] : 0.0f;
             }
     }
-    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc; };
+    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc, Mq, cq; };
     std::vector<AttOff> ao(natt);
+    std::vector<std::vector<double>> Au_d(natt, std::vector<double>(4 * H, 0.0)), ce_d(natt, std::vector<double>(H, 0.0)), bq_d(natt, std::vector<double>(H, 0.0));
     for (int a = 0; a < natt; ++a) {
         const RawHost& r = rh[a];
         AttOff& o = ao[a];
         o.Wq = put(r.pq_k, (size_t)H * H);   // [k][unit] row-major == 4 slabs of 32 k-rows
         o.bq = reserve(H); o.A = reserve(4 * H); o.gd = reserve(H); o.gl = reserve(H); o.gt = reserve(H);
-        o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H);
+        o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H); o.Mq = reserve(4 * H); o.cq = reserve(H);
         o.WqTc = reserve((size_t)kV3UsesQ * kSlabFloats);
         for (int u = 0; u < kV3UsesQ; ++u)
             for (int kk = 0; kk < 2; ++kk)
@@ -304,12 +309,29 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                 if (cc < D1) for (int e2 = 0; e2 < E; ++e2) s += (double)emb_k[cc * E + e2] * r.pr_k[e2 * H + hh];
                 blob[o.Au + cc * H + hh] = (float)s;
                 blob[o.A + cc * H + hh] = (float)(s * (double)kTwoLog2e);
+                Au_d[a][cc * H + hh] = s;
             }
             blob[o.ce + hh] = (float)ce;
             blob[o.bq + hh] = (float)((double)r.pq_b[hh] + ce + cd + cld + ct);
+            ce_d[a][hh] = ce;
+            bq_d[a][hh] = (double)r.pq_b[hh] + ce + cd + cld + ct;
             blob[o.gd + hh] = (float)((gdv - gld) * (double)kTwoLog2e);
             blob[o.gl + hh] = (float)gld;
             blob[o.gt + hh] = (float)gtv;
+        }
+    }
+    // glimpse read-out folded into the next module's query: hy = pf . Au + ce, q' = hy . W_q' + b'
+    for (int a = 0; a + 1 < natt; ++a) {
+        const float* Wn = rh[a + 1].pq_k;   // [k][unit]
+        for (int hh = 0; hh < H; ++hh) {
+            double c0 = bq_d[a + 1][hh];
+            for (int k = 0; k < H; ++k) c0 += ce_d[a][k] * (double)Wn[(size_t)k * H + hh];
+            blob[ao[a].cq + hh] = (float)c0;
+            for (int cc = 0; cc < 4; ++cc) {
+                double m0 = 0;
+                for (int k = 0; k < H; ++k) m0 += Au_d[a][cc * H + k] * (double)Wn[(size_t)k * H + hh];
+                blob[ao[a].Mq + cc * H + hh] = (float)m0;
+            }
         }
     }
     // raw copies for the stand-alone (as-written) kernels
@@ -339,7 +361,7 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     h->WgT3 = d + oWgT3; h->WxT = d + oWxT; h->bgT = d + obgT;
     for (int a = 0; a < natt; ++a) {
         h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
-                               d + ao[a].v, d + ao[a].Au, d + ao[a].ce};
+                               d + ao[a].v, d + ao[a].Au, d + ao[a].ce, d + ao[a].Mq, d + ao[a].cq};
         h->WqTc[a] = d + ao[a].WqTc;
         const RawOff& o = ro[a];
         RawAtt& ra = h->raw.att[a];
@@ -355,6 +377,10 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         double sv = 0.0;
         for (int hh = 0; hh < H; ++hh) { h->vm2[hh] = -2.0f * r.v[hh]; sv += (double)r.v[hh]; }
         h->sumv = (float)sv;
+    }
+    if (c.n_glimpses > 0) {   // device array of the glimpse modules for the fused FP32-pipe kernel
+        if (!h->d_gatt) CUDA_TRY(h, cudaMalloc((void**)&h->d_gatt, sizeof(AttWeights) * 8));
+        CUDA_TRY(h, cudaMemcpy(h->d_gatt, h->att, sizeof(AttWeights) * c.n_glimpses, cudaMemcpyHostToDevice));
     }
     h->raw.lstm_k = d + o_lstm_k;
     h->raw.lstm_b = d + o_lstm_b;
@@ -380,6 +406,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     // VRPTW-100 sampling x 8192, rollout4 is 6 % faster on the 48-row blocks of large batches); beam search: rollout3
     const bool automatic = c.gemm_path == 0;
     int fam = automatic ? kFamV4 : c.gemm_path;
+    if (c.n_glimpses != 0 || c.physics != 0) fam = kFamFfma;   // the one fused kernel with glimpses / UPS_old physics
     if ((fam == kFamV4 || fam == kFamV5) && a.mode == 2) fam = kFamV3;
     int stages = 2;
     auto smem_of = [&](int rb) {
@@ -443,7 +470,8 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     if (mode == VRPB200_BEAM && (beam_width < 1 || beam_width > 64)) return fail(h, VRPB200_E_ARG, "beam_width outside [1,64]");
     if (mode == VRPB200_BEAM && beam_width > h->cfg.n_nodes)   // step 0 has n_nodes candidates: tf.nn.top_k(k > n) is an error in the reference too
         return fail(h, VRPB200_E_ARG, "beam_width %d exceeds n_nodes %d", beam_width, h->cfg.n_nodes);
-    if (h->cfg.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "n_glimpses > 0 is not implemented by the fused kernel yet (use decode_step)");
+    if ((h->cfg.n_glimpses != 0 || h->cfg.physics != 0) && mode == VRPB200_BEAM)
+        return fail(h, VRPB200_E_ARG, "beam search with glimpses or UPS_old physics is not fused (drive decode_step / env_step)");
     if (mode == VRPB200_STOCHASTIC && ((d_uniforms == nullptr) != (d_uniforms_retry == nullptr)))
         return fail(h, VRPB200_E_ARG, "pass both uniform buffers or neither");
     CUDA_TRY(h, cudaSetDevice(h->device));
@@ -468,7 +496,10 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.capacity = c.capacity; a.tanh_C = c.tanh_exploration; a.forget_bias = c.forget_bias;
     a.sumv = h->sumv;
     memcpy(a.vm2, h->vm2, sizeof a.vm2);
-    if ((c.gemm_path == 0 || c.gemm_path >= 6) && mode != VRPB200_BEAM) {   // rollout4 / rollout5 gather node features as aligned 16-byte records
+    a.gatt = h->d_gatt; a.n_glimpses = c.n_glimpses; a.mask_glimpses = c.mask_glimpses; a.physics = c.physics;
+    a.q_Wq = h->att[0].Wq; a.q_bq = h->att[0].bq;   // module 0 = first glimpse, or the pointer when there is none
+    const bool fp32_only = c.n_glimpses != 0 || c.physics != 0;   // glimpses and UPS_old physics live in the FP32-pipe kernel
+    if ((c.gemm_path == 0 || c.gemm_path >= 6) && mode != VRPB200_BEAM && !fp32_only) {   // rollout4 / rollout5 gather node features as aligned 16-byte records
         const int slot = h->ws_slot;
         const long long nn = (long long)B * c.n_nodes;
         int rc = ensure(h, &h->ws_feat4[slot], &h->ws_feat4_bytes[slot], (size_t)nn * sizeof(float4));
@@ -597,12 +628,12 @@ int vrpb200_env_step(vrpb200_handle* h, const float* d_input, int64_t B, int bea
         env_step_kernel<true><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
             d_input, B, beam_width, h->cfg.n_nodes, h->cfg.input_dim, h->cfg.capacity, (const long long*)d_idx,
             (const long long*)d_beam_parent, d_demand_in, d_load_in, d_time_in, d_prev_xy_in, d_demand, d_load, d_time,
-            d_mask, d_prev_xy, d_sat);
+            d_mask, d_prev_xy, d_sat, h->cfg.physics);
     else
         env_step_kernel<false><<<grid, wpb * 32, 0, (cudaStream_t)stream>>>(
             d_input, B, beam_width, h->cfg.n_nodes, h->cfg.input_dim, h->cfg.capacity, (const long long*)d_idx,
             (const long long*)d_beam_parent, d_demand_in, d_load_in, d_time_in, d_prev_xy_in, d_demand, d_load, d_time,
-            d_mask, d_prev_xy, d_sat);
+            d_mask, d_prev_xy, d_sat, 0);
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }
@@ -669,7 +700,7 @@ int vrpb200_reward(vrpb200_handle* h, const float* d_actions, int64_t T, int64_t
     if (!h) return VRPB200_E_ARG;
     if (!d_actions || !d_cost || T < 1 || R < 1 || A < 2) return fail(h, VRPB200_E_ARG, "reward: bad argument");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    reward_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, T, R, A, d_cost);
+    reward_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, T, R, A, d_cost, h->cfg.physics);
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }

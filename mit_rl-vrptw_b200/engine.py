@@ -28,7 +28,7 @@ def config_from_args(args: dict, rows_per_cta: int = 0, gemm_path: int = 0) -> C
         use_tanh=int(bool(args.get("use_tanh", False))), mask_glimpses=int(bool(args.get("mask_glimpses", True))),
         mask_pointer=int(bool(args.get("mask_pointer", True))), rows_per_cta=rows_per_cta, gemm_path=gemm_path,
         capacity=float(args["capacity"]), tanh_exploration=float(args.get("tanh_exploration", 10.0)),
-        forget_bias=float(args.get("forget_bias", 1.0)))
+        forget_bias=float(args.get("forget_bias", 1.0)), physics=int(bool(args.get("ups_old", False))))
 
 
 @dataclass

@@ -110,7 +110,7 @@ def _get_engine(args: dict, params, version_key, device: int = 0):
     from .engine import Engine
     key = (tuple(sorted((k, str(v)) for k, v in args.items() if k in (
         "task_name", "n_nodes", "n_cust", "input_dim", "embedding_dim", "hidden_dim", "decode_len", "n_glimpses",
-        "use_tanh", "mask_glimpses", "mask_pointer", "capacity", "tanh_exploration", "forget_bias"))), version_key, device)
+        "use_tanh", "mask_glimpses", "mask_pointer", "capacity", "tanh_exploration", "forget_bias", "ups_old"))), version_key, device)
     eng = _engine_cache.get(key)
     if eng is None:
         if len(_engine_cache) > 8:
@@ -349,6 +349,7 @@ StateVRPTW = collections.namedtuple("State", ("load", "time", "demand", "d_sat",
 
 class _EnvBase(object):
     TW = False
+    UPS_OLD = False
 
     def __init__(self, args):
         self.args = args
@@ -361,7 +362,7 @@ class _EnvBase(object):
         self.beam_width = 1
         eargs = dict(task_name="vrptw" if self.TW else "vrp", n_nodes=self.n_nodes, n_cust=self.n_cust,
                      input_dim=self.input_dim, embedding_dim=args.get('embedding_dim', 30), hidden_dim=128, decode_len=1,
-                     capacity=float(self.capacity))
+                     capacity=float(self.capacity), ups_old=bool(self.UPS_OLD))
         self._eargs = eargs
 
     # placeholder semantics: assign the batch, everything derived follows
@@ -423,6 +424,12 @@ class VRPTWEnv(_EnvBase):
     TW = True
 
 
+class VRPTWEnvUPSOld(VRPTWEnv):
+    """Env of UPS_old/vrptw_ups_utils.py:170-370: the VRPTW Env with x, y = latitude, longitude in radians, travel time
+    (100/13 * 1.2) x equirectangular km (:321-323, :359-361) and 1.5 clicks of service per package (:332-333)."""
+    UPS_OLD = True
+
+
 def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None, _ups=False):
     """reward_func of VRPTW/vrptw_utils.py:361-414 and VRP/vrp_utils.py:257-307.
     sample_solution: list of T tensors [R, A] or a tensor [T, R, A].
@@ -437,6 +444,19 @@ def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None, _ups=F
         return eng.reward(sol)
     dep = depot.to(device="cuda", dtype=torch.float32).contiguous()
     return eng.reward_min_trucks(sol, dep, float(n_nodes), ups=_ups)
+
+
+def reward_func_vrptw_ups_old(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
+    """reward_func of UPS_old/vrptw_ups_utils.py:372-430, depot=None branch: the closed tour length in km over the
+    equirectangular distance (:416-424).  Its depot form (70/n x depot visits + 30 x km / Euclidean normaliser) is not built."""
+    import torch
+    if depot is not None:
+        raise NotImplementedError("UPS_old reward_func with a depot (min_trucks) is not part of the built path")
+    sol = sample_solution if isinstance(sample_solution, torch.Tensor) else torch.stack(list(sample_solution), 0)
+    sol = sol.to(device="cuda", dtype=torch.float32).contiguous()
+    args = dict(task_name="vrptw", n_nodes=2, n_cust=1, input_dim=5, embedding_dim=1, hidden_dim=128, decode_len=1, capacity=1.0,
+                ups_old=True)
+    return _get_engine(args, lambda: _dummy_model_params(args), ("reward",)).reward(sol)
 
 
 def reward_func_vrptw_ups(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
@@ -478,6 +498,13 @@ class DataGenerator(object):
 
     def get_test_all(self):
         return self.test_data
+
+
+def load_ups_old_components():
+    """The UPS_old package (UPS_old/vrptw_ups_utils.py, UPS_old/vrptw_ups_attention.py): nothing in main.py selects it; its
+    Env physics and reward with the VRPTW actor (the actor file is identical to VRPTW/vrptw_attention.py).  Run the agent
+    with args['ups_old'] = True so that the fused rollout uses the same physics."""
+    return (DataGenerator, VRPTWEnvUPSOld, reward_func_vrptw_ups_old, AttentionVRPTWActor, AttentionVRPTWCritic)
 
 
 def load_task_specific_components(task, ups=False):
@@ -556,15 +583,17 @@ class RLAgent(object):
     def build_model(self, decode_type="greedy", uniforms=None, uniforms_retry=None, seed=0, want_probs=False,
                     backend="auto", want_logprobs=True):
         """attention_agent.py:84-272.  backend 'fused' = the persistent rollout kernel, 'stepwise' = the reference's
-        loop over RNNDecodeStep.step / Env.step on device state (beam search and glimpses take this route in this
-        round), 'auto' picks."""
+        loop over RNNDecodeStep.step / Env.step on device state (per-step probabilities, and beam search combined with
+        glimpses or UPS_old physics, take this route), 'auto' picks."""
         import torch
-        fused_ok = decode_type in ("greedy", "stochastic", "beam_search") and self.args['n_glimpses'] == 0 and not want_probs
+        special = self.args['n_glimpses'] != 0 or bool(self.args.get('ups_old'))   # fused in the FP32-pipe kernel, no beams
+        fused_ok = decode_type in ("greedy", "stochastic", "beam_search") and not want_probs and \
+            not (special and decode_type == "beam_search")
         if backend == "auto":
             backend = "fused" if fused_ok else "stepwise"
         if backend == "fused":
             if not fused_ok:
-                raise NotImplementedError("fused kernel: greedy / stochastic / beam search without glimpses")
+                raise NotImplementedError("fused kernel: greedy / stochastic (beam search without glimpses), no per-step probabilities")
             W = self.args['beam_width'] if decode_type == 'beam_search' else 1
             self.beam_width = W
             # the per-step log-probabilities are only computed on request: without them plain greedy decoding runs the

@@ -97,6 +97,35 @@ def create_dataset(task: str, n_problems: int, seed: int) -> np.ndarray:
     return np.concatenate([x, tw_begin, tw_end, d], axis=2)
 
 
+def create_dataset_ups_old(n_cust: int, n_problems: int, seed: int) -> np.ndarray:
+    """Synthetic instances in the UNITS of UPS_old/vrptw_ups_utils.py:44-71 (its lat/long Gaussian mixture is not shipped with
+    the reference): latitude, longitude in radians around the depot of :44 (42.3775 N, 71.0796 W), time windows in "clicks"
+    after the 892 shift (b in [0, 600), e = b + [100, 300) capped at 950), integer demand 1..9; depot [lat, lon, 0, 1000, 0]."""
+    rnd = np.random.RandomState(seed)
+    dep = np.array([42.3775 * np.pi / 180, -71.0796 * np.pi / 180, 0.0, 1000.0, 0.0])
+    lat = dep[0] + rnd.uniform(-0.12, 0.12, size=(n_problems, n_cust)) * np.pi / 180
+    lon = dep[1] + rnd.uniform(-0.16, 0.16, size=(n_problems, n_cust)) * np.pi / 180
+    b = rnd.uniform(0, 600, size=(n_problems, n_cust))
+    e = np.minimum(b + rnd.uniform(100, 300, size=(n_problems, n_cust)), 950.0)
+    d = rnd.randint(1, 10, size=(n_problems, n_cust)).astype(np.float64)
+    cust = np.stack([lat, lon, b, e, d], 2)
+    return np.concatenate([cust, np.tile(dep[None, None, :], [n_problems, 1, 1])], 1)
+
+
+# the constants of UPS_old/vrptw_ups_utils.py:321-333 as the float32 graph constants TF makes of the Python scalars
+UPS_OLD_RADIUS = 6371                  # km
+UPS_OLD_CLICKS_PER_KM = (100 / 13) * 1.2
+UPS_OLD_SERVICE = 1.5                  # clicks per package
+
+
+def _ups_old_km(ax, ay, bx, by):
+    """6371 * sqrt(square((by - ay) * cos(0.5 * (bx + ax))) + square(bx - ax)): the equirectangular distance of
+    UPS_old/vrptw_ups_utils.py:321-322, 359-360, 421-423 (x = latitude, y = longitude, radians), every op rounded separately."""
+    dt = np.asarray(ax).dtype.type
+    interm = (by - ay) * np.cos(dt(0.5) * (bx + ax))
+    return dt(UPS_OLD_RADIUS) * np.sqrt(np.square(interm) + np.square(bx - ax))
+
+
 # --------------------------------------------------------------------------- #
 # parameters (SURVEY.md App. A.1).  Names are the TF-1 variable names.
 # --------------------------------------------------------------------------- #
@@ -190,6 +219,7 @@ class EnvOracle:
         self.n_cust = args["n_cust"]
         self.input_dim = args["input_dim"]
         self.tw = args["task_name"] == "vrptw"
+        self.ups_old = bool(args.get("ups_old", False))            # UPS_old/vrptw_ups_utils.py physics (VRPTW only)
         self.input_data = np.asarray(input_data).astype(dtype)     # tf.float32 placeholder, vrptw_utils.py:176
         self.batch_size = self.input_data.shape[0]
         self.input_pnt = self.input_data[:, :, : self.input_dim - 1]
@@ -241,9 +271,14 @@ class EnvOracle:
         if self.tw:
             vx = self.all_x[rows, idx][:, None]
             vy = self.all_y[rows, idx][:, None]
-            t_spent = np.sqrt(np.square(self.previous_x - vx) + np.square(self.previous_y - vy))[:, 0]  # :304-309
+            if self.ups_old:                                        # UPS_old/vrptw_ups_utils.py:321-333
+                t_spent = (dt(UPS_OLD_CLICKS_PER_KM) * _ups_old_km(self.previous_x, self.previous_y, vx, vy))[:, 0]
+            else:
+                t_spent = np.sqrt(np.square(self.previous_x - vx) + np.square(self.previous_y - vy))[:, 0]  # :304-309
             self.previous_x, self.previous_y = vx, vy
             self.time = np.maximum(self.time + t_spent, self.all_b_tw[rows, idx])   # :316
+            if self.ups_old:
+                self.time = self.time + dt(UPS_OLD_SERVICE) * d_sat  # service time, UPS_old :332-333
         dep = (idx == self.n_cust).astype(dt)                       # :319
         self.load = self.load * (1 - dep) + dep * self.capacity     # :322
         if self.tw:
@@ -253,20 +288,26 @@ class EnvOracle:
             [np.tile((self.load == 0).astype(dt)[:, None], [1, self.n_cust]),
              ((self.demand.sum(1, dtype=dt) > 0).astype(dt) * dep)[:, None]], 1)
         if self.tw:                                                 # :340-348
-            travel = np.sqrt(np.square(self.previous_x - self.all_x) + np.square(self.previous_y - self.all_y))
+            if self.ups_old:                                        # UPS_old :359-361 (previous - all; squares and cos are even)
+                travel = dt(UPS_OLD_CLICKS_PER_KM) * _ups_old_km(self.all_x, self.all_y, self.previous_x, self.previous_y)
+            else:
+                travel = np.sqrt(np.square(self.previous_x - self.all_x) + np.square(self.previous_y - self.all_y))
             arrival = self.time[:, None] + travel
             self.mask = self.mask + np.concatenate(
                 [(arrival > self.all_e_tw).astype(dt)[:, :-1], np.zeros([R, 1], dt)], 1)
         return State(self.load, self.time, self.demand, d_sat, self.mask)
 
 
-def reward_func(actions: Sequence[np.ndarray], tw: bool) -> np.ndarray:
-    """Closed tour length, ``depot=None`` branch (vrptw_utils.py:397-414, vrp_utils.py:293-307)."""
+def reward_func(actions: Sequence[np.ndarray], tw: bool, ups_old: bool = False) -> np.ndarray:
+    """Closed tour length, ``depot=None`` branch (vrptw_utils.py:397-414, vrp_utils.py:293-307); ups_old: in km over the
+    equirectangular distance (UPS_old/vrptw_ups_utils.py:416-424)."""
     sol = np.stack(actions, 0)
     if tw:
         sol = sol[:, :, :2]
     tilted = np.concatenate([sol[-1:], sol[:-1]], 0)
     dt = sol.dtype.type
+    if ups_old:
+        return np.sum(_ups_old_km(sol[:, :, 0], sol[:, :, 1], tilted[:, :, 0], tilted[:, :, 1]), 0)
     return np.sum(np.power(np.sum(np.power(tilted - sol, dt(2)), 2), dt(0.5)), 0)
 
 
@@ -495,7 +536,7 @@ def rollout(p, args, input_data, decode_type="greedy", uniforms=None, uniforms_r
             ind = (batchBeamSeq + B * beam_path[k])[ind]
     else:
         actions = actions_tmp
-    Rw = reward_func(actions, tw)                                   # :236-240
+    Rw = reward_func(actions, tw, bool(args.get("ups_old", False)))   # :236-240
     return RolloutResult(
         R=Rw, idxs=np.stack(idxs), logprobs=np.stack(logprobs), actions=np.stack(actions),
         beam_parents=np.stack(beam_path) if beam_path else None,

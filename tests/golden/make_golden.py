@@ -61,9 +61,13 @@ _stub("shared.graph_embedding.full_graph_learning", FullGraphEmbedding=_Dummy)
 from model.attention_agent import RLAgent  # noqa: E402
 
 
-def components(task_name, ups=False):
-    """main.py:17-53 (load_task_specific_components): the UPS twins when args['ups'] is set."""
-    if task_name == "vrp" and ups:
+def components(task_name, ups=False, ups_old=False):
+    """main.py:17-53 (load_task_specific_components): the UPS twins when args['ups'] is set; ups_old: the UPS_old package
+    (nothing in main.py imports it; its Env / reward_func / actor are loaded the same way)."""
+    if ups_old:
+        from UPS_old.vrptw_ups_utils import Env, reward_func
+        from UPS_old.vrptw_ups_attention import AttentionVRPTWActor as A, AttentionVRPTWCritic as C
+    elif task_name == "vrp" and ups:
         from UPS.vrp_ups_utils import Env, reward_func
         from UPS.vrp_ups_attention import AttentionVRP_UPS_Actor as A, AttentionVRP_UPS_Critic as C
     elif task_name == "vrp":
@@ -94,7 +98,7 @@ def run_reference(args, params, data, decode_type, uniforms=None, uniforms_retry
     """Build the reference graph for ``decode_type`` and evaluate it on ``data``."""
     tf.reset_shim()
     tf.VARIABLE_STORE.update(params)
-    Env, reward_func, Actor, Critic = components(args["task_name"], bool(args.get("ups")))
+    Env, reward_func, Actor, Critic = components(args["task_name"], bool(args.get("ups")), bool(args.get("ups_old")))
     a = dict(args)
     a["log_dir"] = tempfile.mkdtemp()
     env = Env(a)
@@ -141,7 +145,7 @@ def run_reference(args, params, data, decode_type, uniforms=None, uniforms_retry
 def run_reference_env(args, data, idx_seq, parent_seq, beam_width):
     """Drive the reference Env directly with a prescribed action sequence."""
     tf.reset_shim()
-    Env, _, _, _ = components(args["task_name"])
+    Env, _, _, _ = components(args["task_name"], False, bool(args.get("ups_old")))
     env = Env(dict(args))
     sess = tf.Session()
     out = {"load": [], "time": [], "demand": [], "mask": [], "d_sat": []}
@@ -180,6 +184,12 @@ CASES = [
     ("ups_vrp20_greedy", "vrp20", "greedy", 8, {"ups": True}, 27, 0.2),              # UPS/vrp_ups_utils.Env + UPS actor
     ("vrptw20_tanh", "vrptw20", "greedy", 8, {"use_tanh": True}, 24, 0.3),           # C tanh(u) without glimpses
     ("vrptw10_nomaskptr", "vrptw10", "greedy", 8, {"mask_pointer": False}, 25, 0.3),
+    # glimpses beyond the one-glimpse case above, and the UPS_old package (km physics, service time)
+    ("vrptw10_glimpse2", "vrptw10", "greedy", 8, {"n_glimpses": 2}, 28, 0.3),
+    ("vrptw10_glimpse_nomask", "vrptw10", "stochastic", 8, {"n_glimpses": 1, "mask_glimpses": False}, 29, 0.3),
+    ("vrp10_glimpse", "vrp10", "greedy", 8, {"n_glimpses": 1}, 30, 0.3),
+    ("upsold_vrptw20_greedy", "vrptw20", "greedy", 8, {"ups_old": True, "capacity": 30}, 31, 0.2),
+    ("upsold_vrptw10_stochastic", "vrptw10", "stochastic", 8, {"ups_old": True}, 32, 0.2),
 ]
 
 
@@ -195,7 +205,9 @@ def main():
             continue
         args = O.default_args(task, **over)
         params = O.init_params(args, seed=seed, bias_scale=bscale)
-        if over.get("ups"):   # the UPS generators (GMM samples), restated in the product package's data module
+        if over.get("ups_old"):
+            data = O.create_dataset_ups_old(args["n_cust"], B, seed=1000 + seed)
+        elif over.get("ups"):   # the UPS generators (GMM samples), restated in the product package's data module
             import importlib
             data = importlib.import_module("mit_rl-vrptw_b200.data").create_dataset(args["task_name"], B, args["n_cust"], 1000 + seed, ups=True)
         else:
@@ -222,12 +234,13 @@ def main():
         print(f"{name}: R mean {out['R'].mean():.5f}  idx[0][:8] {out['idxs'][0][:8]}  vars {len(requested)}")
 
     # Env driven directly: random feasible-ish action sequences incl. repeated depot visits and beams
-    for name, task, W in [("env_vrptw10", "vrptw10", 1), ("env_vrp10", "vrp10", 1), ("env_vrptw10_beam", "vrptw10", 3)]:
+    for name, task, W in [("env_vrptw10", "vrptw10", 1), ("env_vrp10", "vrp10", 1), ("env_vrptw10_beam", "vrptw10", 3),
+                          ("env_upsold_vrptw10", "vrptw10", 1), ("env_upsold_vrptw10_beam", "vrptw10", 2)]:
         if only and name not in only:
             continue
-        args = O.default_args(task)
+        args = O.default_args(task, ups_old="upsold" in name)
         B, T = 12, 24
-        data = O.create_dataset(task, B, seed=77)
+        data = O.create_dataset_ups_old(args["n_cust"], B, seed=77) if args["ups_old"] else O.create_dataset(task, B, seed=77)
         rnd = np.random.RandomState(5)
         R_ = B * W
         idx_seq = rnd.randint(0, args["n_nodes"], size=(T, R_))

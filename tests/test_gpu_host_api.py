@@ -15,7 +15,8 @@ def _agent(args, params, task_name=None):
     pkg = load_pkg()
     H = pkg.host
     store = H.VariableStore(seed=0)
-    _, Env, reward_func, Actor, Critic = H.load_task_specific_components(task_name or args["task_name"], False)
+    _, Env, reward_func, Actor, Critic = H.load_ups_old_components() if args.get("ups_old") else \
+        H.load_task_specific_components(task_name or args["task_name"], False)
     env = Env(args)
     agent = H.RLAgent(args, None, env, None, reward_func, Actor, Critic, is_train=False, store=store)
     store.assign(params)
@@ -45,6 +46,66 @@ def test_env_reset_step_bit_exact(name, task, W):
         np.testing.assert_array_equal(st.d_sat.cpu().numpy(), fx["d_sat"][t + 1])
         if args["task_name"] == "vrptw":
             np.testing.assert_array_equal(st.time.cpu().numpy(), fx["time"][t + 1])
+
+
+@pytest.mark.parametrize("name,W", [("env_upsold_vrptw10", 1), ("env_upsold_vrptw10_beam", 2)])
+def test_ups_old_env_matches_reference_fixture(name, W):
+    """host.VRPTWEnvUPSOld -> vrpb200_env_step with VRPB200_PHYSICS_UPS_OLD against UPS_old/vrptw_ups_utils.Env driven
+    directly (tests/golden/make_golden.py): km travel time through cos(), 1.5 clicks of service per package.  Integer state
+    and masks identical; the clock within 2 ulp (cosf of CUDA and of numpy may differ in the last bit)."""
+    import torch
+    fx, _, _ = load_golden(name)
+    pkg = load_pkg()
+    args = pkg.task_specific_params.default_args("vrptw10")
+    _, Env, reward, _, _ = pkg.host.load_ups_old_components()
+    env = Env(args)
+    env.input_data = torch.from_numpy(fx["data"].astype(np.float32))
+    st = env.reset(W)
+    np.testing.assert_array_equal(st.mask.cpu().numpy(), fx["mask"][0])
+    for t in range(fx["idx_seq"].shape[0]):
+        par = torch.from_numpy(fx["parent_seq"][t][:, None]) if "parent_seq" in fx else None
+        st = env.step(torch.from_numpy(fx["idx_seq"][t][:, None]), par)
+        np.testing.assert_array_equal(st.mask.cpu().numpy(), fx["mask"][t + 1], err_msg=f"mask, step {t}")
+        np.testing.assert_array_equal(st.demand.cpu().numpy(), fx["demand"][t + 1])
+        np.testing.assert_array_equal(st.load.cpu().numpy(), fx["load"][t + 1])
+        np.testing.assert_array_equal(st.d_sat.cpu().numpy(), fx["d_sat"][t + 1])
+        np.testing.assert_allclose(st.time.cpu().numpy(), fx["time"][t + 1], rtol=3e-7, atol=1e-4)
+    assert fx["time"].max() > 50.0     # clicks, not unit-square distances
+
+
+def test_ups_old_reward_is_km_tour_length():
+    """reward_func of UPS_old (depot=None): closed tour in km, against the R the reference's own graph produced."""
+    import torch
+    fx, args, params = load_golden("upsold_vrptw20_greedy")
+    pkg = load_pkg()
+    rf = pkg.host.load_ups_old_components()[2]
+    r = rf([torch.from_numpy(a) for a in fx["actions"]])
+    np.testing.assert_allclose(r.cpu().numpy(), fx["R"], rtol=2e-6)
+    with pytest.raises(NotImplementedError):
+        rf([torch.from_numpy(a) for a in fx["actions"]], 40, 20.0, torch.zeros(8, 4))
+
+
+@pytest.mark.parametrize("case", ["vrptw20_glimpse_tanh", "upsold_vrptw20_greedy"])
+def test_rlagent_fuses_glimpses_and_ups_old(case):
+    """RLAgent.build_model picks the fused kernel for glimpses / UPS_old physics (one launch) and returns the reference's
+    tours, rewards and log-probabilities."""
+    import torch
+    fx, args, params = load_golden(case)
+    pkg = load_pkg()
+    H = pkg.host
+    comps = H.load_ups_old_components() if args.get("ups_old") else H.load_task_specific_components("vrptw", False)
+    store = H.VariableStore(seed=1)
+    env = comps[1](args)
+    agent = H.RLAgent(args, None, env, None, comps[2], comps[3], comps[4], is_train=False, store=store)
+    store.assign(params)
+    env.input_data = torch.from_numpy(fx["data"].astype(np.float32))
+    out = agent.build_model("greedy")
+    assert agent.engine().last_launch()["kernels"] == 1
+    idx = torch.stack(out[4])[:, :, 0].cpu().numpy()
+    np.testing.assert_array_equal(idx, fx["idxs"])
+    np.testing.assert_allclose(out[0].cpu().numpy(), fx["R"], rtol=1e-5)
+    np.testing.assert_allclose(torch.stack(out[2]).cpu().numpy(), fx["logprobs"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_array_equal(torch.stack(out[3]).cpu().numpy(), fx["actions"])
 
 
 @pytest.mark.parametrize("task", ["vrp10", "vrptw20"])

@@ -60,7 +60,10 @@ def _compare_trace(out, fx, args, decode_type):
 
 
 FUSED_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
-               if m["decode_type"] in ("greedy", "stochastic") and not m["over"].get("n_glimpses")]
+               if m["decode_type"] in ("greedy", "stochastic") and not m["over"].get("n_glimpses") and not m["over"].get("ups_old")]
+# glimpses (shared/decode_step.py:218-227) and the UPS_old Env physics: fused in the FP32-pipe kernel, whatever gemm= says
+SPECIAL_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
+                 if m["decode_type"] in ("greedy", "stochastic") and (m["over"].get("n_glimpses") or m["over"].get("ups_old"))]
 
 
 @pytest.mark.parametrize("name", FUSED_CASES)
@@ -79,6 +82,25 @@ def test_rollout_matches_reference_fixture(name, rows_per_cta, gemm):
         return
     torch.cuda.synchronize()
     _compare_trace(out, fx, args, meta["decode_type"])
+
+
+@pytest.mark.parametrize("name", SPECIAL_CASES)
+@pytest.mark.parametrize("rows_per_cta", [0, 32])
+def test_fused_glimpses_and_ups_old_match_reference_fixture(name, rows_per_cta):
+    """ONE persistent launch for the whole rollout with glimpses (1 and 2 modules, masked and un-masked, with C tanh on the
+    pointer, VRP and VRPTW) and with the UPS_old Env (km travel time through cos, service time, tour length in km), against
+    fixtures produced by the reference's own decode_step.py / UPS_old/vrptw_ups_utils.py."""
+    fx, args, params = load_golden(name)
+    meta = GOLDEN_INDEX[name]
+    eng, torch = _engine(args, params, rows_per_cta=rows_per_cta)
+    x = torch.from_numpy(fx["data"].astype(np.float32)).cuda()
+    out = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"),
+                      want_logprobs=True, trace=True)
+    torch.cuda.synchronize()
+    assert eng.last_launch()["kernels"] == 1 and eng.last_launch()["family"] == 1
+    _compare_trace(out, fx, args, meta["decode_type"])
+    fast = eng.rollout(x, meta["decode_type"], uniforms=fx.get("uniforms"), uniforms_retry=fx.get("uniforms_retry"))
+    assert torch.equal(fast.idxs, out.idxs) and torch.equal(fast.R, out.R)      # masked nodes skipped, early exit: same tours
 
 
 @pytest.mark.parametrize("name", [n for n in FUSED_CASES if GOLDEN_INDEX[n]["decode_type"] == "greedy"])

@@ -43,10 +43,12 @@ def test_rollout_matches_reference_code(name):
 
 
 @pytest.mark.parametrize("name,task,W", [("env_vrptw10", "vrptw10", 1), ("env_vrp10", "vrp10", 1),
-                                         ("env_vrptw10_beam", "vrptw10", 3)])
+                                         ("env_vrptw10_beam", "vrptw10", 3), ("env_upsold_vrptw10", "vrptw10", 1),
+                                         ("env_upsold_vrptw10_beam", "vrptw10", 2)])
 def test_env_matches_reference_code(name, task, W):
+    """Env driven directly; the upsold fixtures come from UPS_old/vrptw_ups_utils.Env (km travel time, service time)."""
     fx, _, _ = load_golden(name)
-    args = O.default_args(task)
+    args = O.default_args(task, ups_old="upsold" in name)
     env = O.EnvOracle(args, fx["data"])
     st = env.reset(W)
     np.testing.assert_array_equal(st.mask, fx["mask"][0])
