@@ -182,6 +182,19 @@ int vrpb200_reward_min_trucks(vrpb200_handle* h, const float* d_actions, const f
 int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
                                   float* d_reward, void* stream);
 
+/* ---- REINFORCE pieces around the rollout (forward only) ------------------------------ *
+ * Critic value v of RLAgent.build_model('stochastic') (model/attention_agent.py:243-270; critics
+ * VRPTW/vrptw_attention.py:87-169, VRP/vrp_attention.py:79-140): n_process_blocks un-masked attention passes over the
+ * initial instance + Linear/L1 (relu) + Linear/L2.  Needs the Critic/Process/P<i>/{v, emb_d, proj_d, proj_q, proj_e
+ * [, emb_begin_tw, proj_end_tw]} and Critic/Linear/{L1, L2} variables in set_weights (VRPB200_E_STATE otherwise).
+ * d_input [B, N, input_dim] -> d_v [B]. */
+int vrpb200_critic(vrpb200_handle* h, const float* d_input, int64_t B, float* d_v, void* stream);
+
+/* build_train_step's losses (model/attention_agent.py:286-294): d_losses[0] = mean((R - v) * sum_t logprob[t]) (actor,
+ * v as a constant), d_losses[1] = mean((R - v)^2) (critic).  d_R, d_v [R], d_logprob [T, R] (vrpb200_rollout's). */
+int vrpb200_reinforce_loss(vrpb200_handle* h, const float* d_R, const float* d_v, const float* d_logprob, int64_t T, int64_t R,
+                           float* d_losses, void* stream);
+
 /* Measured throughput of one SM pipe on the handle's device, for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: kind 0 = MUFU (ex2/rcp, ops/s), 1 = FP32 FMA (FMA/s, 2 flop each).
  * Runs a register-only micro-benchmark on every SM for ~`iters` x 4096 ops per thread.  Synchronous. */

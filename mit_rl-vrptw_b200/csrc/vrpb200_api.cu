@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include "launchers.h"
 #include "standalone_kernels.cuh"
+#include "critic_kernels.cuh"
 
 using namespace vrpb200;
 
@@ -39,6 +40,9 @@ struct vrpb200_handle {
     const float* WqTc[8] = {nullptr};
     AttWeights att[8];
     AttWeights* d_gatt = nullptr;   // device copy of att[0..n_glimpses-1]
+    float* d_critic = nullptr;      // critic constants (critic_kernels.cuh), null until set_weights saw Critic/* variables
+    int critic_blocks = 0;
+    float* d_loss = nullptr;        // [2] scratch of reinforce_loss
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
     // staging of the *_host call: kChunks in-flight chunks, one stream each
@@ -159,6 +163,8 @@ int vrpb200_destroy(vrpb200_handle* h) {
     cudaSetDevice(h->device);
     if (h->d_blob) cudaFree(h->d_blob);
     if (h->d_gatt) cudaFree(h->d_gatt);
+    if (h->d_critic) cudaFree(h->d_critic);
+    if (h->d_loss) cudaFree(h->d_loss);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
         if (h->dev_idx[i]) cudaFree(h->dev_idx[i]);
@@ -381,6 +387,90 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     if (c.n_glimpses > 0) {   // device array of the glimpse modules for the fused FP32-pipe kernel
         if (!h->d_gatt) CUDA_TRY(h, cudaMalloc((void**)&h->d_gatt, sizeof(AttWeights) * 8));
         CUDA_TRY(h, cudaMemcpy(h->d_gatt, h->att, sizeof(AttWeights) * c.n_glimpses, cudaMemcpyHostToDevice));
+    }
+
+    // ---- optional: the critic (Critic/Process/P<i>/..., Critic/Linear/L1|L2; attention_agent.py:243-270) ------------------
+    h->critic_blocks = 0;
+    if (m.count("Critic/Process/P0/v")) {
+        int nb = 0;
+        while (nb < 8 && m.count("Critic/Process/P" + std::to_string(nb) + "/v")) ++nb;
+        std::string miss;
+        auto getc = [&](const std::string& name, int64_t want) -> const float* {
+            auto it = m.find(name);
+            if (it == m.end() || it->second.n != want) { miss += " " + name; return nullptr; }
+            return it->second.p;
+        };
+        std::vector<float> cb((size_t)nb * kCriticBlockFloats + kCriticTailFloats, 0.0f);
+        std::vector<double> Au_prev(4 * H, 0.0), ce_prev(H, 0.0);
+        for (int i = 0; i < nb; ++i) {
+            const std::string p = "Critic/Process/P" + std::to_string(i);
+            const float* v = getc(p + "/v", H);
+            const float *ed_k = getc(p + "/emb_d/kernel", H), *ed_b = getc(p + "/emb_d/bias", H);
+            const float *pd_k = getc(p + "/proj_d/kernel", H * H), *pd_b = getc(p + "/proj_d/bias", H);
+            const float *pq_k = getc(p + "/proj_q/kernel", H * H), *pq_b = getc(p + "/proj_q/bias", H);
+            const float *pe_k = getc(p + "/proj_e/kernel", (int64_t)E * H), *pe_b = getc(p + "/proj_e/bias", H);
+            const float *et_k = nullptr, *et_b = nullptr, *pt_k = nullptr, *pt_b = nullptr;
+            if (h->tw) {   // emb_begin_tw embeds and proj_end_tw projects BOTH windows (vrptw_attention.py:147-150)
+                et_k = getc(p + "/emb_begin_tw/kernel", H); et_b = getc(p + "/emb_begin_tw/bias", H);
+                pt_k = getc(p + "/proj_end_tw/kernel", H * H); pt_b = getc(p + "/proj_end_tw/bias", H);
+            }
+            if (!miss.empty()) break;
+            float* blk = &cb[(size_t)i * kCriticBlockFloats];
+            std::vector<double> Au(4 * H, 0.0), ce(H, 0.0), cst(H, 0.0);
+            for (int hh = 0; hh < H; ++hh) {
+                double gd = 0, cd = pd_b[hh], gt = 0, ct = 0;
+                for (int k = 0; k < H; ++k) { gd += (double)ed_k[k] * pd_k[k * H + hh]; cd += (double)ed_b[k] * pd_k[k * H + hh]; }
+                if (h->tw) {
+                    ct = pt_b[hh];
+                    for (int k = 0; k < H; ++k) { gt += (double)et_k[k] * pt_k[k * H + hh]; ct += (double)et_b[k] * pt_k[k * H + hh]; }
+                }
+                double c0 = pe_b[hh];
+                for (int e2 = 0; e2 < E; ++e2) c0 += (double)emb_b[e2] * pe_k[e2 * H + hh];
+                ce[hh] = c0;
+                for (int cc = 0; cc < 4; ++cc) {
+                    double s = 0;
+                    if (cc < D1) for (int e2 = 0; e2 < E; ++e2) s += (double)emb_k[cc * E + e2] * pe_k[e2 * H + hh];
+                    Au[cc * H + hh] = s;
+                    blk[cc * H + hh] = (float)((s + ((h->tw && cc >= 2) ? gt : 0.0)) * (double)kTwoLog2e);
+                }
+                blk[4 * H + hh] = (float)(gd * (double)kTwoLog2e);
+                cst[hh] = (double)pq_b[hh] + c0 + cd + (h->tw ? 2.0 * ct : 0.0);
+                blk[10 * H + hh] = v[hh];
+            }
+            for (int hh = 0; hh < H; ++hh) {   // query of this block from the previous block's read-out (block 0: hy = 0)
+                double c0 = cst[hh];
+                if (i > 0) {
+                    for (int k = 0; k < H; ++k) c0 += ce_prev[k] * (double)pq_k[(size_t)k * H + hh];
+                    for (int cc = 0; cc < 4; ++cc) {
+                        double m0 = 0;
+                        for (int k = 0; k < H; ++k) m0 += Au_prev[cc * H + k] * (double)pq_k[(size_t)k * H + hh];
+                        blk[5 * H + cc * H + hh] = (float)m0;
+                    }
+                }
+                blk[9 * H + hh] = (float)c0;
+            }
+            Au_prev = Au; ce_prev = ce;
+        }
+        const float *l1_k = getc("Critic/Linear/L1/kernel", H * H), *l1_b = getc("Critic/Linear/L1/bias", H);
+        const float *l2_k = getc("Critic/Linear/L2/kernel", H), *l2_b = getc("Critic/Linear/L2/bias", 1);
+        if (!miss.empty()) return fail(h, VRPB200_E_WEIGHTS, "critic: missing or mis-sized variables:%s", miss.c_str());
+        float* tail = &cb[(size_t)nb * kCriticBlockFloats];
+        for (int hh = 0; hh < H; ++hh) {
+            double c0 = l1_b[hh];
+            for (int k = 0; k < H; ++k) c0 += ce_prev[k] * (double)l1_k[(size_t)k * H + hh];
+            for (int cc = 0; cc < 4; ++cc) {
+                double m0 = 0;
+                for (int k = 0; k < H; ++k) m0 += Au_prev[cc * H + k] * (double)l1_k[(size_t)k * H + hh];
+                tail[cc * H + hh] = (float)m0;
+            }
+            tail[4 * H + hh] = (float)c0;
+            tail[5 * H + hh] = l2_k[hh];
+        }
+        tail[6 * H] = l2_b[0];
+        if (h->d_critic) { cudaFree(h->d_critic); h->d_critic = nullptr; }
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_critic, cb.size() * 4));
+        CUDA_TRY(h, cudaMemcpy(h->d_critic, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice));
+        h->critic_blocks = nb;
     }
     h->raw.lstm_k = d + o_lstm_k;
     h->raw.lstm_b = d + o_lstm_b;
@@ -692,6 +782,30 @@ int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp
         decode_step_kernel<false><<<(unsigned)R, kH, 0, (cudaStream_t)stream>>>(
             h->raw, c.n_nodes, c.embedding_dim, d_decoder_inp, d_context, d_demand, d_load, d_time, d_mask, d_c, d_h,
             c.use_tanh, c.tanh_exploration, c.mask_glimpses, c.mask_pointer, c.forget_bias, d_logit, d_prob, d_logprob);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_critic(vrpb200_handle* h, const float* d_input, int64_t B, float* d_v, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights || h->critic_blocks == 0) return fail(h, VRPB200_E_STATE, "critic: set_weights has not seen the Critic/* variables");
+    if (!d_input || !d_v || B < 1) return fail(h, VRPB200_E_ARG, "critic: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int wpb = 8, NP = align_up(h->cfg.n_nodes, 8);
+    const size_t smem = (size_t)wpb * 6 * NP * sizeof(float);
+    const unsigned grid = (unsigned)((B + wpb - 1) / wpb);
+    if (h->tw) critic_kernel<true><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(d_input, B, h->cfg.n_nodes, h->cfg.input_dim, h->critic_blocks, h->d_critic, d_v);
+    else critic_kernel<false><<<grid, wpb * 32, smem, (cudaStream_t)stream>>>(d_input, B, h->cfg.n_nodes, h->cfg.input_dim, h->critic_blocks, h->d_critic, d_v);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_reinforce_loss(vrpb200_handle* h, const float* d_R, const float* d_v, const float* d_logprob, int64_t T, int64_t R,
+                           float* d_losses, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_R || !d_v || !d_logprob || !d_losses || T < 1 || R < 1) return fail(h, VRPB200_E_ARG, "reinforce_loss: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    reinforce_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_R, d_v, d_logprob, T, R, d_losses);
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }

@@ -252,6 +252,25 @@ class Engine:
                     "decode_step")
         return logit, prob, logprob
 
+    def critic(self, input_data: torch.Tensor) -> torch.Tensor:
+        """v of build_model('stochastic') (attention_agent.py:243-270): input [B, N, D] -> [B].  The weights given to
+        set_weights must include the Critic/* variables."""
+        x = self._f32(input_data, "input_data")
+        out = torch.empty((x.shape[0],), device=self.device)
+        self._check(self.lib.vrpb200_critic(self.handle, _ptr(x), x.shape[0], _ptr(out), self._stream()), "critic")
+        return out
+
+    def reinforce_loss(self, R: torch.Tensor, v: torch.Tensor, logprobs: torch.Tensor):
+        """build_train_step's (actor_loss, critic_loss) (attention_agent.py:286-294): R, v [rows], logprobs [T, rows]."""
+        r, vv, lp = self._f32(R, "R"), self._f32(v, "v"), self._f32(logprobs, "logprobs")
+        T, rows = lp.shape
+        if r.shape != (rows,) or vv.shape != (rows,):
+            raise VrpB200Error(f"R and v must be [{rows}]")
+        out = torch.empty((2,), device=self.device)
+        self._check(self.lib.vrpb200_reinforce_loss(self.handle, _ptr(r), _ptr(vv), _ptr(lp), T, rows, _ptr(out), self._stream()),
+                    "reinforce_loss")
+        return out[0], out[1]
+
     def reward(self, actions: torch.Tensor) -> torch.Tensor:
         a = self._f32(actions, "actions")
         T, R, A = a.shape

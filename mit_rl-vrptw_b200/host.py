@@ -242,15 +242,53 @@ class AttentionVRPTW_UPS_Actor(AttentionVRPTWActor):  # UPS/vrptw_ups_attention.
     pass
 
 
-class _CriticNotOnPath(object):
-    """Attention*Critic is only used by the REINFORCE training step (model/attention_agent.py:243-322),
-    which is outside the rollout path."""
+class _AttentionCriticBase(object):
+    """Attention*Critic of VRP/vrp_attention.py:79-140 and VRPTW/vrptw_attention.py:87-169 (and the UPS twins): one process
+    block of the critic.  It owns the variables the reference creates - v, emb_d, proj_d, proj_q, proj_e and, for VRPTW, the
+    two time-window layers the reference actually CALLS (emb_begin_tw and proj_end_tw, each for both windows, :147-150).
+    The blocks are evaluated together by vrpb200_critic (RLAgent.build_model('stochastic'))."""
+    TW = False
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("the critic belongs to the training step, which this library does not implement")
+    def __init__(self, dim, use_tanh=False, C=10, _name='Attention', _scope='', store: Optional[VariableStore] = None):
+        self.use_tanh = use_tanh
+        self.dim = dim
+        self.C = C
+        self.store = store or default_store()
+        self.prefix = _scope + _name
+        st, p, H = self.store, self.prefix, dim
+        st.get(p + '/v', [1, H], fans=(1, H))
+        for blk in ['emb_d'] + (['emb_begin_tw'] if self.TW else []):
+            st.get(f'{p}/{blk}/kernel', [1, 1, H], fans=(1, H))
+            st.get(f'{p}/{blk}/bias', [H], init="zeros")
+        for blk in ['proj_d'] + (['proj_end_tw'] if self.TW else []):
+            st.get(f'{p}/{blk}/kernel', [1, H, H], fans=(H, H))
+            st.get(f'{p}/{blk}/bias', [H], init="zeros")
+        st.get(p + '/proj_q/kernel', [H, H], fans=(H, H))
+        st.get(p + '/proj_q/bias', [H], init="zeros")
+
+    def _build_ref(self, E):
+        self.store.get(self.prefix + '/proj_e/kernel', [1, E, self.dim], fans=(E, self.dim))
+        self.store.get(self.prefix + '/proj_e/bias', [self.dim], init="zeros")
+
+    def __call__(self, query, ref, env):
+        raise NotImplementedError("a single critic block is not exposed; RLAgent.build_model('stochastic') evaluates the "
+                                  "whole critic (vrpb200_critic)")
 
 
-AttentionVRPCritic = AttentionVRPTWCritic = AttentionVRP_UPS_Critic = AttentionVRPTW_UPS_Critic = _CriticNotOnPath
+class AttentionVRPCritic(_AttentionCriticBase):
+    TW = False
+
+
+class AttentionVRPTWCritic(_AttentionCriticBase):
+    TW = True
+
+
+class AttentionVRP_UPS_Critic(AttentionVRPCritic):      # UPS/vrp_ups_attention.py: identical arithmetic
+    pass
+
+
+class AttentionVRPTW_UPS_Critic(AttentionVRPTWCritic):  # UPS/vrptw_ups_attention.py: identical arithmetic
+    pass
 
 
 class DecodeStep(object):
@@ -532,8 +570,7 @@ class RLAgent(object):
 
     def __init__(self, args, prt, env, dataGen, reward_func, clAttentionActor, clAttentionCritic, is_train=False, _scope='',
                  store: Optional[VariableStore] = None, device: int = 0):
-        if is_train:
-            raise NotImplementedError("the REINFORCE training step is outside the rollout path (SURVEY section 8f, N1)")
+        self.is_train = is_train       # forward side of the training step only: build_train_step() returns the losses
         if args.get('embedding_graph', 0) != 0:
             raise NotImplementedError("only embedding_graph=0 (LinearEmbedding) is on the rollout path")
         self.args = args
@@ -556,6 +593,8 @@ class RLAgent(object):
         self.decodeStep._build_lstm(args['embedding_dim'])
         self.sess = None
         self.last_time = None
+        self._scope = _scope
+        self._critic_built = False
 
     # -- checkpoint ------------------------------------------------------------------------------
     def Initialize(self, sess=None):
@@ -572,7 +611,38 @@ class RLAgent(object):
             print("have load model")
 
     def model_params(self):
-        return self.decodeStep.model_params(self.embedder_model)
+        p = self.decodeStep.model_params(self.embedder_model)
+        sc = self._scope + 'Critic/'
+        for k, v in self.store.vars.items():
+            if k.startswith(sc):
+                p['Critic/' + k[len(sc):]] = v
+        return p
+
+    def _build_critic(self):
+        """Variables of the critic, created where the reference creates them: in build_model('stochastic')
+        (attention_agent.py:246-268) - n_process_blocks Attention*Critic blocks under Critic/Process, Critic/Linear/L1, L2."""
+        if self._critic_built or self.clAttentionCritic is None:
+            return
+        H, st, sc = self.args['hidden_dim'], self.store, self._scope + 'Critic/'
+        for i in range(self.args.get('n_process_blocks', 3)):
+            blk = self.clAttentionCritic(H, _name="P" + str(i), _scope=sc + 'Process/', store=st)
+            blk._build_ref(self.args['embedding_dim'])
+        st.get(sc + 'Linear/L1/kernel', [H, H], fans=(H, H))
+        st.get(sc + 'Linear/L1/bias', [H], init="zeros")
+        st.get(sc + 'Linear/L2/kernel', [H, 1], fans=(H, 1))
+        st.get(sc + 'Linear/L2/bias', [1], init="zeros")
+        self._critic_built = True
+
+    def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0):
+        """attention_agent.py:272-322, forward side: the stochastic rollout, the critic and the two losses.  Returns the
+        reference's list [actor_train_step, critic_train_step, actor_loss, critic_loss, actor_gra_and_var, critic_gra_and_var,
+        R, v, logprobs, probs, actions, idxs] with None in the optimizer / gradient slots: back-propagation through the
+        rollout and Adam are not built (out of scope of this round)."""
+        import torch
+        R, v, logprobs, actions, idxs, batch, probs = self.build_model('stochastic', uniforms=uniforms, uniforms_retry=uniforms_retry,
+                                                                       seed=seed)
+        actor_loss, critic_loss = self.engine().reinforce_loss(R, v, torch.stack(logprobs))
+        return [None, None, actor_loss, critic_loss, None, None, R, v, logprobs, probs, actions, idxs]
 
     def engine(self):
         eargs = dict(self.args)
@@ -616,9 +686,17 @@ class RLAgent(object):
                     ind = (inst + B * par[k])[ind]
                 actions = torch.stack(bt)
             R_out = self._reward(list(actions), pnt, W) if self.args.get('min_trucks') else out.R
-            v = torch.zeros((), device=idx.device)
+            v = self._critic_value(decode_type)
             return (R_out, v, list(out.logprobs) if want_logprobs else None, list(actions), [i[:, None] for i in idx], pnt, None)
         return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs)
+
+    def _critic_value(self, decode_type):
+        """attention_agent.py:243-270: v = 0 unless decoding stochastically; then the critic's value of every instance."""
+        import torch
+        if decode_type != 'stochastic' or self.clAttentionCritic is None:
+            return torch.zeros((), device="cuda")
+        self._build_critic()
+        return self.engine().critic(self.env.input_data)
 
     def _reward(self, actions, input_pnt, beam_width):
         """attention_agent.py:236-240: the tour length, or with args['min_trucks'] the depot form of reward_func on the
@@ -703,7 +781,7 @@ class RLAgent(object):
             actions = actions_tmp
         self.last_beam_path = beam_path
         R = self._reward(actions, input_pnt, beam_width)                                   # :236-240
-        v = torch.zeros((), device=dev)
+        v = self._critic_value(decode_type)
         return (R, v, logprobs, actions, idxs, input_pnt, probs if want_probs else None)
 
     # -- evaluation ------------------------------------------------------------------------------

@@ -435,6 +435,84 @@ def decode_step(p, args, decoder_inp, context, env, c, h):
 
 
 # --------------------------------------------------------------------------- #
+# critic + REINFORCE losses (model/attention_agent.py:243-270, 286-294; critics
+# VRPTW/vrptw_attention.py:87-169, VRP/vrp_attention.py:79-140)
+# --------------------------------------------------------------------------- #
+def init_critic_params(args: dict, seed: int = 4321, bias_scale: float = 0.0) -> Dict[str, np.ndarray]:
+    """Variables of the critic as the reference creates them: ``Critic/Process/P<i>/{v, emb_d, proj_d, proj_q, proj_e}`` (+
+    ``emb_begin_tw``, ``proj_end_tw`` for VRPTW - the only two time-window layers the reference ever CALLS, each for both
+    windows, vrptw_attention.py:147-150; ``emb_end_tw`` / ``proj_begin_tw`` are constructed but never built), then
+    ``Critic/Linear/{L1, L2}``.  Glorot-uniform kernels, zero (or U(-s, s)) biases."""
+    rnd = np.random.RandomState(seed)
+    tw = args["task_name"] == "vrptw"
+    E, H = args["embedding_dim"], args["hidden_dim"]
+    p: Dict[str, np.ndarray] = {}
+    bias = (lambda n: np.zeros([n], np.float32)) if bias_scale == 0.0 else \
+        (lambda n: rnd.uniform(-bias_scale, bias_scale, size=[n]).astype(np.float32))
+    for i in range(args["n_process_blocks"]):
+        pre = f"Critic/Process/P{i}"
+        p[pre + "/v"] = _glorot(rnd, 1, H, [1, H])
+        for blk in ["emb_d"] + (["emb_begin_tw"] if tw else []):
+            p[f"{pre}/{blk}/kernel"] = _glorot(rnd, 1, H, [1, 1, H])
+            p[f"{pre}/{blk}/bias"] = bias(H)
+        for blk in ["proj_d"] + (["proj_end_tw"] if tw else []):
+            p[f"{pre}/{blk}/kernel"] = _glorot(rnd, H, H, [1, H, H])
+            p[f"{pre}/{blk}/bias"] = bias(H)
+        p[pre + "/proj_q/kernel"] = _glorot(rnd, H, H, [H, H])
+        p[pre + "/proj_q/bias"] = bias(H)
+        p[pre + "/proj_e/kernel"] = _glorot(rnd, E, H, [1, E, H])
+        p[pre + "/proj_e/bias"] = bias(H)
+    p["Critic/Linear/L1/kernel"] = _glorot(rnd, H, H, [H, H])
+    p["Critic/Linear/L1/bias"] = bias(H)
+    p["Critic/Linear/L2/kernel"] = _glorot(rnd, H, 1, [H, 1])
+    p["Critic/Linear/L2/bias"] = bias(1)
+    return p
+
+
+def critic_value(p, args, input_data, dtype=np.float32) -> np.ndarray:
+    """``v`` of ``RLAgent.build_model('stochastic')`` (attention_agent.py:243-270): hy = 0; n_process_blocks times
+    ``(e, logit) = AttentionCritic(hy, emb, env)``, ``hy = softmax(logit) . e`` (no mask); ``v = L2(relu(L1(hy)))``.
+    The critic reads the INITIAL demand and the time windows of ``env.input_data`` (vrptw_attention.py:135-137) and the
+    actor's embedding.  p holds the actor AND the critic variables."""
+    x = np.asarray(input_data).astype(dtype)
+    tw = args["task_name"] == "vrptw"
+    H = args["hidden_dim"]
+    emb = linear_embedding(p, x[:, :, : args["input_dim"] - 1])
+    B, N = x.shape[0], x.shape[1]
+    hy = np.zeros([B, H], dtype)
+    demand = x[:, :, -1]
+    for i in range(args["n_process_blocks"]):
+        g = lambda n: p[f"Critic/Process/P{i}/{n}"].astype(dtype)
+        d = conv1d_k1(conv1d_k1(demand[:, :, None], g("emb_d/kernel"), g("emb_d/bias")), g("proj_d/kernel"), g("proj_d/bias"))
+        e = conv1d_k1(emb, g("proj_e/kernel"), g("proj_e/bias"))
+        q = (hy @ g("proj_q/kernel") + g("proj_q/bias")).astype(dtype, copy=False)
+        arg = np.tile(q[:, None, :], [1, N, 1]) + e + d
+        if tw:   # emb_begin_tw embeds BOTH windows, proj_end_tw projects BOTH (vrptw_attention.py:147-150)
+            emb_end = conv1d_k1(x[:, :, 3][:, :, None], g("emb_begin_tw/kernel"), g("emb_begin_tw/bias"))
+            emb_begin = conv1d_k1(x[:, :, 2][:, :, None], g("emb_begin_tw/kernel"), g("emb_begin_tw/bias"))
+            p_end = conv1d_k1(emb_end, g("proj_end_tw/kernel"), g("proj_end_tw/bias"))
+            p_begin = conv1d_k1(emb_begin, g("proj_end_tw/kernel"), g("proj_end_tw/bias"))
+            arg = arg + p_begin + p_end                             # :163
+        u = (np.tanh(arg) @ g("v").reshape(H, 1))[:, :, 0]
+        prob = softmax(u)
+        hy = (prob[:, None, :] @ e)[:, 0, :]
+    l1 = np.maximum(hy @ p["Critic/Linear/L1/kernel"].astype(dtype) + p["Critic/Linear/L1/bias"].astype(dtype), dtype(0))
+    return (l1 @ p["Critic/Linear/L2/kernel"].astype(dtype) + p["Critic/Linear/L2/bias"].astype(dtype))[:, 0].astype(dtype)
+
+
+def reinforce_losses(R, v, logprobs):
+    """``build_train_step`` (attention_agent.py:286-294): actor_loss = mean((R - stop_grad(v)) * add_n(logprobs)),
+    critic_loss = tf.losses.mean_squared_error(R, v).  logprobs [T, B]."""
+    dt = R.dtype
+    slp = np.zeros_like(R)
+    for lp in logprobs:                                             # tf.add_n: in list order
+        slp = slp + lp.astype(dt)
+    actor = np.mean((R - v) * slp, 0, dtype=dt)
+    critic = np.mean(np.square(R - v), dtype=dt)                    # mean_squared_error: SUM_BY_NONZERO_WEIGHTS = mean
+    return actor, critic
+
+
+# --------------------------------------------------------------------------- #
 # the rollout  (model/attention_agent.py:84-240)
 # --------------------------------------------------------------------------- #
 @dataclass

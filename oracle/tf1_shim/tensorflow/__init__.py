@@ -518,11 +518,21 @@ def _dynamic_rnn(cell, inputs, initial_state=None, scope=None, **k):
 
 
 class _Layer:
-    """tf.layers.Layer: `_scope=` names the variable scope outright; `name=` is relative."""
+    """tf.layers.Layer: `name=` is relative to the variable scope at construction.  A string `_scope=` is entered with
+    tf.variable_scope(self._scope) when the layer is first CALLED (tf/python/layers/base.py, __call__), i.e. relative to the
+    variable scope that is current at that call: top level for the actor's layers ("Actor/Decoder/Attention/emb_d"), inside
+    "Critic/Process" for the critic's ("Critic/Process/P0/emb_d")."""
 
     def __init__(self, units, activation=None, _scope=None, name=None, **k):
         self.units, self.activation = units, activation
-        self.scope = _scope.rstrip("/") if _scope is not None else _scoped(name)
+        self._raw_scope = _scope.rstrip("/") if _scope is not None else None
+        self._scope_name = None if _scope is not None else _scoped(name)
+
+    @property
+    def scope(self):
+        if self._scope_name is None:       # first call: resolve against the current variable scope
+            self._scope_name = _scoped(self._raw_scope)
+        return self._scope_name
 
 
 class Conv1D(_Layer):

@@ -371,3 +371,73 @@ def test_mask_pointer_false_matches_oracle(task, gemm):
     np.testing.assert_allclose(out.R.cpu().numpy()[same], ref.R[same], rtol=1e-4)
     np.testing.assert_allclose(out.logprobs.cpu().numpy()[:, same], ref.logprobs[:, same], rtol=2e-4, atol=2e-5)
     np.testing.assert_array_equal(out.final_demand.cpu().numpy()[same], ref.final_state.demand[same])
+
+
+@pytest.mark.parametrize("name,task", [("vrptw10", "vrptw10"), ("vrp10", "vrp10"), ("vrptw20", "vrptw20")])
+def test_critic_and_reinforce_losses_match_reference_fixture(name, task):
+    """SURVEY 8f N1, forward side: vrpb200_critic against the v the reference's own AttentionVRP(TW)Critic produced
+    (tests/golden/critic.npz), and vrpb200_reinforce_loss on the kernel's own stochastic rollout (same uniforms as the
+    fixture) against build_train_step's formulas (attention_agent.py:286-294)."""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    pkg = load_pkg()
+    fx = np.load(os.path.join(GOLDEN, "critic.npz"))
+    args = O.default_args(task)
+    seed, bs = int(fx[f"{name}_seed"]), float(fx[f"{name}_bias_scale"])
+    p = O.init_params(args, seed=seed, bias_scale=bs)
+    p.update(O.init_critic_params(args, seed=seed + 100, bias_scale=bs))
+    eng = pkg.Engine(args, device=0)
+    eng.set_weights(p)
+    x = torch.from_numpy(fx[f"{name}_data"].astype(np.float32)).cuda()
+    v = eng.critic(x)
+    np.testing.assert_allclose(v.cpu().numpy(), fx[f"{name}_v"], rtol=1e-4, atol=2e-6)
+    out = eng.rollout(x, "stochastic", uniforms=fx[f"{name}_uniforms"], uniforms_retry=fx[f"{name}_uniforms_retry"], want_logprobs=True)
+    np.testing.assert_allclose(out.R.cpu().numpy(), fx[f"{name}_R"], rtol=1e-4)
+    np.testing.assert_allclose(out.logprobs.cpu().numpy(), fx[f"{name}_logprobs"], rtol=2e-4, atol=2e-5)
+    actor, critic = eng.reinforce_loss(out.R, v, out.logprobs)
+    want_a, want_c = O.reinforce_losses(fx[f"{name}_R"], fx[f"{name}_v"], fx[f"{name}_logprobs"])
+    np.testing.assert_allclose(actor.item(), want_a, rtol=2e-4)
+    np.testing.assert_allclose(critic.item(), want_c, rtol=2e-4)
+    # without the Critic/* variables the entry point refuses (no silent zeros)
+    eng2 = pkg.Engine(args, device=0)
+    eng2.set_weights(O.init_params(args, seed=seed, bias_scale=bs))
+    with pytest.raises(pkg.VrpB200Error):
+        eng2.critic(x)
+
+
+def test_rlagent_build_train_step_forward_side():
+    """RLAgent(is_train=True).build_train_step(): stochastic rollout + critic + losses through the reference's protocol;
+    the critic variables appear in the store under the reference's names when the stochastic model is first built."""
+    import torch
+    pkg = load_pkg()
+    H = pkg.host
+    args = O.default_args("vrptw10")
+    comps = H.load_task_specific_components("vrptw", False)
+    store = H.VariableStore(seed=5)
+    env = comps[1](args)
+    agent = H.RLAgent(args, None, env, None, comps[2], comps[3], comps[4], is_train=True, store=store)
+    data = O.create_dataset("vrptw10", 32, seed=9)
+    env.input_data = torch.from_numpy(data.astype(np.float32))
+    assert not any(k.startswith("Critic/") for k in store.vars)
+    T = args["decode_len"]
+    rnd = np.random.RandomState(3)
+    u1, u2 = rnd.uniform(size=(T, 32)).astype(np.float32), rnd.uniform(size=(T, 32)).astype(np.float32)
+    step = agent.build_train_step(uniforms=u1, uniforms_retry=u2)
+    assert len(step) == 12 and step[0] is None and step[1] is None
+    names = {k for k in store.vars if k.startswith("Critic/")}
+    assert "Critic/Process/P2/proj_end_tw/kernel" in names and "Critic/Linear/L2/bias" in names and len(names) == 3 * 13 + 4
+    params = {k: v for k, v in store.vars.items() if k != "decoder_input"}
+    ref = O.rollout(params, args, data, "stochastic", uniforms=u1, uniforms_retry=u2)
+    v_ref = O.critic_value(params, args, data)
+    R, v = step[6].cpu().numpy(), step[7].cpu().numpy()
+    np.testing.assert_allclose(v, v_ref, rtol=1e-4, atol=2e-6)
+    same = (torch.stack(step[11])[:, :, 0].cpu().numpy() == ref.idxs).all(0)
+    assert same.mean() >= 0.9
+    np.testing.assert_allclose(R[same], ref.R[same], rtol=1e-4)
+    if same.all():
+        a_ref, c_ref = O.reinforce_losses(ref.R, v_ref, ref.logprobs)
+        np.testing.assert_allclose(step[2].item(), a_ref, rtol=5e-4)
+        np.testing.assert_allclose(step[3].item(), c_ref, rtol=5e-4)
+    # greedy decoding keeps v = 0 (attention_agent.py:244)
+    assert float(agent.build_model("greedy")[1]) == 0.0

@@ -126,3 +126,26 @@ def test_committed_oracle_tours_are_reproducible(name):
         np.testing.assert_allclose(r.R, fx["R" + tag][:n], rtol=1e-6)
     if name == "ups_vrptw100":   # saturated tanh: fp32 rounding alone moves tours - the reason for the fp64 adjudication
         assert (fx["idx32"] == fx["idx64"]).all(0).mean() < 0.99
+
+
+@pytest.mark.parametrize("name,task", [("vrptw10", "vrptw10"), ("vrp10", "vrp10"), ("vrptw20", "vrptw20")])
+def test_critic_value_and_reinforce_losses_match_reference_code(name, task):
+    """the critic value v of build_model('stochastic') (attention_agent.py:243-270) against the reference's own
+    AttentionVRP(TW)Critic run under the shim (tests/golden/make_golden_critic.py), and the two losses of build_train_step
+    (:286-294) re-derived from the fixture's R, v, logprobs."""
+    import os
+    from tests.helpers import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, "critic.npz"))
+    args = O.default_args(task)
+    seed, bs = int(fx[f"{name}_seed"]), float(fx[f"{name}_bias_scale"])
+    p = O.init_params(args, seed=seed, bias_scale=bs)
+    p.update(O.init_critic_params(args, seed=seed + 100, bias_scale=bs))
+    v = O.critic_value(p, args, fx[f"{name}_data"])
+    np.testing.assert_allclose(v, fx[f"{name}_v"], rtol=2e-6, atol=1e-7)
+    res = O.rollout(p, args, fx[f"{name}_data"], "stochastic", uniforms=fx[f"{name}_uniforms"], uniforms_retry=fx[f"{name}_uniforms_retry"])
+    np.testing.assert_allclose(res.R, fx[f"{name}_R"], rtol=1e-6)
+    actor, critic = O.reinforce_losses(res.R, v, res.logprobs)
+    R, lp = fx[f"{name}_R"], fx[f"{name}_logprobs"]
+    want_actor = np.mean((R - fx[f"{name}_v"]) * np.sum(lp.astype(np.float64), 0))
+    np.testing.assert_allclose(actor, want_actor, rtol=1e-4)
+    np.testing.assert_allclose(critic, np.mean((R - fx[f"{name}_v"]) ** 2), rtol=1e-5)
