@@ -123,6 +123,14 @@ int vrpb200_rollout(vrpb200_handle* h, const float* d_input, int64_t B, int mode
                     int32_t* d_idx, float* d_cost, float* d_logprob, int32_t* d_beam_parent,
                     const vrpb200_trace* trace, void* stream);
 
+/* Sampling retry policy of vrpb200_rollout(STOCHASTIC).  whole_batch = 0 (default): a row whose uniform lies beyond its
+ * CDF redraws alone (multi-GPU friendly; probability ~1e-7 per row-step).  whole_batch = 1: the reference's my_multinomial
+ * (model/attention_agent.py:148-167) - if ANY row of the batch fails its first draw, EVERY row of the batch decides that
+ * step with d_uniforms_retry instead; rows failing again take node 0.  The call then synchronises the stream (it re-runs the
+ * rollout once per redrawn step; vrpb200_last_redraws tells how many).  One batch = one vrpb200_rollout call on one GPU. */
+int vrpb200_set_sampling_retry(vrpb200_handle* h, int whole_batch);
+int vrpb200_last_redraws(vrpb200_handle* h);
+
 /* The same call with HOST buffers (what evaluate_batch's sess.run(feed_dict) is to a caller): the batch is
  * cut into chunks that are copied H2D, decoded and copied back D2H on a few streams so that transfers
  * overlap decoding.  Pass page-locked (pinned) buffers for full PCIe speed; pageable memory works, slower.

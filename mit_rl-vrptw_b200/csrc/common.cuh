@@ -89,6 +89,10 @@ struct RolloutArgs {
     const float* q_bq;
     int n_glimpses, mask_glimpses;
     int physics;             // 0: VRP / VRPTW / UPS Env (Euclidean travel time); 1: UPS_old/vrptw_ups_utils.py:321-361
+    // whole-batch sampling retry of the reference (attention_agent.py:163-167), opt-in: retry_steps[t] != 0 = every row draws
+    // step t from uniforms_retry; fail_steps[t] is set when a row's FIRST draw of a step that was not redrawn finds no node
+    const int* retry_steps;  // [T] or null
+    int* fail_steps;         // [T] or null (null: per-row retry, the default)
 };
 
 __host__ __device__ inline int align_up(int x, int a) { return (x + a - 1) / a * a; }
@@ -236,6 +240,12 @@ VRP_DEVINL float counter_uniform(unsigned long long seed, unsigned t, unsigned l
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
     z ^= z >> 31;
     return (float)(unsigned)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+// which of the two uniform draws a row may use at step t (see RolloutArgs::retry_steps)
+VRP_DEVINL void draw_range(const RolloutArgs& a, int t, int& d0, int& d1) {
+    if (a.fail_steps) { d0 = a.retry_steps[t] ? 1 : 0; d1 = d0 + 1; }
+    else { d0 = 0; d1 = 2; }
 }
 
 // Env mask of one node after a step (VRPTW/vrptw_utils.py:328-348, VRP/vrp_utils.py:228-247), as a count 0..3.

@@ -721,7 +721,9 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                 int sel = -1;
                 if (sl == 0 && live) {
                     const long long o = (long long)t * R + row;
-                    for (int draw = 0; draw < 2 && sel < 0; ++draw) {
+                    int d0_, d1_;
+                    draw_range(a, t, d0_, d1_);   // per-row retry, or the reference's whole-batch redraw (attention_agent.py:165-167)
+                    for (int draw = d0_; draw < d1_ && sel < 0; ++draw) {
                         const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
                         const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
                         float cum = 0.0f;   // tf.cumsum: sequential fp32 (masked nodes add exactly 0)
@@ -730,6 +732,7 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
                             if (cum > u) { sel = n; break; }
                         }
                     }
+                    if (sel < 0 && a.fail_steps && d0_ == 0) a.fail_steps[t] = 1;   // some row of the batch needs the redraw: the host re-runs with this step redrawn
                 }
                 if (sel < 0) sel = 0;
                 idx = __shfl_sync(kFull, sel, sub * LPR);

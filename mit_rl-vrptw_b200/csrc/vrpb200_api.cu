@@ -43,6 +43,9 @@ struct vrpb200_handle {
     float* d_critic = nullptr;      // critic constants (critic_kernels.cuh), null until set_weights saw Critic/* variables
     int critic_blocks = 0;
     float* d_loss = nullptr;        // [2] scratch of reinforce_loss
+    int whole_batch_retry = 0;      // vrpb200_set_sampling_retry
+    int* d_retry = nullptr;         // [2][T]: retry_steps | fail_steps
+    int last_redraws = 0;
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
     // staging of the *_host call: kChunks in-flight chunks, one stream each
@@ -165,6 +168,7 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (h->d_gatt) cudaFree(h->d_gatt);
     if (h->d_critic) cudaFree(h->d_critic);
     if (h->d_loss) cudaFree(h->d_loss);
+    if (h->d_retry) cudaFree(h->d_retry);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
         if (h->dev_idx[i]) cudaFree(h->dev_idx[i]);
@@ -598,6 +602,30 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
         CUDA_TRY(h, cudaGetLastError());
         a.feat4 = h->ws_feat4[slot];
     }
+    if (mode == VRPB200_STOCHASTIC && h->whole_batch_retry) {
+        // the reference's my_multinomial (attention_agent.py:148-167): if ANY row of the batch finds no node with its first
+        // draw, EVERY row redraws that step once.  The kernel flags such steps; the rollout is repeated with the earliest
+        // flagged step redrawn until no new step is flagged (probability ~1e-7 per row-step: one launch almost always).
+        const int T = c.decode_len;
+        if (!h->d_retry) CUDA_TRY(h, cudaMalloc((void**)&h->d_retry, sizeof(int) * 2 * 65536));
+        if (T > 65536) return fail(h, VRPB200_E_ARG, "decode_len too large for whole-batch retry");
+        std::vector<int> retry(T, 0), failed(T, 0);
+        h->last_redraws = 0;
+        a.retry_steps = h->d_retry; a.fail_steps = h->d_retry + T;
+        for (;;) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_retry, retry.data(), sizeof(int) * T, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+            CUDA_TRY(h, cudaMemsetAsync(h->d_retry + T, 0, sizeof(int) * T, (cudaStream_t)stream));
+            int rc = launch_rollout(h, a, (cudaStream_t)stream);
+            if (rc) return rc;
+            CUDA_TRY(h, cudaMemcpyAsync(failed.data(), h->d_retry + T, sizeof(int) * T, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+            CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));
+            int first = -1;
+            for (int t = 0; t < T && first < 0; ++t) if (failed[t] && !retry[t]) first = t;
+            if (first < 0) return 0;
+            retry[first] = 1;           // later flags came from a trajectory that this redraw changes: decide them again
+            ++h->last_redraws;
+        }
+    }
     return launch_rollout(h, a, (cudaStream_t)stream);
 }
 
@@ -615,6 +643,7 @@ int vrpb200_rollout_host(vrpb200_handle* h, const float* h_input, int64_t B, int
     if (!h_input || !h_cost) return fail(h, VRPB200_E_ARG, "h_input and h_cost are required");
     if (B < 1) return fail(h, VRPB200_E_ARG, "B must be >= 1");
     if (mode == VRPB200_BEAM) return fail(h, VRPB200_E_ARG, "rollout_host: beam search goes through vrpb200_rollout");
+    if (mode == VRPB200_STOCHASTIC && h->whole_batch_retry) return fail(h, VRPB200_E_ARG, "rollout_host decodes in chunks: whole-batch retry needs vrpb200_rollout");
     const vrpb200_config& c = h->cfg;
     CUDA_TRY(h, cudaSetDevice(h->device));
     constexpr int NC = vrpb200_handle::kChunks;
@@ -785,6 +814,14 @@ int vrpb200_decode_step(vrpb200_handle* h, int64_t R, const float* d_decoder_inp
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }
+
+int vrpb200_set_sampling_retry(vrpb200_handle* h, int whole_batch) {
+    if (!h) return VRPB200_E_ARG;
+    h->whole_batch_retry = whole_batch ? 1 : 0;
+    return VRPB200_OK;
+}
+
+int vrpb200_last_redraws(vrpb200_handle* h) { return h ? h->last_redraws : VRPB200_E_ARG; }
 
 int vrpb200_critic(vrpb200_handle* h, const float* d_input, int64_t B, float* d_v, void* stream) {
     if (!h) return VRPB200_E_ARG;

@@ -176,6 +176,15 @@ class Engine:
             C.c_void_p(stats.ctypes.data) if want_stats else None), "rollout_host")
         return (idx, cost, stats) if want_stats else (idx, cost)
 
+    def set_sampling_retry(self, whole_batch: bool) -> None:
+        """False (default): per-row retry.  True: the reference's whole-batch single redraw (attention_agent.py:148-167);
+        stochastic rollout() calls then synchronise their stream."""
+        self._check(self.lib.vrpb200_set_sampling_retry(self.handle, int(bool(whole_batch))), "set_sampling_retry")
+
+    def last_redraws(self) -> int:
+        """Steps the last whole-batch stochastic rollout redrew for every row."""
+        return int(self.lib.vrpb200_last_redraws(self.handle))
+
     def pipe_peak(self, kind: str, iters: int = 256) -> float:
         """Measured throughput (ops/s) of the MUFU ('mufu') or FP32 FMA ('fma') pipe on this device."""
         out = C.c_double()

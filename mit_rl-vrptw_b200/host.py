@@ -668,6 +668,9 @@ class RLAgent(object):
             self.beam_width = W
             # the per-step log-probabilities are only computed on request: without them plain greedy decoding runs the
             # kernel's fast per-row tail (evaluate_batch / evaluate_single never read them)
+            # args['whole_batch_retry']: the reference's sampling retry (one redraw of EVERY row when any row fails) instead
+            # of the per-row retry; single-GPU batches only
+            self.engine().set_sampling_retry(bool(self.args.get('whole_batch_retry', False)))
             out = self.engine().rollout(self.env.input_data, decode_type, beam_width=W, uniforms=uniforms,
                                         uniforms_retry=uniforms_retry, seed=seed, want_logprobs=want_logprobs)
             idx = out.idxs.long()                                      # [T, R]

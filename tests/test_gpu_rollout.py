@@ -226,6 +226,38 @@ def test_stochastic_given_uniforms_vs_oracle():
     np.testing.assert_allclose(out.logprobs.cpu().numpy()[:, agree], ref.logprobs[:, agree], rtol=2e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
+def test_stochastic_whole_batch_retry_is_the_reference_policy(gemm):
+    """Opt-in whole-batch retry (attention_agent.py:148-167): when ANY row fails its first draw, EVERY row of the batch decides
+    that step with the second set of uniforms.  Two draws are forced to fail (u = 2 > any CDF) at steps 0 and 3; the tours
+    must equal the oracle's as-written policy (per_row_retry=False), differ from the per-row policy, and the library must
+    report exactly the redrawn steps."""
+    args = O.default_args("vrptw20")
+    params = O.init_params(args, seed=78, bias_scale=0.2)
+    B, T = 96, args["decode_len"]
+    data = O.create_dataset("vrptw20", B, seed=10)
+    rnd = np.random.RandomState(4)
+    u1 = rnd.uniform(size=(T, B)).astype(np.float32)
+    u2 = rnd.uniform(size=(T, B)).astype(np.float32)
+    u1[0, 5] = 2.0
+    u1[3, 40] = 2.0
+    eng, torch = _engine(args, params, gemm=gemm)
+    x = torch.from_numpy(data.astype(np.float32)).cuda()
+    per_row = eng.rollout(x, "stochastic", uniforms=u1, uniforms_retry=u2)
+    eng.set_sampling_retry(True)
+    whole = eng.rollout(x, "stochastic", uniforms=u1, uniforms_retry=u2, want_logprobs=True)
+    assert eng.last_redraws() == 2
+    eng.set_sampling_retry(False)
+    ref = O.rollout(params, args, data, "stochastic", uniforms=u1, uniforms_retry=u2, per_row_retry=False)
+    assert sorted(ref.retried) == [0, 3]
+    idx = whole.idxs.cpu().numpy().astype(np.int64)
+    agree = first_divergence(idx, ref.idxs) == T
+    assert agree.mean() >= 0.97
+    np.testing.assert_array_equal(idx[0], ref.idxs[0])          # the redrawn first step: every row took its second uniform
+    np.testing.assert_allclose(whole.R.cpu().numpy()[agree], ref.R[agree], rtol=1e-4)
+    assert (per_row.idxs.cpu().numpy()[0] != idx[0]).any()      # ... which the per-row policy does not do
+
+
 def test_stochastic_in_kernel_stream_is_valid_and_reproducible():
     args = O.default_args("vrptw20")
     params = O.init_params(args, seed=78)
