@@ -1,3 +1,7 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_rollout.py -m gpu -q --timeout 300 --timeout-method=thread -p no:cacheprovider -k "whole_batch or stochastic" > gpurun_out/r2p_tests.log 2>&1; tail -40 gpurun_out/r2p_tests.log
+{
+timeout 120 python tools/time_variant.py libvrpb200_notok.so tc6 14208 greedy ups 2>&1 | tail -1
+UPS=1 timeout 200 python tools/phase_clocks.py vrptw100 14208 tc6 48 2>&1 | tail -50
+} > gpurun_out/r2r_clocks.txt 2>&1
+cat gpurun_out/r2r_clocks.txt

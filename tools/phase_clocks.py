@@ -20,7 +20,7 @@ eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))
 x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2, ups=bool(os.environ.get("UPS"))).astype(np.float32)).cuda()
 eng.rollout(x)
-stats = torch.zeros(32, dtype=torch.int64, device="cuda")
+stats = torch.zeros(64, dtype=torch.int64, device="cuda")
 tr = L.Trace(); tr.d_stats = stats.data_ptr()
 idx = torch.empty((eng.T, B), dtype=torch.int32, device="cuda"); cost = torch.empty(B, device="cuda")
 rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 0, 1, None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
@@ -43,6 +43,18 @@ if gemm == "tc5":
     for i in (0, 1, 2, 3, 5, 4):
         print(f"    {an[i]:40s} {s[20 + i] / blocksteps:10.0f} clk/step")
     print(f"    total {s[20:27].sum() / blocksteps:.0f} clk/step;  near-tie softmax visits (row-steps of this warp): {s[27]}")
+    sys.exit(0)
+if gemm == "tc6":
+    nm = {0: "wait gates (W_h pass of both teams)", 1: "offsets + LSTM epilogue + team barrier", 2: "C1 set-up (first tiles)", 3: "wait q", 4: "q epilogue + team barrier",
+          18: "wait for the score token", 11: "C1: loop top", 7: "C1: wait MMA", 9: "C1: TMEM load, free", 10: "C1: arithmetic", 8: "C1: psum / logits / next F",
+          5: "after scores / after rows", 12: "rows: wait for logits", 14: "rows fast: prefetch issue", 15: "rows fast: arg-max + merge", 16: "rows fast: Env.step",
+          17: "rows fast: feasibility + lists", 13: "rows: rest", 6: "consts + end-of-step team barrier"}
+    for who, o in (("team 0, warp 2", 4), ("team 1, warp 2", 36)):
+        print(" ", who)
+        for i in (0, 1, 2, 3, 4, 18, 11, 7, 9, 10, 8, 5, 12, 14, 15, 16, 17, 13, 6):
+            print(f"    {nm[i]:42s} {s[o + i] / blocksteps:10.0f} clk/step")
+        print(f"    total {s[o:o + 25].sum() / blocksteps:.0f} clk/step")
+    print(f"  near-tie softmax visits (warp-steps): {s[29]} = {s[29] / blocksteps:.3f} per block-step")
     sys.exit(0)
 if gemm in ("tc4", "tc4s", "tc4x"):
     names = ["wait gates MMA", "LSTM epilogue", "C1 set-up (first tiles)", "wait q", "q epilogue + barrier", "C1 tiles | rows (C2, Env, mask, items)",
