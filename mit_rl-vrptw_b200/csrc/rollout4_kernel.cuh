@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         }
         // ================= LSTM epilogue: gates = gates^T(TMEM, h part) + x part + bias ; c, h' ; h' -> X ==========
         {
+            VRP_CLK(19);      // (row offsets of the step)
             if (t > 0) {
                 mbar_wait(bar_g, (t - 1) & 1);
                 tc_fence_after();

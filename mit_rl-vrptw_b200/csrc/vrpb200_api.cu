@@ -509,14 +509,26 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
         if (fam == kFamV3) return smem_rollout3(rb, rb / a.W, c.n_nodes, FD, a.W, h->max_smem_optin, &stages);
         return smem_ffma(rb, rb, c.n_nodes, FD);
     };
-    // rows per CTA: the largest block that fits shared memory and still gives every SM >= 2 blocks; when no candidate
-    // fills the device twice, the smallest one that fits (more, lighter CTAs for small batches; with beam search the
-    // smallest block that still holds every beam of an instance)
+    // rows per CTA.  A decode step of a block is a latency chain (LSTM epilogue -> query GEMM -> scores -> per-row tail) whose
+    // length hardly depends on the number of rows: measured on B200 (profiles/r2_rows_per_cta_sweep.txt) the time of one wave
+    // of CTAs is proportional to (85 + rows_per_cta) for VRPTW-20, -50 and -100 alike.  So the block size that minimises
+    // waves x (85 + rows) wins: big blocks for big batches, but e.g. 32 rows for 8 192 or 4 096 instances (2 waves / 1 wave
+    // instead of 4 / 2 waves of 16-row blocks: 1.4 - 1.7 x faster).  Beam search keeps the rule "largest block that still
+    // fills the device twice, else the smallest that holds every beam of an instance" (rollout3, not re-measured).
     const int cand[4] = {64, 48, 32, 16};
     int RB = 0;
     if (c.rows_per_cta) {
         RB = c.rows_per_cta;
         if ((fam == kFamV4 || fam == kFamV5) && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
+    } else if (a.mode != 2) {
+        double best = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            const int rb = cand[i];
+            if (smem_of(rb) > h->max_smem_optin) continue;
+            const long long ctas = (a.B + rb - 1) / rb;
+            const double cost = (double)((ctas + h->num_sms - 1) / h->num_sms) * (85.0 + rb);
+            if (!RB || cost < best) { RB = rb; best = cost; }
+        }
     } else {
         int smallest_fit = 0;
         for (int i = 0; i < 4 && !RB; ++i) {

@@ -63,6 +63,7 @@ if gemm in ("tc4", "tc4s", "tc4x"):
         print(" ", who)
         for n, v in zip(names, s[o:o + len(names)]):
             print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
+        print(f"    {'row offsets of the step':40s} {s[o + 19] / blocksteps:10.0f} clk/step")
         print(f"    total {s[o:o + 25].sum() / blocksteps:.0f} clk/step")
     print(f"  near-tie softmax visits (warp-steps): {s[29]} = {s[29] / blocksteps:.3f} per block-step")
     print(f"  exact-tail visits (warp-steps, all warps): {s[30]} = {s[30] / blocksteps:.3f} per block-step; rows without un-masked node: {s[31]}")

@@ -1,4 +1,5 @@
-"""Scratch: time the fused rollout of one library variant (path in argv[1]) on UPS VRPTW-100."""
+"""Scratch: time the fused rollout of one library variant.
+usage: time_variant.py <lib.so> <gemm> <B> [mode] [ups|uniform] [task] [rows_per_cta]"""
 import importlib, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,9 +10,11 @@ L.LIB_PATH = os.path.join(L.LIB_DIR, sys.argv[1]); L._lib = None
 gemm, B = sys.argv[2], int(sys.argv[3])
 mode = sys.argv[4] if len(sys.argv) > 4 else "greedy"
 ups = (sys.argv[5] == "ups") if len(sys.argv) > 5 else True
-args = pkg.task_specific_params.default_args("vrptw100")
-x = torch.from_numpy(pkg.data.create_dataset("vrptw", B, 100, 2, ups=ups).astype(np.float32)).cuda()
-eng = pkg.Engine(args, gemm=gemm)
+task = sys.argv[6] if len(sys.argv) > 6 else "vrptw100"
+rb = int(sys.argv[7]) if len(sys.argv) > 7 else 0
+args = pkg.task_specific_params.default_args(task)
+x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2, ups=ups).astype(np.float32)).cuda()
+eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1234))
 eng.rollout(x, mode, seed=1); torch.cuda.synchronize()
 ts = []
@@ -19,4 +22,6 @@ for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); out = eng.rollout(x, mode, seed=2); e1.record(); torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
-print(sys.argv[1], gemm, B, mode, "ups" if ups else "uniform", eng.last_launch()["rows_per_cta"], "ms per launch:", " ".join(f"{t:.2f}" for t in ts), "cost", float(out.R.mean()), flush=True)
+ll = eng.last_launch()
+print(sys.argv[1], gemm, task, B, mode, "ups" if ups else "uniform", "rb", ll["rows_per_cta"], "fam", ll["family"], "grid", ll["grid"], "ms per launch:",
+      " ".join(f"{t:.3f}" for t in ts), "cost", float(out.R.mean()), flush=True)
