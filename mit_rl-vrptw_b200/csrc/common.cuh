@@ -151,6 +151,14 @@ VRP_DEVINL void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, u
         "r"(accumulate)
         : "memory");
 }
+// one lane of a fully converged warp (elect.sync): tcgen05.mma / tcgen05.commit issued under this predicate from warp-uniform
+// control flow compile to a single predicated UTCHMMA; under `if (lane == 0)` the compiler wraps every one of them into an
+// ELECT ... BRA.U.ANY loop over the active threads (6 serial instructions per MMA on the issuing thread)
+VRP_DEVINL bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 // shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
 VRP_DEVINL uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |

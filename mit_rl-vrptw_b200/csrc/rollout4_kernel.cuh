@@ -24,7 +24,7 @@ namespace vrpb200 {
 
 
 struct Smem4 {
-    int ring, X, qq, F, logits, items, alive, bc, vsm, psum, dem, mask, rs, meta, bar, total, stages;
+    int ring, X, qq, F, logits, items, alive, bc, vsm, psum, dem, mask, rs, meta, bar, rowmap, total, stages;
 };
 
 __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw) {
@@ -48,6 +48,7 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
     L.rs = off;     off += RB * kRowState * 4;
     L.meta = off;   off += align_up((RB + 68 + RB + RB + 20) * 4, 16);   // nact[RB], off[<=65 (+pad)], flags[RB], nalive[RB], done[16], stop
     L.bar = off;    off += 320 + 64 * 8;                      // ... + one mbarrier per tile of the step (row warps wait on them)
+    L.rowmap = off; off += align_up(RB * NP, 16);             // row of every item slot of the step (one byte; replaces a 6-step binary search per item)
     L.total = off;
     return L;
 }
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     float* psum = reinterpret_cast<float*>(smem + L.psum);
     float* dem = reinterpret_cast<float*>(smem + L.dem);
     unsigned char* maskb = smem + L.mask;
+    unsigned char* rowmap = smem + L.rowmap;
     float* rowst = reinterpret_cast<float*>(smem + L.rs);
     int* nact_s = reinterpret_cast<int*>(smem + L.meta);
     int* off_s = nact_s + RB;            // [RB + 1] exclusive prefix of nact (this step)
@@ -181,35 +183,52 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 pre = STAGES < kV3UsesQ ? STAGES : kV3UsesQ;
                 for (int u = 0; u < pre; ++u) issue(u);
             }
-        } else if (warp == 17 && lane == 0) {
+        } else if (warp == 17) {   // the whole warp runs the loop (uniform control flow), one elected lane issues
             uint32_t c = 0;
             int step = 0;
+            const uint64_t wdesc0 = tc_desc(ring_u32, 128, 256), xdesc_hi0 = VRP_XDESC(x_hi, 0), xdesc_lo0 = VRP_XDESC(x_lo, 0);
+#ifdef VRPB200_PHASE_CLOCKS
+            long long ic_[6] = {0, 0, 0, 0, 0, 0}, ic_last_ = clock64();   // wait h', q: wait weights, q: issue, gates: wait weights, gates: throttle, gates: issue
+#define VRP_ICLK(i) do { const long long c_ = clock64(); ic_[i] += c_ - ic_last_; ic_last_ = c_; } while (0)
+#else
+#define VRP_ICLK(i) do { } while (0)
+#endif
             for (;; ++step) {
                 mbar_wait(bar_x, step & 1);
                 tc_fence_after();
+                VRP_ICLK(0);
                 if (*stop_s) break;
 #pragma unroll 1
                 for (int u = 0; u < kV3UsesQ; ++u, ++c) {          // q^T[unit, row] = W_q^T . h^T  -> columns kQCol..
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
                     tc_fence_after();
+                    VRP_ICLK(1);
+                    // descriptors by addition (the address field counts 16-byte units and never carries out of its 14 bits):
+                    // the single issuing thread is latency-bound on the uniform datapath, every instruction per MMA counts
+                    const uint64_t w0 = wdesc0 + (uint64_t)(st * (kSlabBytes >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int kc = 2 * u + kk;
-                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192, 128, 256);
-                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192 + 4096, 128, 256);
-                        const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
-                        tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
-                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
-                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int kc = 2 * u + kk;
+                            const uint64_t w_hi = w0 + (uint64_t)(kk * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
+                            const uint64_t dx_hi = xdesc_hi0 + (uint64_t)(kc * 16), dx_lo = xdesc_lo0 + (uint64_t)(kc * 16);
+                            tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
+                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                        }
+                        tc_commit(bar_empty + 8 * st);
                     }
-                    tc_commit(bar_empty + 8 * st);
+                    __syncwarp();
+                    VRP_ICLK(2);
                 }
-                tc_commit(bar_q);
+                if (elect_one()) tc_commit(bar_q);
+                __syncwarp();
 #pragma unroll 1
                 for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
+                    VRP_ICLK(3);
 #ifndef VRP_NO_THROTTLE_GATES
                     if (u > 0) {   // throttle: this GEMM has a whole step of slack, the score MMAs of C1 queue behind it
                         const uint32_t cp = c - 1;
@@ -217,29 +236,39 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     }
 #endif
                     tc_fence_after();
+                    VRP_ICLK(4);
                     const int kc = u >> 1, mp = u & 1;
-                    const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
+                    const uint64_t dx_hi = xdesc_hi0 + (uint64_t)(kc * 16), dx_lo = xdesc_lo0 + (uint64_t)(kc * 16);
+                    const uint64_t w0 = wdesc0 + (uint64_t)(st * (kSlabBytes >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) {
-                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192, 128, 256);
-                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192 + 4096, 128, 256);
-                        const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
-                        tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
-                        tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
-                        tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                        for (int mi = 0; mi < 2; ++mi) {
+                            const uint64_t w_hi = w0 + (uint64_t)(mi * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
+                            const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
+                            tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
+                            tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                        }
+                        tc_commit(bar_empty + 8 * st);
                     }
-                    tc_commit(bar_empty + 8 * st);
+                    __syncwarp();
+                    VRP_ICLK(5);
                 }
-                tc_commit(bar_g);
+                if (elect_one()) tc_commit(bar_g);
+                __syncwarp();
             }
             if (step > 0) mbar_wait(bar_g, (step - 1) & 1);
+#ifdef VRPB200_PHASE_CLOCKS
+            if (a.stats && lane == 0) for (int i = 0; i < 6; ++i) atomicAdd(a.stats + 40 + i, (unsigned long long)ic_[i]);   // the clock variant's stats buffer has 64 slots
+#endif
         }
-        else if (DEEP && warp >= 18 && lane == 0) {
+        else if (DEEP && warp >= 18) {   // (whole warp, one elected lane issues: see elect_one)
             // ---- score-MMA issuer of group g: one tile per "F ready"; quarter q goes to TMEM buffer q once the four score
             //      warps have copied the previous tile's quarter q out of it
             const int g = warp - 18;
             const uint32_t bfull = bar_grp + 80 * g, bfree = bfull + 32, bfrdy = bfull + 64;
             const uint32_t fbase = smem_u32(smem + L.F) + g * 4 * kC1TileBytes;
+            const uint64_t bdesc0 = tc_desc(bc_u32, 128, 256);
             for (uint32_t tc = 0;; ++tc) {
                 const uint32_t fb = tc & 1;
                 mbar_wait(bfrdy + 8 * fb, (tc >> 1) & 1);
@@ -249,12 +278,15 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 for (int q = 0; q < 4; ++q) {
                     if (tc > 0) mbar_wait(bfree + 8 * q, (tc - 1) & 1);
                     tc_fence_after();
-                    const uint64_t dbh = tc_desc(bc_u32 + q * 1024, 128, 256), dbl = tc_desc(bc_u32 + 4096 + q * 1024, 128, 256);
+                    const uint64_t dbh = bdesc0 + (uint64_t)(q * (1024 >> 4)), dbl = dbh + (4096 >> 4);
                     const uint32_t d = tmem_base + 128 * g + 32 * q;
-                    tc_mma_tf32(d, dfl, dbh, idescQ, 0);
-                    tc_mma_tf32(d, dfh, dbl, idescQ, 1);
-                    tc_mma_tf32(d, dfh, dbh, idescQ, 1);
-                    tc_commit(bfull + 8 * q);
+                    if (elect_one()) {
+                        tc_mma_tf32(d, dfl, dbh, idescQ, 0);
+                        tc_mma_tf32(d, dfh, dbl, idescQ, 1);
+                        tc_mma_tf32(d, dfh, dbh, idescQ, 1);
+                        tc_commit(bfull + 8 * q);
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -407,6 +439,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 if (lane == 0) off_s[RB] = m_tot;
             }
             if (tid < 64 && tid >= ((m_tot + 127) >> 7)) mbar_arrive_n(bar_tile + 8 * tid, 4);   // tiles that do not exist in this step
+            if (NSW == 16) {   // item slot -> row: the warp that owns rows 4w..4w+3 in the per-row tail fills their slots (8 lanes per row)
+                const int rr = 4 * warp + (lane >> 3);
+                const int o0 = __shfl_sync(kFull, s0 - n0, rr & 31), o1 = __shfl_sync(kFull, tot0 + s1 - n1, rr & 31);
+                if (warp < RB / 4) {
+                    const int ofs = rr < 32 ? o0 : o1, cnt = nact_s[rr];
+                    for (int k = lane & 7; k < cnt; k += 8) rowmap[ofs + k] = (unsigned char)rr;
+                }
+            }
         }
         // ================= LSTM epilogue: gates = gates^T(TMEM, h part) + x part + bias ; c, h' ; h' -> X ==========
         {
@@ -487,13 +527,16 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
 #pragma unroll
             for (int k = 0; k < 5; ++k) f[k] = 0.0f;
             if (valid) {
-                int lo = 0, hi = RB;
+                if (NSW == 16) r = rowmap[it];
+                else {
+                    int lo = 0, hi = RB;
 #pragma unroll
-                for (int s = 0; s < 6; ++s) {
-                    const int mid = (lo + hi) >> 1;
-                    if (off_s[mid] <= it) lo = mid; else hi = mid;
+                    for (int s = 0; s < 6; ++s) {
+                        const int mid = (lo + hi) >> 1;
+                        if (off_s[mid] <= it) lo = mid; else hi = mid;
+                    }
+                    r = lo;
                 }
-                r = lo;
                 n = items[r * NP + (it - off_s[r])];
                 if (feats) {
                     const float4 fv = ldcg4_volatile(gfeat4 + (size_t)r * N + n);

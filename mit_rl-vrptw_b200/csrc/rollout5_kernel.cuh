@@ -246,10 +246,11 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 pre = STAGES < kV3UsesQ ? STAGES : kV3UsesQ;
                 for (int u = 0; u < pre; ++u) issue(u);
             }
-        } else if (warp == 21 && lane == 0) {
-            // ---- LSTM / query MMA issuer
+        } else if (warp == 21) {
+            // ---- LSTM / query MMA issuer (the whole warp runs the loop, one elected lane issues: see elect_one in common.cuh)
             uint32_t c = 0;
             int step = 0;
+            const uint64_t wdesc0 = tc_desc(ring_u32, 128, 256), xdesc_hi0 = VRP_XDESC(x_hi, 0), xdesc_lo0 = VRP_XDESC(x_lo, 0);
             for (;; ++step) {
                 mbar_wait(bar_x, step & 1);
                 tc_fence_after();
@@ -259,19 +260,23 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
                     tc_fence_after();
+                    const uint64_t w0 = wdesc0 + (uint64_t)(st * (kSlabBytes >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int kk = 0; kk < 2; ++kk) {
-                        const int kc = 2 * u + kk;
-                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192, 128, 256);
-                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + kk * 8192 + 4096, 128, 256);
-                        const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
-                        tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
-                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
-                        tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const int kc = 2 * u + kk;
+                            const uint64_t w_hi = w0 + (uint64_t)(kk * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
+                            const uint64_t dx_hi = xdesc_hi0 + (uint64_t)(kc * 16), dx_lo = xdesc_lo0 + (uint64_t)(kc * 16);
+                            tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
+                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                        }
+                        tc_commit(bar_empty + 8 * st);
                     }
-                    tc_commit(bar_empty + 8 * st);
+                    __syncwarp();
                 }
-                tc_commit(bar_q);
+                if (elect_one()) tc_commit(bar_q);
+                __syncwarp();
 #pragma unroll 1
                 for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
                     const uint32_t st = c % STAGES;
@@ -284,22 +289,26 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
 #endif
                     tc_fence_after();
                     const int kc = u >> 1, mp = u & 1;
-                    const uint64_t dx_hi = VRP_XDESC(x_hi, kc), dx_lo = VRP_XDESC(x_lo, kc);
+                    const uint64_t dx_hi = xdesc_hi0 + (uint64_t)(kc * 16), dx_lo = xdesc_lo0 + (uint64_t)(kc * 16);
+                    const uint64_t w0 = wdesc0 + (uint64_t)(st * (kSlabBytes >> 4));
+                    if (elect_one()) {
 #pragma unroll
-                    for (int mi = 0; mi < 2; ++mi) {
-                        const uint64_t w_hi = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192, 128, 256);
-                        const uint64_t w_lo = tc_desc(ring_u32 + st * kSlabBytes + mi * 8192 + 4096, 128, 256);
-                        const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
-                        tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
-                        tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
-                        tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                        for (int mi = 0; mi < 2; ++mi) {
+                            const uint64_t w_hi = w0 + (uint64_t)(mi * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
+                            const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
+                            tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
+                            tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                        }
+                        tc_commit(bar_empty + 8 * st);
                     }
-                    tc_commit(bar_empty + 8 * st);
+                    __syncwarp();
                 }
-                tc_commit(bar_g);
+                if (elect_one()) tc_commit(bar_g);
+                __syncwarp();
             }
             if (step > 0) mbar_wait(bar_g, (step - 1) & 1);       // the last gates GEMM must have drained before TMEM is freed
-        } else if (warp >= 22 && lane == 0) {
+        } else if (warp >= 22) {
             // ---- score-MMA issuer of group g: one tile per "F ready"; its quarters go to the group's three TMEM buffers in
             //      rotation, each as soon as the four score warps that read the buffer's previous content have copied it out
             const int g = warp - 22;
@@ -315,12 +324,15 @@ __global__ void __launch_bounds__(kV5Threads, 1) rollout5_kernel(const __grid_co
                 for (int q = 0; q < 4; ++q) {
                     if (use > 0) mbar_wait(bfree + 8 * buf, (use - 1) & 1);
                     tc_fence_after();
-                    const uint64_t dbh = tc_desc(bc_u32 + q * 1024, 128, 256), dbl = tc_desc(bc_u32 + 4096 + q * 1024, 128, 256);
+                    const uint64_t dbh = tc_desc(bc_u32 + q * 1024, 128, 256), dbl = dbh + (4096 >> 4);
                     const uint32_t d = tmem_base + 96 * g + 32 * buf;
-                    tc_mma_tf32(d, dfl, dbh, idescQ, 0);
-                    tc_mma_tf32(d, dfh, dbl, idescQ, 1);
-                    tc_mma_tf32(d, dfh, dbh, idescQ, 1);
-                    tc_commit(bfull + 8 * buf);
+                    if (elect_one()) {
+                        tc_mma_tf32(d, dfl, dbh, idescQ, 0);
+                        tc_mma_tf32(d, dfh, dbl, idescQ, 1);
+                        tc_mma_tf32(d, dfh, dbh, idescQ, 1);
+                        tc_commit(bfull + 8 * buf);
+                    }
+                    __syncwarp();
                     if (++buf == 3) { buf = 0; ++use; }
                 }
             }

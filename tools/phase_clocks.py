@@ -66,6 +66,10 @@ if gemm in ("tc4", "tc4s", "tc4x"):
         print(f"    {'row offsets of the step':40s} {s[o + 19] / blocksteps:10.0f} clk/step")
         print(f"    total {s[o:o + 25].sum() / blocksteps:.0f} clk/step")
     print(f"  near-tie softmax visits (warp-steps): {s[29]} = {s[29] / blocksteps:.3f} per block-step")
+    inames = ["wait for h' (bar_x)", "q: wait for weights", "q: issue + commit", "gates: wait for weights", "gates: throttle (previous stage's MMAs)", "gates: issue + commit"]
+    print("  MMA issuer (warp 17)")
+    for n, v in zip(inames, s[40:46]):
+        print(f"    {n:40s} {v / blocksteps:10.0f} clk/step")
     print(f"  exact-tail visits (warp-steps, all warps): {s[30]} = {s[30] / blocksteps:.3f} per block-step; rows without un-masked node: {s[31]}")
     sys.exit(0)
 for n, v in zip(names, s[4:4 + len(names)]):
