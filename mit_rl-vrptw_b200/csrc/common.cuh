@@ -287,6 +287,12 @@ VRP_DEVINL void tc_ld4(uint32_t taddr, float (&v)[4]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
 }
+VRP_DEVINL void tc_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
+                 : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 // TMEM load split into issue + wait so that the load can overlap arithmetic; the wait carries the destination
 // registers as in/out operands, which keeps the compiler from consuming them early
 VRP_DEVINL void tc_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {

@@ -60,12 +60,6 @@ __host__ __device__ inline Smem5 make_layout5(int RB, int N, int stages) {
     return L;
 }
 
-VRP_DEVINL void tc_st4(uint32_t taddr, const float (&v)[4]) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-                 "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
-                 : "memory");
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
 // non-blocking test of an mbarrier phase
 VRP_DEVINL bool mbar_test(uint32_t bar, uint32_t parity) {
     uint32_t ok;
