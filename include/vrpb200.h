@@ -64,8 +64,8 @@ typedef struct vrpb200_config {
     int32_t mask_pointer;    /* shared/decode_step.py:231-232 */
     int32_t rows_per_cta;    /* 0 = choose; else 16/32/48/64 (tuning knob, no effect on results) */
     int32_t gemm_path;       /* fused kernel family (every family gives the same results up to fp32 rounding):
-                                0 = default: rollout4 for large batches (32 / 48 rows per CTA), rollout5 for small ones
-                                    (16 rows per CTA), rollout3 for beam search,
+                                0 = default: rollout4 (greedy, stochastic), rollout3 for beam search, the FP32-pipe kernel
+                                    with glimpses or UPS_old physics,
                                 1 = everything on the FP32 pipe (independent cross-check of the tensor-core kernels),
                                 3 = rollout3 (transposed tcgen05 GEMMs, lock-step phases, fused beam search),
                                 6 = rollout4 (per-row item lists, fast greedy tail, shared-reciprocal tanh, deep MMA

@@ -2,6 +2,7 @@
 // tcgen05 / TMEM, packed FP32x2), the separately-rounded Env arithmetic and the fast activations.  Every fused kernel
 // (rollout_ffma.cuh, rollout3_kernel.cuh, rollout5_kernel.cuh) and the stand-alone kernels include this file.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -51,6 +52,8 @@ struct RolloutArgs {
     const float* Wg;         // [17 slabs][8][2][2][32][4]  permuted LSTM kernel (+ folded embedding rows)
     const float* WqTc;       // [8 uses][2 k-chunks][hi 4 KB | lo 4 KB], tiles [128 units][K=8] of W_q^T (TF32 hi/lo split)
     const float* WgT3;       // rollout3: [32 uses][2 gate types][hi 4 KB | lo 4 KB], tiles [128 units][K=8] of W_h^T
+    const float* WqTh;       // rollout4/5: [4 uses][2 k-chunks][hi 4 KB | lo 4 KB], tiles [128 units][K=16] of W_q^T as FP16 hi + FP16 lo
+    const float* WgTh;       // rollout4/5: [16 uses][2 gate types][hi 4 KB | lo 4 KB], tiles [128 units][K=16] of W_h^T, FP16 hi/lo
     const float* WxT;        // rollout3: [4 features][4 gate types][128 units]  W_emb . W_lstm[:E]
     const float* bgT;        // rollout3: [4 gate types][128 units]  b_lstm + b_emb . W_lstm[:E]
     const float* bg;         // [128][4]  gate bias per unit: i, j, f, o (b_lstm + b_emb . W_x)
@@ -159,6 +162,14 @@ VRP_DEVINL bool elect_one() {
     asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\tselp.b32 %0, 1, 0, px;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+VRP_DEVINL void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc),
+        "r"(accumulate)
+        : "memory");
+}
 // shared-memory matrix descriptor: K-major, no swizzle (cute::UMMA::SmemDescriptor, version 1)
 VRP_DEVINL uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) |
@@ -167,6 +178,10 @@ VRP_DEVINL uint64_t tc_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo
 // instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32, both K-major, M x N
 __host__ __device__ constexpr uint32_t tc_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// instruction descriptor for kind::f16: F32 accumulate, FP16 x FP16, both K-major, M x N
+__host__ __device__ constexpr uint32_t tc_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 VRP_DEVINL float tf32_rna(float x) {   // round to TF32 (10 explicit mantissa bits), ties away
     uint32_t y;
@@ -275,6 +290,16 @@ constexpr int kV3UsesG = 0;
 #else
 constexpr int kV3UsesG = 32;                // W_h^T: (k-chunk, pair of gate types) per ring stage
 #endif
+// rollout4/5: the LSTM / query GEMMs on kind::f16 with a two-term FP16 split of both operands, x = hi + lo, hi = fp16(x), lo =
+// fp16(x - hi): |x| <= 1 (h') or <= 0.2 (Glorot weights), so lo lies in FP16's subnormal range where the spacing is 2^-24 -
+// the residual x - hi - lo is <= 2^-25 ABSOLUTE, and hi.hi + lo.hi + hi.lo is as accurate as an FP32 matmul (measured on
+// Glorot weights: rms error 7.7e-8 against 7.4e-8 for numpy's fp32 matmul and 2.8e-8 for 3xTF32).  K = 16 per MMA instead of 8:
+// half the MMAs (the issue rate of the single issuing thread, ~65 clk per MMA, is what the query GEMM waits for), half the
+// weight bytes streamed from L2 per step, half the shared memory of the h' operand tiles.
+constexpr int kHUsesQ = 4;                  // W_q^T: 2 k-chunks (K = 16 each) per 16 KB ring stage
+constexpr int kHUsesG = 16;                 // W_h^T: (k-chunk, pair of gate types) per ring stage
+// h' as the [row][k] K-major B operand in FP16, [row/8][k/8][row%8][k%8]: descriptor of k-chunk kc (K = 16)
+#define VRP_XDESC_H(base, kc) tc_desc((base) + (kc) * 256, 128, 2048)
 // h as the [row][k] K-major B operand of the transposed GEMMs, [row/8][k/4][row%8][k%4]: descriptor of k-chunk kc
 #define VRP_XDESC(base, kc) tc_desc((base) + (kc) * 256, 128, 4096)
 

@@ -6,7 +6,8 @@ namespace vrpb200 {
 
 int smem_rollout4(int rb, int n_nodes, int max_smem, int* stages) {
     if (rb > 48) return 1 << 30;                      // TMEM: q^T and the score buffers need their own columns
-    *stages = make_layout4(rb, n_nodes, 3, 17).total <= max_smem ? 3 : 2;
+    // ring depth: 4 stages hold the whole of W_q^T (FP16 hi/lo, 64 KB) - the query GEMM then never waits for weights
+    *stages = make_layout4(rb, n_nodes, 4, 17).total <= max_smem ? 4 : make_layout4(rb, n_nodes, 3, 17).total <= max_smem ? 3 : 2;
     return make_layout4(rb, n_nodes, *stages, 17).total;
 }
 
@@ -20,6 +21,7 @@ static cudaError_t go(const RolloutArgs& a, int grid, int smem, cudaStream_t st)
 
 template <int RB>
 static cudaError_t go_rb(const RolloutArgs& a, bool tw, int stages, int grid, int smem, cudaStream_t st) {
+    if (stages == 4) return tw ? go<RB, true, 4>(a, grid, smem, st) : go<RB, false, 4>(a, grid, smem, st);
     if (stages == 3) return tw ? go<RB, true, 3>(a, grid, smem, st) : go<RB, false, 3>(a, grid, smem, st);
     return tw ? go<RB, true, 2>(a, grid, smem, st) : go<RB, false, 2>(a, grid, smem, st);
 }

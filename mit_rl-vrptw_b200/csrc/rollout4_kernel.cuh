@@ -33,7 +33,7 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
     int off = 0;
     L.stages = stages;
     L.ring = off;   off += stages * kSlabBytes;
-    L.X = off;      off += 2 * RB * kH * 4;
+    L.X = off;      off += 2 * RB * kH * 2;                    // h' as the K-major B operand, FP16 hi | lo
     L.qq = off;     off += RB * kH * 4;
     L.F = off;      off += 4 * 2 * kC1TileBytes;               // nsw 16: 4 groups x 1 F tile; nsw 8: 2 groups x 2 F tiles
     (void)nsw;
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     const uint32_t bar_empty = bar0 + 32, bar_q = bar0 + 64, bar_g = bar0 + 72, bar_x = bar0 + 80, tmem_slot = bar0 + 120,
                    bar_tile = bar0 + 320, bar_grp = bar0 + 128;   // group g at +40 g: full[0], full[1] (MMA commit), free[0], free[1] (4 warps copied the buffer), F ready (4 warps)
     const uint32_t ring_u32 = smem_u32(smem + L.ring), bc_u32 = smem_u32(smem + L.bc);
-    const uint32_t x_hi = smem_u32(xt), x_lo = x_hi + RB * kH * 4;
+    const uint32_t x_hi = smem_u32(xt), x_lo = x_hi + RB * kH * 2;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sp = warp & 3, ub = warp >> 2;
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         *reinterpret_cast<float*>(smem + L.bc + 4096 + o) = lo;
     }
     if (tid < 128) vsm[tid] = a.vm2[tid];
-    for (int i = tid; i < 2 * RB * kH; i += kV4Threads) reinterpret_cast<float*>(xt)[i] = 0.0f;   // h_0 = 0
+    for (int i = tid; i < RB * kH; i += kV4Threads) reinterpret_cast<float*>(xt)[i] = 0.0f;   // h_0 = 0
     for (int i = tid; i < IBv * N; i += kV4Threads) {
         const int lb = i / N, n = i - lb * N;
         dem[lb * NP + n] = a.input[((b0 + lb) * N + n) * D + D - 1];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + L.bar + 120);
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(32 * sp) << 16);
-    constexpr uint32_t idescL = tc_idesc(128, RB), idescQ = tc_idesc(128, 32);
+    constexpr uint32_t idescL = tc_idesc_f16(128, RB), idescQ = tc_idesc(128, 32);
 
     if (warp >= 16) {
         // ============ streaming warps: warp 16 feeds the weight ring from L2, warp 17 issues every LSTM / query MMA.
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 const uint32_t st = c % STAGES;
                 mbar_wait(bar_empty + 8 * st, ((c / STAGES) & 1) ^ 1);
                 mbar_expect_tx(bar0 + 8 * st, kSlabBytes);
-                const float* src = u < kV3UsesQ ? a.WqTc + (size_t)u * kSlabFloats : a.WgT3 + (size_t)(u - kV3UsesQ) * kSlabFloats;
+                const float* src = u < kHUsesQ ? a.WqTh + (size_t)u * kSlabFloats : a.WgTh + (size_t)(u - kHUsesQ) * kSlabFloats;
                 bulk_g2s(ring_u32 + st * kSlabBytes, src, kSlabBytes, bar0 + 8 * st);
                 ++c;
             };
@@ -179,14 +179,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                     for (uint32_t j = c - pre; j < c; ++j) mbar_wait(bar0 + 8 * (j % STAGES), (j / STAGES) & 1);
                     break;
                 }
-                for (int u = pre; u < kV3UsesQ + kV3UsesG; ++u) issue(u);
-                pre = STAGES < kV3UsesQ ? STAGES : kV3UsesQ;
+                for (int u = pre; u < kHUsesQ + kHUsesG; ++u) issue(u);
+                pre = STAGES < kHUsesQ ? STAGES : kHUsesQ;
                 for (int u = 0; u < pre; ++u) issue(u);
             }
         } else if (warp == 17) {   // the whole warp runs the loop (uniform control flow), one elected lane issues
             uint32_t c = 0;
             int step = 0;
-            const uint64_t wdesc0 = tc_desc(ring_u32, 128, 256), xdesc_hi0 = VRP_XDESC(x_hi, 0), xdesc_lo0 = VRP_XDESC(x_lo, 0);
+            const uint64_t wdesc0 = tc_desc(ring_u32, 128, 256), xdesc_hi0 = VRP_XDESC_H(x_hi, 0), xdesc_lo0 = VRP_XDESC_H(x_lo, 0);
 #ifdef VRPB200_PHASE_CLOCKS
             long long ic_[6] = {0, 0, 0, 0, 0, 0}, ic_last_ = clock64();   // wait h', q: wait weights, q: issue, gates: wait weights, gates: throttle, gates: issue
 #define VRP_ICLK(i) do { const long long c_ = clock64(); ic_[i] += c_ - ic_last_; ic_last_ = c_; } while (0)
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 VRP_ICLK(0);
                 if (*stop_s) break;
 #pragma unroll 1
-                for (int u = 0; u < kV3UsesQ; ++u, ++c) {          // q^T[unit, row] = W_q^T . h^T  -> columns kQCol..
+                for (int u = 0; u < kHUsesQ; ++u, ++c) {          // q^T[unit, row] = W_q^T . h^T  -> columns kQCol..
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
                     tc_fence_after();
@@ -213,9 +213,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             const int kc = 2 * u + kk;
                             const uint64_t w_hi = w0 + (uint64_t)(kk * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
                             const uint64_t dx_hi = xdesc_hi0 + (uint64_t)(kc * 16), dx_lo = xdesc_lo0 + (uint64_t)(kc * 16);
-                            tc_mma_tf32(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
-                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
-                            tc_mma_tf32(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
+                            tc_mma_f16(tmem_base + kQCol, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_f16(tmem_base + kQCol, w_hi, dx_lo, idescL, 1);
+                            tc_mma_f16(tmem_base + kQCol, w_hi, dx_hi, idescL, 1);
                         }
                         tc_commit(bar_empty + 8 * st);
                     }
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 if (elect_one()) tc_commit(bar_q);
                 __syncwarp();
 #pragma unroll 1
-                for (int u = 0; u < kV3UsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
+                for (int u = 0; u < kHUsesG; ++u, ++c) {          // gates^T of the NEXT step, h part
                     const uint32_t st = c % STAGES;
                     mbar_wait(bar0 + 8 * st, (c / STAGES) & 1);
                     VRP_ICLK(3);
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         for (int mi = 0; mi < 2; ++mi) {
                             const uint64_t w_hi = w0 + (uint64_t)(mi * (8192 >> 4)), w_lo = w_hi + (4096 >> 4);
                             const uint32_t d = tmem_base + kGCol + RB * (2 * mp + mi);
-                            tc_mma_tf32(d, w_lo, dx_hi, idescL, kc > 0);
-                            tc_mma_tf32(d, w_hi, dx_lo, idescL, 1);
-                            tc_mma_tf32(d, w_hi, dx_hi, idescL, 1);
+                            tc_mma_f16(d, w_lo, dx_hi, idescL, kc > 0);
+                            tc_mma_f16(d, w_hi, dx_lo, idescL, 1);
+                            tc_mma_f16(d, w_hi, dx_hi, idescL, 1);
                         }
                         tc_commit(bar_empty + 8 * st);
                     }
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                                                __fmul_rn(sigmoid_fast(gg[0]), tanh_fast(gg[1])));
                     cst[i] = cn;
                     const float hn = __fmul_rn(tanh_fast(cn), sigmoid_fast(gg[3]));
-                    hi[i] = tf32_rna(hn);
+                    hi[i] = __half2float(__float2half_rn(hn));      // FP16 two-term split (common.cuh): hi, then lo = fp16(h - hi) at the store
                     lo[i] = hn - hi[i];
                 }
                 if (RPT > 4) {   // rotate the cell-state registers: the chunk just updated goes to the back
@@ -495,9 +495,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 transpose4(lo, lane);
                 {
                     const int rr = r0 + (lane & 3);
-                    const int off = (rr >> 3) * 4096 + (unit >> 2) * 128 + (rr & 7) * 16;
-                    *reinterpret_cast<float4*>(xt + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<float4*>(xt + RB * kH * 4 + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    // [row/8][k/8][row%8][k%8] halves: this lane holds units 4 (unit/4) .. +3 of row rr = 8 bytes
+                    const int off = (rr >> 3) * 2048 + (unit >> 3) * 128 + (rr & 7) * 16 + ((unit >> 2) & 1) * 8;
+                    const __half2 h01 = __floats2half2_rn(hi[0], hi[1]), h23 = __floats2half2_rn(hi[2], hi[3]);
+                    const __half2 l01 = __floats2half2_rn(lo[0], lo[1]), l23 = __floats2half2_rn(lo[2], lo[3]);
+                    *reinterpret_cast<uint2*>(xt + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                    *reinterpret_cast<uint2*>(xt + RB * kH * 2 + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
                 }
             }
             fence_proxy_async();

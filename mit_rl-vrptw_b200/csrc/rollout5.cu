@@ -6,7 +6,7 @@ namespace vrpb200 {
 
 int smem_rollout5(int rb, int n_nodes, int max_smem, int* stages) {
     if (rb > 48) return 1 << 30;                      // TMEM: gates^T, q^T, the cell state and the score buffers share 512 columns
-    *stages = make_layout5(rb, n_nodes, 3).total <= max_smem ? 3 : 2;
+    *stages = make_layout5(rb, n_nodes, 4).total <= max_smem ? 4 : make_layout5(rb, n_nodes, 3).total <= max_smem ? 3 : 2;   // 4 stages = all of W_q^T
     return make_layout5(rb, n_nodes, *stages).total;
 }
 
@@ -20,6 +20,7 @@ static cudaError_t go(const RolloutArgs& a, int grid, int smem, cudaStream_t st)
 
 template <int RB>
 static cudaError_t go_rb(const RolloutArgs& a, bool tw, int stages, int grid, int smem, cudaStream_t st) {
+    if (stages == 4) return tw ? go<RB, true, 4>(a, grid, smem, st) : go<RB, false, 4>(a, grid, smem, st);
     if (stages == 3) return tw ? go<RB, true, 3>(a, grid, smem, st) : go<RB, false, 3>(a, grid, smem, st);
     return tw ? go<RB, true, 2>(a, grid, smem, st) : go<RB, false, 2>(a, grid, smem, st);
 }

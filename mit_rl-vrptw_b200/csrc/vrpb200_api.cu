@@ -14,6 +14,7 @@
 #include <vector>
 
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "launchers.h"
 #include "standalone_kernels.cuh"
 #include "critic_kernels.cuh"
@@ -38,6 +39,7 @@ struct vrpb200_handle {
     const float* bg = nullptr;
     const float *WgT3 = nullptr, *WxT = nullptr, *bgT = nullptr;
     const float* WqTc[8] = {nullptr};
+    const float *WgTh = nullptr, *WqTh[8] = {nullptr};   // FP16 hi/lo tiles of W_h^T / W_q^T (rollout4/5)
     AttWeights att[8];
     AttWeights* d_gatt = nullptr;   // device copy of att[0..n_glimpses-1]
     float* d_critic = nullptr;      // critic constants (critic_kernels.cuh), null until set_weights saw Critic/* variables
@@ -232,6 +234,16 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     const size_t oWg = reserve((size_t)kGateSlabs * kSlabFloats);
     const size_t obg = reserve(4 * H);
     const size_t oWgT3 = reserve((size_t)kV3UsesG * kSlabFloats), oWxT = reserve(16 * H), obgT = reserve(4 * H);
+    const size_t oWgTh = reserve((size_t)kHUsesG * kSlabFloats);
+    // FP16 two-term split into a [128 units][K = 16] K-major tile (8 x 16-byte core matrices, as the TF32 tiles): hi at hi_off, lo 4 KB on
+    auto put_f16 = [&](size_t slab_float_off, int tile, int unit, int kl, float val) {
+        uint16_t* base = reinterpret_cast<uint16_t*>(&blob[slab_float_off]) + (size_t)tile * 4096;
+        const __half hh = __float2half_rn(val);
+        const __half ll = __float2half_rn(val - __half2float(hh));
+        const size_t idx = (size_t)(unit / 8) * 128 + (kl / 8) * 64 + (unit % 8) * 8 + (kl % 8);
+        base[idx] = __half_as_ushort(hh);
+        base[2048 + idx] = __half_as_ushort(ll);
+    };
     {
         std::vector<double> Wx((size_t)D1 * 4 * H, 0.0), bx(4 * H, 0.0);
         for (int col = 0; col < 4 * H; ++col) {
@@ -274,6 +286,13 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                         blob[oWgT3 + (size_t)u * kSlabFloats + mi * 2048 + 1024 + o] = lo;
                     }
         }
+        for (int u = 0; u < kHUsesG; ++u) {   // rollout4/5: the same tiles with K = 16 per k-chunk, FP16 hi/lo
+            const int kc = u >> 1, mp = u & 1;
+            for (int mi = 0; mi < 2; ++mi)
+                for (int unit = 0; unit < H; ++unit)
+                    for (int kl = 0; kl < 16; ++kl)
+                        put_f16(oWgTh + (size_t)u * kSlabFloats, mi, unit, kl, lstm_k[(size_t)(E + kc * 16 + kl) * 4 * H + (2 * mp + mi) * H + unit]);
+        }
         for (int m = 0; m < 4; ++m)
             for (int unit = 0; unit < H; ++unit) {
                 blob[obgT + m * H + unit] = (float)bx[m * H + unit];
@@ -281,7 +300,7 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                     blob[oWxT + (cc * 4 + m) * H + unit] = cc < D1 ? (float)Wx[(size_t)cc * 4 * H + m * H + unit] : 0.0f;
             }
     }
-    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc, Mq, cq; };
+    struct AttOff { size_t Wq, bq, A, gd, gl, gt, v, Au, ce, WqTc, Mq, cq, WqTh; };
     std::vector<AttOff> ao(natt);
     std::vector<std::vector<double>> Au_d(natt, std::vector<double>(4 * H, 0.0)), ce_d(natt, std::vector<double>(H, 0.0)), bq_d(natt, std::vector<double>(H, 0.0));
     for (int a = 0; a < natt; ++a) {
@@ -291,6 +310,12 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         o.bq = reserve(H); o.A = reserve(4 * H); o.gd = reserve(H); o.gl = reserve(H); o.gt = reserve(H);
         o.v = put(r.v, H); o.Au = reserve(4 * H); o.ce = reserve(H); o.Mq = reserve(4 * H); o.cq = reserve(H);
         o.WqTc = reserve((size_t)kV3UsesQ * kSlabFloats);
+        o.WqTh = reserve((size_t)kHUsesQ * kSlabFloats);
+        for (int u = 0; u < kHUsesQ; ++u)
+            for (int kk = 0; kk < 2; ++kk)
+                for (int n = 0; n < H; ++n)
+                    for (int kl = 0; kl < 16; ++kl)
+                        put_f16(o.WqTh + (size_t)u * kSlabFloats, kk, n, kl, r.pq_k[(size_t)((2 * u + kk) * 16 + kl) * H + n]);
         for (int u = 0; u < kV3UsesQ; ++u)
             for (int kk = 0; kk < 2; ++kk)
                 for (int n = 0; n < H; ++n)
@@ -368,11 +393,12 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     const float* d = h->d_blob;
     h->Wg = d + oWg;
     h->bg = d + obg;
-    h->WgT3 = d + oWgT3; h->WxT = d + oWxT; h->bgT = d + obgT;
+    h->WgT3 = d + oWgT3; h->WxT = d + oWxT; h->bgT = d + obgT; h->WgTh = d + oWgTh;
     for (int a = 0; a < natt; ++a) {
         h->att[a] = AttWeights{d + ao[a].Wq, d + ao[a].bq, d + ao[a].A, d + ao[a].gd, d + ao[a].gl, d + ao[a].gt,
                                d + ao[a].v, d + ao[a].Au, d + ao[a].ce, d + ao[a].Mq, d + ao[a].cq};
         h->WqTc[a] = d + ao[a].WqTc;
+        h->WqTh[a] = d + ao[a].WqTh;
         const RawOff& o = ro[a];
         RawAtt& ra = h->raw.att[a];
         ra.v = d + o.v;
@@ -495,9 +521,8 @@ enum Family { kFamFfma = 1, kFamV3 = 3, kFamV4 = 6, kFamV5 = 7 };
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
-    // gemm_path 0: rollout4 for large blocks of rows (48 or 32 rows per CTA), rollout5 when the batch is small enough for
-    // 16-row blocks (measured on B200: rollout5 is 7 % faster on VRP-10 x 128 / VRPTW-20 x 4096 and 20 % faster on
-    // VRPTW-100 sampling x 8192, rollout4 is 6 % faster on the 48-row blocks of large batches); beam search: rollout3
+    // gemm_path 0: rollout4 for greedy and stochastic decoding (with the FP16-split GEMMs it is as fast as or faster than
+    // rollout5 at every block size: profiles/r2_rows_per_cta_sweep.txt), rollout3 for beam search
     const bool automatic = c.gemm_path == 0;
     int fam = automatic ? kFamV4 : c.gemm_path;
     if (c.n_glimpses != 0 || c.physics != 0) fam = kFamFfma;   // the one fused kernel with glimpses / UPS_old physics
@@ -540,7 +565,6 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
         if (!RB) RB = smallest_fit;
     }
     if (!RB) return fail(h, VRPB200_E_ARG, "no rows_per_cta fits shared memory (n_nodes %d, beam_width %d)", c.n_nodes, a.W);
-    if (automatic && fam == kFamV4 && RB == 16 && smem_rollout5(16, c.n_nodes, h->max_smem_optin, &stages) <= h->max_smem_optin) fam = kFamV5;
     a.IB = RB / a.W;
     const int total = smem_of(RB);
     if (total > h->max_smem_optin)
@@ -587,6 +611,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.input = d_input; a.Wg = h->Wg; a.bg = h->bg; a.att = h->att[c.n_glimpses];
     a.WqTc = h->WqTc[c.n_glimpses];
     a.WgT3 = h->WgT3; a.WxT = h->WxT; a.bgT = h->bgT;
+    a.WqTh = h->WqTh[c.n_glimpses]; a.WgTh = h->WgTh;
     a.uniforms = d_uniforms; a.uniforms_retry = d_uniforms_retry;
     a.idx_out = d_idx; a.cost_out = d_cost; a.logprob_out = d_logprob;
     a.parent_out = mode == VRPB200_BEAM ? d_beam_parent : nullptr;

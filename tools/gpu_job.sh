@@ -1,11 +1,11 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 {
-timeout 100 python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups 2>&1 | tail -1
-timeout 100 python tools/time_variant.py libvrpb200.so auto 8192 stochastic uniform vrptw100 0 2>&1 | tail -1
-timeout 100 python tools/time_variant.py libvrpb200.so auto 4096 greedy uniform vrptw20 0 2>&1 | tail -1
-timeout 100 python tools/time_variant.py libvrpb200.so tc4x 128 greedy uniform vrp10 16 2>&1 | tail -1
-UPS=1 timeout 200 python tools/phase_clocks.py vrptw100 14208 tc4x 48 2>&1 | tail -32
-} > gpurun_out/r3b_qsplit.txt 2>&1
-cat gpurun_out/r3b_qsplit.txt
-timeout 900 python -m pytest tests/test_gpu_rollout.py -m gpu -q --timeout 120 --timeout-method=thread -x -k "tc4x or auto or fast" -p no:cacheprovider > gpurun_out/r3b_tests.log 2>&1; tail -4 gpurun_out/r3b_tests.log
+timeout 100 python tools/time_variant.py libvrpb200.so auto 128 greedy uniform vrp10 0 2>&1 | tail -1
+timeout 100 python tools/time_variant.py libvrpb200.so auto 2000 greedy uniform vrptw20 0 2>&1 | tail -1
+timeout 100 python tools/time_variant.py libvrpb200.so tc4x 2000 greedy uniform vrptw20 16 2>&1 | tail -1
+timeout 100 python tools/time_variant.py libvrpb200.so tc5 8192 stochastic uniform vrptw100 16 2>&1 | tail -1
+timeout 100 python tools/time_variant.py libvrpb200.so tc5 8192 stochastic uniform vrptw100 32 2>&1 | tail -1
+} > gpurun_out/r3d_small.txt 2>&1
+cat gpurun_out/r3d_small.txt
+timeout 1500 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread -x -p no:cacheprovider > gpurun_out/r3d_tests.log 2>&1; tail -5 gpurun_out/r3d_tests.log
