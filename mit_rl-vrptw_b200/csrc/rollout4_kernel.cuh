@@ -610,8 +610,12 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         bool v_cur = false, v_nx = false;
         const bool scoring = warp < NSW && g < ntiles;
         if (scoring) {
+            // split variant: the F tile of the group's tile number c (counted over all steps) lives in F buffer c & 1 and is
+            // gathered and staged by the warps of half c & 1 - the two warps of a pair take turns, so neither carries the
+            // gathers and the F stores of every tile
+            const int st0 = SPLIT ? (int)(c1_nq & 1) : 0;        // the half that stages the group's first tile of this step
             float fc[5];
-            load_item(g, r_cur, n_cur, v_cur, fc, half == 0);
+            load_item(g, r_cur, n_cur, v_cur, fc, half == st0);
             if (!DEEP) {
                 store_F(fgrp, fc);
                 __syncwarp();
@@ -623,16 +627,16 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                 __syncwarp();
             } else {   // the F tiles of the group's first two tiles of the step; warp 18 + g issues the MMAs
                 float f2[5];
-                load_item(g + NG, r_nx, n_nx, v_nx, f2, half == 0);
-                if (half == 0) {
+                load_item(g + NG, r_nx, n_nx, v_nx, f2, SPLIT ? half != st0 : half == 0);
+                if (half == st0) {
                     store_F(fgrp + (c1_nq & 1) * 2 * kC1TileBytes, fc);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bfrdy + 8 * (c1_nq & 1));
-                    if (g + NG < ntiles) {
-                        store_F(fgrp + ((c1_nq + 1) & 1) * 2 * kC1TileBytes, f2);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bfrdy + 8 * ((c1_nq + 1) & 1));
-                    }
+                }
+                if ((SPLIT ? half != st0 : half == 0) && g + NG < ntiles) {
+                    store_F(fgrp + ((c1_nq + 1) & 1) * 2 * kC1TileBytes, f2);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bfrdy + 8 * ((c1_nq + 1) & 1));
                 }
             }
         }
@@ -738,11 +742,16 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         __syncwarp();
                         VRP_CLK(9);
                         // the items two tiles ahead: row look-up and feature loads are scheduled into the arithmetic below
-                        if (qi == 0) load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn, half == 0);
+                        if (qi == 0) load_item(tile + 2 * NG, r_n2, n_n2, v_n2, fn, half == (int)par);      // (features: the half that will stage that tile)
                         quarter_arith(cur, brow + 32 * q, vsm + 32 * q, acc0, acc1);
                         VRP_CLK(10);
                     }
                     if (half == 1) {
+                        if (par == 1 && tile + 2 * NG < ntiles) {   // this half has seen quarter 3 complete: every MMA of the tile has read F
+                            store_F(fgrp + 2 * kC1TileBytes, fn);
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bfrdy + 8);
+                        }
                         if (c1_nq > 0) mbar_wait(bpack, (c1_nq - 1) & 1);   // the other half has taken the previous tile's sums
                         ps[par * 128 + m] = acc0 + acc1;
                         __syncwarp();
@@ -756,10 +765,10 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         n_eval += v_cur ? 1 : 0;
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar_tile + 8 * tile);   // the rows of this tile may be finished
-                        if (tile + 2 * NG < ntiles) {
-                            store_F(fgrp + par * 2 * kC1TileBytes, fn);
+                        if (par == 0 && tile + 2 * NG < ntiles) {
+                            store_F(fgrp, fn);
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(bfrdy + 8 * par);
+                            if (lane == 0) mbar_arrive(bfrdy);
                         }
                     }
                     VRP_CLK(8);
