@@ -1132,8 +1132,14 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                                 for (int draw = d0_; draw < d1_ && sel < 0; ++draw) {
                                     const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
                                     const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
-                                    float cum = 0.0f;   // tf.cumsum: sequential fp32 (masked nodes add exactly 0)
-                                    for (int n = 0; n < N; ++n) {
+                                    // tf.cumsum: sequential fp32 in node order.  Masked nodes have probability exactly 0 and cannot be
+                                    // the first node whose running sum exceeds u, so the scan runs over the row's item list (ascending
+                                    // node ids; every node when the row has no un-masked one) - same sums, a third of the serial adds
+                                    const unsigned char* itl = items + lrs * NP;
+                                    const int nal = nact_s[lrs];
+                                    float cum = 0.0f;
+                                    for (int k = 0; k < nal; ++k) {
+                                        const int n = itl[k];
                                         cum = __fadd_rn(cum, ulog[n]);
                                         if (cum > u) { sel = n; break; }
                                     }

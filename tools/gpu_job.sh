@@ -1,10 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 40 python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups > gpurun_out/r3h_psum.txt 2>&1 || { echo HUNG; cat gpurun_out/r3h_psum.txt | tail -3; exit 0; }
-{
-timeout 40 python tools/time_variant.py libvrpb200.so auto 8192 stochastic uniform vrptw100 0 2>&1 | tail -1
-timeout 40 python tools/time_variant.py libvrpb200.so auto 4096 greedy uniform vrptw20 0 2>&1 | tail -1
-UPS=1 timeout 60 python tools/phase_clocks.py vrptw100 14208 tc4x 48 2>&1 | tail -32
-} >> gpurun_out/r3h_psum.txt 2>&1
-cat gpurun_out/r3h_psum.txt
-timeout 300 python -m pytest tests/test_gpu_rollout.py -m gpu -q --timeout 60 --timeout-method=thread -x -k "tc4x or auto or fast" -p no:cacheprovider > gpurun_out/r3h_tests.log 2>&1; tail -4 gpurun_out/r3h_tests.log
+timeout 40 python tools/time_variant.py libvrpb200.so auto 8192 stochastic uniform vrptw100 0 > gpurun_out/r3i_samp.txt 2>&1 || { echo HUNG; tail -3 gpurun_out/r3i_samp.txt; exit 0; }
+timeout 40 python tools/time_variant.py libvrpb200.so auto 65536 stochastic uniform vrptw100 0 >> gpurun_out/r3i_samp.txt 2>&1
+cat gpurun_out/r3i_samp.txt
+timeout 300 python -m pytest tests/test_gpu_rollout.py tests/test_gpu_host_api.py -m gpu -q --timeout 60 --timeout-method=thread -x -k "stochastic or critic or train_step" -p no:cacheprovider > gpurun_out/r3i_tests.log 2>&1; tail -4 gpurun_out/r3i_tests.log
