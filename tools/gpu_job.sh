@@ -1,7 +1,8 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q --timeout 300 --timeout-method=thread -x -p no:cacheprovider > gpurun_out/r3j_tests.log 2>&1; tail -3 gpurun_out/r3j_tests.log
-timeout 300 python -m pytest tests/test_gpu_parity_large.py -m gpu -q -s -p no:cacheprovider 2>&1 | grep -E "^\[parity|passed|failed" > gpurun_out/r3j_agreement.txt; cat gpurun_out/r3j_agreement.txt
-python bench.py --steps 20 --warmup 3 > gpurun_out/r3j_bench_headline.json 2> gpurun_out/r3j_bench_headline.err; tail -2 gpurun_out/r3j_bench_headline.err; head -c 600 gpurun_out/r3j_bench_headline.json; echo
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r3j_bench_reference.json 2> gpurun_out/r3j_bench_reference.err; head -c 400 gpurun_out/r3j_bench_reference.json; echo
-python __graft_entry__.py smoke 2>&1 | tail -2
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r3k_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r3k_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r3k_ncu_bench.log 2>&1
+tail -2 gpurun_out/r3k_ncu_bench.log | head -c 300; echo
+python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups > gpurun_out/r3k_plain2.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:rollout4 -s 2 -c 1 -o gpurun_out/r3k_prof python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups > gpurun_out/r3k_ncu.log 2>&1
+tail -2 gpurun_out/r3k_ncu.log; ls -la gpurun_out/r3k_*
