@@ -54,7 +54,7 @@ WORKLOADS = {
     "vrptw50_greedy": ("vrptw50", False, "greedy", 1, 131072, 0, 512),
 }
 BASELINE_ORDER = ["vrp10_greedy", "vrptw20_greedy", "vrptw50_beam10", "vrptw100_stochastic", "ups_vrptw100_greedy"]
-KERNEL_NAMES = {1: "rollout_ffma_kernel", 3: "rollout3_kernel", 6: "rollout4_kernel", 7: "rollout5_kernel"}
+KERNEL_NAMES = {1: "rollout_ffma_kernel", 3: "rollout3_kernel", 6: "rollout4_kernel"}
 
 
 def parse():
@@ -248,7 +248,7 @@ def run_workload(a, pkg, name, rank, world, local_rank, dist):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms_total = float(tt.item())
     mean_cost = float(out.R.mean().item())
-    launches_per_step = 2 if eng.last_launch()["family"] in (6, 7) else 1   # rollout4/5: feature re-packing kernel + fused rollout kernel
+    launches_per_step = 2 if eng.last_launch()["family"] in (6,) else 1   # rollout4/5: feature re-packing kernel + fused rollout kernel
 
     # ---- end to end: host buffers in, host buffers out, every copy inside the timed region
     idx_host = torch.empty((T, R), dtype=torch.int32).pin_memory()
@@ -296,7 +296,7 @@ def run_workload(a, pkg, name, rank, world, local_rank, dist):
         #   live_rowsteps  live rows x executed steps: LSTM cell + query of a row that is still decoding (the GEMMs themselves
         #                  run over every row slot of a block, block_rowsteps; only live valid rows are counted as work)
         softmax = 0.0 if (decode_type == "greedy") else 1.0 * node_evals + 2.0 * live_rowsteps     # exp per item, log per row
-        if fam in (6, 7):
+        if fam in (6,):
             # 4 ex2 + ONE shared rcp per 4 tanh terms; LSTM gates 5 x (ex2 + rcp); greedy fast tail: no softmax
             mufu_ops = 1.25 * H * node_evals + 10.0 * H * live_rowsteps + softmax
         else:
@@ -306,7 +306,7 @@ def run_workload(a, pkg, name, rank, world, local_rank, dist):
         if fam == 1:
             fp32_ops = 8.0 * H * node_evals + gemm_macs                                            # everything on the FP32 pipe
             tensor_flops = 0.0
-        elif fam in (6, 7):
+        elif fam in (6,):
             fp32_ops = 7.25 * H * node_evals + 46.0 * H * live_rowsteps                            # add, clamp, +1, shared-reciprocal algebra (lane-ops; issued as packed FP32x2)
             tensor_flops = 3 * 2.0 * (gemm_macs + score_macs * 8.0 / 5.0)
             f16_flops = 3 * 2.0 * gemm_macs                                                        # LSTM / query GEMMs: kind::f16, two-term FP16 split (3 products)
@@ -331,7 +331,7 @@ def run_workload(a, pkg, name, rank, world, local_rank, dist):
         }
         for p in pipes.values():
             p["frac"] = (p["achieved"] / p["peak"]) if p["peak"] else 0.0
-        if fam in (6, 7):   # the GEMM part runs as kind::f16 (full bf16/fp16 rate), the score tiles as kind::tf32 (half rate)
+        if fam in (6,):   # the GEMM part runs as kind::f16 (full bf16/fp16 rate), the score tiles as kind::tf32 (half rate)
             pipes["tensor"]["frac"] = (f16_flops / tc_peak + (tensor_flops - f16_flops) / (tc_peak / 2.0)) / sec_step / 1e12
             pipes["tensor"]["note"] = ("issued flops incl. the 3-product splits: LSTM / query GEMMs as kind::f16 (FP16 hi/lo) at the measured bf16 peak, "
                                        "score tiles as kind::tf32 (3xTF32) at half of it; frac = busy fraction of the two combined")

@@ -69,10 +69,8 @@ typedef struct vrpb200_config {
                                 1 = everything on the FP32 pipe (independent cross-check of the tensor-core kernels),
                                 3 = rollout3 (transposed tcgen05 GEMMs, lock-step phases, fused beam search),
                                 6 = rollout4 (per-row item lists, fast greedy tail, shared-reciprocal tanh, deep MMA
-                                    buffering, 640 threads),
-                                7 = rollout5 (rollout4's score phase + dedicated warps that stream the per-row tails
-                                    behind the score tiles, setmaxnreg register split, cell state in TMEM, 768 threads).
-                                6 and 7 run beam search on rollout3. */
+                                    buffering, FP16-split LSTM / query GEMMs, 640 threads).
+                                6 also runs beam search on rollout3. */
     float capacity;
     float tanh_exploration;  /* C */
     float forget_bias;       /* BasicLSTMCell forget_bias, shared/decode_step.py:175 */

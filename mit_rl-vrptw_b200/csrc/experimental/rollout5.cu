@@ -1,5 +1,9 @@
 // Translation unit of rollout5 (gemm_path 7): the warp-specialised pipeline (score warps | aux warps | service warps).
-#include "launchers.h"
+// EXPERIMENT, not part of the build since the FP16-split GEMMs made rollout4 as fast or faster at every block size (DESIGN.md
+// section 4.3, profiles/r2_rows_per_cta_sweep.txt).  Bit-identical to rollout4 on the whole GPU suite when it was retired.
+// To build it again: move both files back to csrc/, declare smem_rollout5 / launch_rollout5 in launchers.h, add family 7 to
+// launch_rollout (vrpb200_api.cu) and "tc5": 7 to engine.GEMM_PATHS.
+#include "../launchers.h"
 #include "rollout5_kernel.cuh"
 
 namespace vrpb200 {

@@ -24,7 +24,7 @@
 // One synchronisation point per decode step: T0 = "h'(t) is in the X tiles and every row has moved"; both GEMMs of the step
 // are issued at T0, the gates GEMM (whose result is needed one step later) in the background of the score phase.
 #pragma once
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace vrpb200 {
 

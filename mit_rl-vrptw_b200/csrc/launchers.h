@@ -9,11 +9,9 @@ namespace vrpb200 {
 int smem_ffma(int rb, int ib, int n_nodes, int fd);
 int smem_rollout3(int rb, int ib, int n_nodes, int fd, int W, int max_smem, int* stages);
 int smem_rollout4(int rb, int n_nodes, int max_smem, int* stages);
-int smem_rollout5(int rb, int n_nodes, int max_smem, int* stages);
 
 cudaError_t launch_ffma(const RolloutArgs& a, int rb, bool tw, int grid, int smem, cudaStream_t st);
 cudaError_t launch_rollout3(const RolloutArgs& a, int rb, bool tw, int stages, int grid, int smem, cudaStream_t st);
 cudaError_t launch_rollout4(const RolloutArgs& a, int rb, bool tw, int stages, int grid, int smem, cudaStream_t st);
-cudaError_t launch_rollout5(const RolloutArgs& a, int rb, bool tw, int stages, int grid, int smem, cudaStream_t st);
 
 }  // namespace vrpb200

@@ -137,8 +137,8 @@ int vrpb200_create(const vrpb200_config* cfg, int device, vrpb200_handle** out) 
     if (c.embedding_dim < 1 || c.embedding_dim > 128) return fail(nullptr, VRPB200_E_ARG, "embedding_dim %d outside [1,128]", c.embedding_dim);
     if (c.decode_len < 1) return fail(nullptr, VRPB200_E_ARG, "decode_len must be >= 1");
     if (c.n_glimpses < 0 || c.n_glimpses > 7) return fail(nullptr, VRPB200_E_ARG, "n_glimpses outside [0,7]");
-    if (c.gemm_path != 0 && c.gemm_path != 1 && c.gemm_path != 3 && c.gemm_path != 6 && c.gemm_path != 7)
-        return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (default), 1 (FP32 pipe), 3 (rollout3), 6 (rollout4) or 7 (rollout5)");
+    if (c.gemm_path != 0 && c.gemm_path != 1 && c.gemm_path != 3 && c.gemm_path != 6)
+        return fail(nullptr, VRPB200_E_ARG, "gemm_path must be 0 (default), 1 (FP32 pipe), 3 (rollout3) or 6 (rollout4)");
     if (c.physics != VRPB200_PHYSICS_EUCLID && c.physics != VRPB200_PHYSICS_UPS_OLD) return fail(nullptr, VRPB200_E_ARG, "physics must be 0 (Euclidean) or 1 (UPS_old)");
     if (c.physics == VRPB200_PHYSICS_UPS_OLD && c.task != VRPB200_TASK_VRPTW) return fail(nullptr, VRPB200_E_ARG, "UPS_old physics is a VRPTW environment");
     if (c.rows_per_cta != 0 && c.rows_per_cta != 16 && c.rows_per_cta != 32 && c.rows_per_cta != 48 && c.rows_per_cta != 64)
@@ -516,20 +516,18 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
 namespace {
 
 // gemm_path -> kernel family.  0 picks the default (rollout4 split; beam search on rollout3).
-enum Family { kFamFfma = 1, kFamV3 = 3, kFamV4 = 6, kFamV5 = 7 };
+enum Family { kFamFfma = 1, kFamV3 = 3, kFamV4 = 6 };
 
 int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const vrpb200_config& c = h->cfg;
     const int FD = h->tw ? 4 : 2;
-    // gemm_path 0: rollout4 for greedy and stochastic decoding (with the FP16-split GEMMs it is as fast as or faster than
-    // rollout5 at every block size: profiles/r2_rows_per_cta_sweep.txt), rollout3 for beam search
+    // gemm_path 0: rollout4 for greedy and stochastic decoding, rollout3 for beam search
     const bool automatic = c.gemm_path == 0;
     int fam = automatic ? kFamV4 : c.gemm_path;
     if (c.n_glimpses != 0 || c.physics != 0) fam = kFamFfma;   // the one fused kernel with glimpses / UPS_old physics
-    if ((fam == kFamV4 || fam == kFamV5) && a.mode == 2) fam = kFamV3;
+    if (fam == kFamV4 && a.mode == 2) fam = kFamV3;
     int stages = 2;
     auto smem_of = [&](int rb) {
-        if (fam == kFamV5) return smem_rollout5(rb, c.n_nodes, h->max_smem_optin, &stages);
         if (fam == kFamV4) return smem_rollout4(rb, c.n_nodes, h->max_smem_optin, &stages);
         if (fam == kFamV3) return smem_rollout3(rb, rb / a.W, c.n_nodes, FD, a.W, h->max_smem_optin, &stages);
         return smem_ffma(rb, rb, c.n_nodes, FD);
@@ -544,7 +542,7 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     int RB = 0;
     if (c.rows_per_cta) {
         RB = c.rows_per_cta;
-        if ((fam == kFamV4 || fam == kFamV5) && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
+        if (fam == kFamV4 && RB > 48) RB = 48;   // rollout4 owns TMEM columns for q^T and the score buffers: at most 48 rows (a tuning knob only)
     } else if (a.mode != 2) {
         double best = 0.0;
         for (int i = 0; i < 4; ++i) {
@@ -572,11 +570,10 @@ int launch_rollout(vrpb200_handle* h, RolloutArgs& a, cudaStream_t st) {
     const long long grid = (a.B + a.IB - 1) / a.IB;
     if (grid > 0x7fffffffLL) return fail(h, VRPB200_E_ARG, "batch too large");
     h->last_launch[0] = (int)grid;
-    h->last_launch[1] = fam == kFamV5 ? 768 : fam == kFamV4 ? kV4Threads : fam == kFamV3 ? kV3Threads : RB * 8;
+    h->last_launch[1] = fam == kFamV4 ? kV4Threads : fam == kFamV3 ? kV3Threads : RB * 8;
     h->last_launch[2] = total; h->last_launch[3] = RB; h->last_launch[4] = 1; h->last_launch[5] = fam;
     cudaError_t e;
-    if (fam == kFamV5) e = launch_rollout5(a, RB, h->tw, stages, (int)grid, total, st);
-    else if (fam == kFamV4) e = launch_rollout4(a, RB, h->tw, stages, (int)grid, total, st);
+    if (fam == kFamV4) e = launch_rollout4(a, RB, h->tw, stages, (int)grid, total, st);
     else if (fam == kFamV3) e = launch_rollout3(a, RB, h->tw, stages, (int)grid, total, st);
     else e = launch_ffma(a, RB, h->tw, (int)grid, total, st);
     if (e != cudaSuccess) return fail(h, VRPB200_E_CUDA, "rollout launch (family %d, rows_per_cta %d): %s", fam, RB, cudaGetErrorString(e));
@@ -630,7 +627,7 @@ static int rollout_impl(vrpb200_handle* h, const float* d_input, int64_t B, int 
     a.gatt = h->d_gatt; a.n_glimpses = c.n_glimpses; a.mask_glimpses = c.mask_glimpses; a.physics = c.physics;
     a.q_Wq = h->att[0].Wq; a.q_bq = h->att[0].bq;   // module 0 = first glimpse, or the pointer when there is none
     const bool fp32_only = c.n_glimpses != 0 || c.physics != 0;   // glimpses and UPS_old physics live in the FP32-pipe kernel
-    if ((c.gemm_path == 0 || c.gemm_path >= 6) && mode != VRPB200_BEAM && !fp32_only) {   // rollout4 / rollout5 gather node features as aligned 16-byte records
+    if ((c.gemm_path == 0 || c.gemm_path >= 6) && mode != VRPB200_BEAM && !fp32_only) {   // rollout4 gathers node features as aligned 16-byte records
         const int slot = h->ws_slot;
         const long long nn = (long long)B * c.n_nodes;
         int rc = ensure(h, &h->ws_feat4[slot], &h->ws_feat4_bytes[slot], (size_t)nn * sizeof(float4));

@@ -49,7 +49,7 @@ class RolloutOutput:
 
 
 # fused-kernel families (vrpb200_config.gemm_path): the default, the FP32-pipe cross-check, rollout3, rollout4 (split)
-GEMM_PATHS = {"auto": 0, "ffma": 1, "tc3": 3, "tc4x": 6, "tc5": 7}
+GEMM_PATHS = {"auto": 0, "ffma": 1, "tc3": 3, "tc4x": 6}
 
 
 def _ptr(t: Optional[torch.Tensor]):

@@ -68,7 +68,7 @@ SPECIAL_CASES = [n for n, m in sorted(GOLDEN_INDEX.items())
 
 @pytest.mark.parametrize("name", FUSED_CASES)
 @pytest.mark.parametrize("rows_per_cta", [0, 64])
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc3", "ffma"])
 def test_rollout_matches_reference_fixture(name, rows_per_cta, gemm):
     fx, args, params = load_golden(name)
     meta = GOLDEN_INDEX[name]
@@ -121,7 +121,7 @@ def test_fast_path_equals_trace_path(name):
     assert int(fast.steps.max()) <= args["decode_len"]
 
 
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x"])
+@pytest.mark.parametrize("gemm", ["tc4x"])
 @pytest.mark.parametrize("task,B,seed,ups", [("vrptw100", 1500, 21, True), ("vrptw100", 700, 22, False), ("vrptw20", 900, 23, False),
                                              ("vrp50", 500, 24, False), ("vrp100", 300, 25, True), ("vrptw50", 777, 26, True)])
 def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
@@ -142,7 +142,7 @@ def test_plain_greedy_fast_tail_equals_exact_tail(gemm, task, B, seed, ups):
     assert torch.equal(fast.R, exact.R)
 
 
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x"])
+@pytest.mark.parametrize("gemm", ["tc4x"])
 def test_fast_tail_hands_rows_without_unmasked_node_to_the_exact_tail(gemm):
     """Time windows that close almost immediately: after its first customer a vehicle finds every other customer too late,
     returns to the depot, and there NO node is un-masked (the depot is masked while demand is left).  The reference then
@@ -175,7 +175,7 @@ def test_fast_tail_hands_rows_without_unmasked_node_to_the_exact_tail(gemm):
 @pytest.mark.parametrize("task,B,seed", [("vrp10", 128, 1), ("vrptw20", 512, 2), ("vrp20", 300, 3),
                                          ("vrptw50", 256, 4), ("vrp100", 96, 5), ("vrptw100", 200, 6)])
 @pytest.mark.parametrize("bias", [0.0, 0.3])
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc3", "ffma"])
 def test_greedy_vs_oracle_seeded(task, B, seed, bias, gemm):
     """Ragged batch sizes, every task size; per-instance comparison up to the first near-tie."""
     args = O.default_args(task)
@@ -226,7 +226,7 @@ def test_stochastic_given_uniforms_vs_oracle():
     np.testing.assert_allclose(out.logprobs.cpu().numpy()[:, agree], ref.logprobs[:, agree], rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3", "ffma"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc3", "ffma"])
 def test_stochastic_whole_batch_retry_is_the_reference_policy(gemm):
     """Opt-in whole-batch retry (attention_agent.py:148-167): when ANY row fails its first draw, EVERY row of the batch decides
     that step with the second set of uniforms.  Two draws are forced to fail (u = 2 > any CDF) at steps 0 and 3; the tours
@@ -292,7 +292,7 @@ def test_host_entry_point_equals_device_entry_point():
     np.testing.assert_array_equal(cost_h, out.R.cpu().numpy())
 
 
-@pytest.mark.parametrize("gemm", ["tc5", "tc4x", "tc3"])
+@pytest.mark.parametrize("gemm", ["tc4x", "tc3"])
 def test_tensor_core_path_equals_fp32_path_up_to_near_ties(gemm):
     """The tcgen05 (3xTF32 split) GEMMs against the FP32-pipe GEMMs of the same kernel: logits within 2e-6,
     identical tours except at near-ties, every rows_per_cta."""
