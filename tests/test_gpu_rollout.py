@@ -408,3 +408,23 @@ def test_errors_are_reported_not_thrown():
     p.pop("Actor/Decoder/Attention/v")
     with pytest.raises(pkg.VrpB200Error, match="Attention/v"):
         eng.set_weights(p)
+
+
+@pytest.mark.parametrize("task,B,want_rb", [("vrp10", 128, 16), ("vrptw20", 2000, 16), ("vrptw20", 4096, 32), ("vrptw100", 8192, 32),
+                                            ("vrptw50", 16384, 48), ("vrptw100", 30000, 48)])
+def test_rows_per_cta_follow_the_wave_cost_model(task, B, want_rb):
+    """The automatic block size minimises waves x (85 + rows) (profiles/r2_rows_per_cta_sweep.txt): 16-row blocks only while
+    they fit one wave, 32 rows for 4 096 / 8 192 instances, 48 rows for large batches - and the choice never changes a result."""
+    pkg = load_pkg()
+    args = O.default_args(task)
+    params = pkg.data.glorot_params(args, seed=3)
+    data = pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 4).astype(np.float32)
+    eng, torch = _engine(args, params)
+    x = torch.from_numpy(data).cuda()
+    out = eng.rollout(x, "greedy")
+    ll = eng.last_launch()
+    assert ll["rows_per_cta"] == want_rb and ll["family"] == 6 and ll["grid"] == -(-B // want_rb)
+    other = 48 if want_rb != 48 else 32
+    eng2, _ = _engine(args, params, rows_per_cta=other)
+    out2 = eng2.rollout(x, "greedy")
+    assert torch.equal(out.idxs, out2.idxs) and torch.equal(out.R, out2.R)
