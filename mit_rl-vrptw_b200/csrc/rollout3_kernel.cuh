@@ -546,6 +546,58 @@ __global__ void __launch_bounds__(kV3Threads, 1) rollout3_kernel(const RolloutAr
             for (int ib = warp; ib < IBv; ib += 16) {
                 const int wc = (t == 0) ? 1 : W;       // step 0: every beam is a copy of beam 0 (attention_agent.py:171)
                 const int ncand = wc * N;
+                constexpr int CPL = 20;                 // candidates per lane that fit registers (W x N <= 640: e.g. 10 beams x 51 nodes)
+                if (ncand <= 32 * CPL) {
+                    // candidates in registers (flat index c = lane + 32 j), one local (value, index) maximum per lane; per beam
+                    // slot one warp arg-max, then only the winning lane strikes its candidate and rescans its registers
+                    float cv[CPL];
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j) {
+                        const int c = lane + 32 * j;
+                        float v = __int_as_float(0x7fc00000);          // NaN: never selected
+                        if (c < ncand) {
+                            const int w = c / N, n = c - w * N;
+                            v = logits[(w * IB + ib) * NP + n];
+                            if (t > 0) v = __fadd_rn(v, prevlog_s[w * IB + ib]);
+                        }
+                        cv[j] = v;
+                    }
+                    auto local_best = [&](float& bv, int& bc) {
+                        bv = -INFINITY; bc = 0x7fffffff;
+#pragma unroll
+                        for (int j = 0; j < CPL; ++j) {
+                            const int c = lane + 32 * j;
+                            if (cv[j] > bv || (cv[j] == bv && c < bc)) { bv = cv[j]; bc = c; }   // (increasing c: first maximum wins)
+                        }
+                    };
+                    float lv; int lc;
+                    local_best(lv, lc);
+                    for (int k = 0; k < W; ++k) {
+                        float bv = lv; int bc = lc;
+#pragma unroll
+                        for (int o = 16; o; o >>= 1) {
+                            const float ov = __shfl_xor_sync(kFull, bv, o);
+                            const int oc = __shfl_xor_sync(kFull, bc, o);
+                            if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+                        }
+                        if (bc == 0x7fffffff) bc = 0;      // cannot happen (candidates are never all NaN), keeps indices in range
+                        const int w = bc / N, n = bc - w * N;
+                        if ((bc & 31) == lane) {           // the owner of the winner
+                            const int jj = bc >> 5;
+#pragma unroll
+                            for (int j = 0; j < CPL; ++j) if (j == jj) cv[j] = __int_as_float(0x7fc00000);
+                            local_best(lv, lc);
+                        }
+                        if (lane == 0) {
+                            const int nr = k * IB + ib;
+                            sel_idx_s[nr] = n;
+                            sel_par_s[nr] = w;
+                            sel_lp_s[nr] = logits[(w * IB + ib) * NP + n];
+                            reinterpret_cast<float*>(ftile)[nr] = bv; // new log-probability of beam nr, staged
+                        }
+                    }
+                    __syncwarp();
+                } else
                 for (int k = 0; k < W; ++k) {
                     float bv = -INFINITY;
                     int bc = 0x7fffffff;

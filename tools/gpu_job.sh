@@ -1,8 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r3k_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r3k_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r3k_ncu_bench.log 2>&1
-tail -2 gpurun_out/r3k_ncu_bench.log | head -c 300; echo
-python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups > gpurun_out/r3k_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:rollout4 -s 2 -c 1 -o gpurun_out/r3k_prof python tools/time_variant.py libvrpb200.so tc4x 14208 greedy ups > gpurun_out/r3k_ncu.log 2>&1
-tail -2 gpurun_out/r3k_ncu.log; ls -la gpurun_out/r3k_*
+timeout 300 python -m pytest tests -m gpu -q --timeout 100 --timeout-method=thread -x -k "beam" -p no:cacheprovider > gpurun_out/r3n_tests.log 2>&1; tail -3 gpurun_out/r3n_tests.log
+BEAM=10 timeout 120 python tools/phase_clocks.py vrptw50 2960 tc3 0 > gpurun_out/r3n_beam_clocks.txt 2>&1
+cat gpurun_out/r3n_beam_clocks.txt | tail -8
+timeout 200 python bench.py --workload vrptw50_beam10 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r3n_bench_beam.json 2>gpurun_out/r3n_bench_beam.err; head -c 300 gpurun_out/r3n_bench_beam.json; echo

@@ -15,16 +15,19 @@ L.LIB_PATH = so
 L._lib = None
 _ = 0
 task, B, gemm, rb = sys.argv[1], int(sys.argv[2]), sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0
+W = int(os.environ.get("BEAM", "0"))          # BEAM=10: beam search with 10 beams (rollout3)
 args = pkg.task_specific_params.default_args(task)
 eng = pkg.Engine(args, gemm=gemm, rows_per_cta=rb)
 eng.set_weights(pkg.data.glorot_params(args, 1))
 x = torch.from_numpy(pkg.data.create_dataset(args["task_name"], B, args["n_cust"], 2, ups=bool(os.environ.get("UPS"))).astype(np.float32)).cuda()
-eng.rollout(x)
+eng.rollout(x, "beam_search", beam_width=W) if W else eng.rollout(x)
 stats = torch.zeros(64, dtype=torch.int64, device="cuda")
 tr = L.Trace(); tr.d_stats = stats.data_ptr()
-idx = torch.empty((eng.T, B), dtype=torch.int32, device="cuda"); cost = torch.empty(B, device="cuda")
-rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 0, 1, None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
-                             C.c_void_p(cost.data_ptr()), None, None, C.byref(tr), None)
+RW = B * max(W, 1)
+idx = torch.empty((eng.T, RW), dtype=torch.int32, device="cuda"); cost = torch.empty(RW, device="cuda")
+par = torch.empty((eng.T, RW), dtype=torch.int32, device="cuda")
+rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 2 if W else 0, max(W, 1), None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
+                             C.c_void_p(cost.data_ptr()), None, C.c_void_p(par.data_ptr()) if W else None, C.byref(tr), None)
 torch.cuda.synchronize()
 s = stats.cpu().numpy()
 blocksteps = s[2] / eng.last_launch()["rows_per_cta"]
