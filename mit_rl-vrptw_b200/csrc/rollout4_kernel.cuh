@@ -389,8 +389,10 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
         build_alive(lr < IBv ? lr : 0, lr < IBv, sub, sl);
     }
     // the fast per-row tail serves plain greedy decoding when nobody reads probabilities, log-probabilities or masks
-    const bool fastk = a.mode == 0 && !a.full && a.mask_pointer && !a.use_tanh && a.logprob_out == nullptr && a.fin_mask == nullptr &&
-                       a.tr_logits == nullptr && a.tr_probs == nullptr && a.tr_masks == nullptr;
+    // (sampling takes it too: the soft-max is then always evaluated - in the exact tail's summation order, so both tails draw
+    //  the same node from the same uniform - and log-probabilities may be requested)
+    const bool fastk = !a.full && a.mask_pointer && !a.use_tanh && a.fin_mask == nullptr && a.tr_logits == nullptr && a.tr_probs == nullptr &&
+                       a.tr_masks == nullptr && (a.mode == 0 ? a.logprob_out == nullptr : a.mode == 1);
     const int unit = 32 * sp + lane;
     float cst[RPT];
 #pragma unroll
@@ -910,7 +912,9 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                     }
                     handled = !__any_sync(kFull, live && fl != 0);
-                    if (handled && __any_sync(kFull, live && second > mx - 1e-5f)) {
+                    const bool sampling = a.mode != 0;
+                    float psel = 1.0f;
+                    if (handled && (sampling || __any_sync(kFull, live && second > mx - 1e-5f))) {
                         // near-tie: the reference takes argmax(prob) (attention_agent.py:146-147) and two close logits may round
                         // to one probability, so evaluate the probabilities exactly as the exact tail does (masked nodes have
                         // probability 0 and add 0 to the denominator; the mask bytes are kept as un-masked / masked flags)
@@ -942,15 +946,42 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             if (n < N) {
                                 const float p = (live && mk[n] == 0) ? expf((ulog[n] - mx) - lse) : 0.0f;
                                 if (p > bestp) { bestp = p; besti = n; }
+                                if (sampling && live) ulog[n] = p;      // probabilities for the sequential CDF below
                             }
                         }
+                        if (!sampling) {
 #pragma unroll
-                        for (int o = LPR / 2; o; o >>= 1) {
-                            const float ov = __shfl_xor_sync(kFull, bestp, o);
-                            const int oi = __shfl_xor_sync(kFull, besti, o);
-                            if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+                            for (int o = LPR / 2; o; o >>= 1) {
+                                const float ov = __shfl_xor_sync(kFull, bestp, o);
+                                const int oi = __shfl_xor_sync(kFull, besti, o);
+                                if (ov > bestp || (ov == bestp && oi < besti)) { bestp = ov; besti = oi; }
+                            }
+                            mxi = besti;
+                        } else {   // inverse-CDF sampling (attention_agent.py:148-167), as in the exact tail: sequential fp32 sums over the items
+                            __syncwarp();
+                            int sel = -1;
+                            if (sl == 0 && live) {
+                                const long long o = (long long)t * R + row;
+                                int d0_, d1_;
+                                draw_range(a, t, d0_, d1_);
+                                for (int draw = d0_; draw < d1_ && sel < 0; ++draw) {
+                                    const float* ubuf = draw ? a.uniforms_retry : a.uniforms;
+                                    const float u = ubuf ? ubuf[o] : counter_uniform(a.seed, t, a.row_base + row, draw);
+                                    float cum = 0.0f;
+                                    for (int k = 0; k < na; ++k) {
+                                        const int n = it[k];
+                                        cum = __fadd_rn(cum, ulog[n]);
+                                        if (cum > u) { sel = n; break; }
+                                    }
+                                }
+                                if (sel < 0 && a.fail_steps && d0_ == 0) a.fail_steps[t] = 1;
+                            }
+                            if (sel < 0) sel = 0;
+                            mxi = __shfl_sync(kFull, sel, sub * LPR);
+                            __syncwarp();
+                            psel = ulog[mxi < N ? mxi : 0];
+                            __syncwarp();
                         }
-                        mxi = besti;
                     }
                     VRP_CLK(15);
                     if (handled) {
@@ -982,6 +1013,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             reinterpret_cast<int*>(rs)[8] = done_now;
                             rs[9] = sx; rs[10] = sy; rs[11] = sb; rs[12] = se_tw; rs[13] = nz; rs[15] = dep;
                             a.idx_out[(long long)t * R + row] = idx;
+                            if (a.logprob_out) a.logprob_out[(long long)t * R + row] = logf(psel);
                         }
                         VRP_CLK(16);
                         // (3) customers with demand left -> new list; those that are feasible (vehicle not empty, time window

@@ -428,3 +428,29 @@ def test_rows_per_cta_follow_the_wave_cost_model(task, B, want_rb):
     eng2, _ = _engine(args, params, rows_per_cta=other)
     out2 = eng2.rollout(x, "greedy")
     assert torch.equal(out.idxs, out2.idxs) and torch.equal(out.R, out2.R)
+
+
+@pytest.mark.parametrize("task,B,seed,ups", [("vrptw100", 1500, 31, True), ("vrptw100", 700, 32, False), ("vrptw20", 900, 33, False),
+                                             ("vrp50", 500, 34, False), ("vrptw50", 777, 35, True)])
+def test_sampling_fast_tail_equals_exact_tail(task, B, seed, ups):
+    """Sampling without traces / final state runs rollout4's fast per-row tail (soft-max in the exact tail's summation order,
+    CDF over the item list, feasibility only for customers with demand left).  Given the same uniforms - the caller's or the
+    in-kernel stream's - it must draw the same nodes, costs and log-probabilities as the exact tail, bit for bit."""
+    pkg = load_pkg()
+    args = O.default_args(task)
+    params = pkg.data.glorot_params(args, seed=seed)
+    data = pkg.data.create_dataset(args["task_name"], B, args["n_cust"], seed, ups=ups).astype(np.float32)
+    eng, torch = _engine(args, params)
+    x = torch.from_numpy(data).cuda()
+    rnd = np.random.RandomState(seed)
+    T = args["decode_len"]
+    u1, u2 = rnd.uniform(size=(T, B)).astype(np.float32), rnd.uniform(size=(T, B)).astype(np.float32)
+    for kw in (dict(uniforms=u1, uniforms_retry=u2), dict(seed=7)):
+        fast = eng.rollout(x, "stochastic", want_logprobs=True, **kw)
+        plain = eng.rollout(x, "stochastic", **kw)
+        exact = eng.rollout(x, "stochastic", want_logprobs=True, final_state=True, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(fast.idxs, exact.idxs) and torch.equal(plain.idxs, exact.idxs)
+        assert torch.equal(fast.R, exact.R) and torch.equal(plain.R, exact.R)
+        assert torch.equal(fast.logprobs, exact.logprobs)
+    assert (fast.idxs != eng.rollout(x, "stochastic", seed=8).idxs).any()      # another seed, another sample

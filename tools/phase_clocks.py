@@ -26,7 +26,8 @@ tr = L.Trace(); tr.d_stats = stats.data_ptr()
 RW = B * max(W, 1)
 idx = torch.empty((eng.T, RW), dtype=torch.int32, device="cuda"); cost = torch.empty(RW, device="cuda")
 par = torch.empty((eng.T, RW), dtype=torch.int32, device="cuda")
-rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, 2 if W else 0, max(W, 1), None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
+MODE = 1 if os.environ.get("STOCHASTIC") else (2 if W else 0)     # STOCHASTIC=1: sampling with the in-kernel stream
+rc = eng.lib.vrpb200_rollout(eng.handle, C.c_void_p(x.data_ptr()), B, MODE, max(W, 1), None, None, C.c_uint64(0), C.c_void_p(idx.data_ptr()),
                              C.c_void_p(cost.data_ptr()), None, C.c_void_p(par.data_ptr()) if W else None, C.byref(tr), None)
 torch.cuda.synchronize()
 s = stats.cpu().numpy()
