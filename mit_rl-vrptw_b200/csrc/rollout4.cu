@@ -11,12 +11,17 @@ int smem_rollout4(int rb, int n_nodes, int max_smem, int* stages) {
     return make_layout4(rb, n_nodes, *stages, 17).total;
 }
 
+template <int RB, bool TW, int STAGES, bool SAMP>
+static cudaError_t go2(const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, 16, true, SAMP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    rollout4_kernel<RB, TW, STAGES, 16, true, SAMP><<<grid, kV4Threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int RB, bool TW, int STAGES>
 static cudaError_t go(const RolloutArgs& a, int grid, int smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(rollout4_kernel<RB, TW, STAGES, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) return e;
-    rollout4_kernel<RB, TW, STAGES, 16, true><<<grid, kV4Threads, smem, st>>>(a);
-    return cudaGetLastError();
+    return a.mode == 1 ? go2<RB, TW, STAGES, true>(a, grid, smem, st) : go2<RB, TW, STAGES, false>(a, grid, smem, st);
 }
 
 template <int RB>

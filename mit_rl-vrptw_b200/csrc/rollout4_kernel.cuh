@@ -63,7 +63,9 @@ __host__ __device__ inline Smem4 make_layout4(int RB, int N, int stages, int nsw
 //   16 + SPLIT -> every warp scores, in 2 groups of 8 warps with the deep buffering of the 8-warp variant: the two warps of a
 //         TMEM sub-partition share the 32 items of a tile and take hidden units 0..63 / 64..127 (partial sums meet in
 //         shared memory and are added in a fixed order); then every warp runs the per-row tail
-template <int RB, bool TW, int STAGES, int NSW, bool SPLIT>
+// SAMP: the kernel launched for sampling (its fast per-row tail evaluates the soft-max and the CDF; the greedy kernel carries
+// none of that code in its step loop - measured: 1.5 % of the greedy step)
+template <int RB, bool TW, int STAGES, int NSW, bool SPLIT, bool SAMP>
 __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_constant__ RolloutArgs a) {
     constexpr int NT = 512, RPW = RB / 16, RPT = RB / 4, FD = TW ? 4 : 2;
     constexpr bool DEEP = NSW == 8 || SPLIT;                     // 4 TMEM buffers + 2 F tiles per group, MMAs issued by warps 18/19
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
     // (sampling takes it too: the soft-max is then always evaluated - in the exact tail's summation order, so both tails draw
     //  the same node from the same uniform - and log-probabilities may be requested)
     const bool fastk = !a.full && a.mask_pointer && !a.use_tanh && a.fin_mask == nullptr && a.tr_logits == nullptr && a.tr_probs == nullptr &&
-                       a.tr_masks == nullptr && (a.mode == 0 ? a.logprob_out == nullptr : a.mode == 1);
+                       a.tr_masks == nullptr && (SAMP ? a.mode == 1 : (a.mode == 0 && a.logprob_out == nullptr));
     const int unit = 32 * sp + lane;
     float cst[RPT];
 #pragma unroll
@@ -912,7 +914,7 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                         if (ov > mx || (ov == mx && oi < mxi)) { mx = ov; mxi = oi; }
                     }
                     handled = !__any_sync(kFull, live && fl != 0);
-                    const bool sampling = a.mode != 0;
+                    constexpr bool sampling = SAMP;
                     float psel = 1.0f;
                     if (handled && (sampling || __any_sync(kFull, live && second > mx - 1e-5f))) {
                         // near-tie: the reference takes argmax(prob) (attention_agent.py:146-147) and two close logits may round
