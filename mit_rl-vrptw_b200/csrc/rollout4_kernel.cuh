@@ -929,10 +929,11 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
                             const int nb = sl + 32 * k;
                             float ev[4];
 #pragma unroll
-                            for (int qv = 0; qv < 4; ++qv) {
-                                const int n = nb + 8 * qv;
-                                const bool um = n < N && live && mk[n < N ? n : 0] == 0;
-                                ev[qv] = um ? expf(ulog[n] - mx) : 0.0f;
+                            for (int qv = 0; qv < 4; ++qv) {   // branch-free: loads and expf for every slot, then a select (the
+                                const int n = nb + 8 * qv;       // branchy form re-derived the shared-memory window per element)
+                                const int nn = n < N ? n : N - 1;
+                                const float e = expf(ulog[nn] - mx);
+                                ev[qv] = (n < N && live && mk[nn] == 0) ? e : 0.0f;
                             }
                             P0 = __fadd_rn(P0, ev[0]); P1 = __fadd_rn(P1, ev[1]); P2 = __fadd_rn(P2, ev[2]); P3 = __fadd_rn(P3, ev[3]);
                         }
@@ -945,11 +946,11 @@ __global__ void __launch_bounds__(kV4Threads, 1) rollout4_kernel(const __grid_co
 #pragma unroll 1
                         for (int j = 0; j < NJ; ++j) {
                             const int n = sl + LPR * j;
-                            if (n < N) {
-                                const float p = (live && mk[n] == 0) ? expf((ulog[n] - mx) - lse) : 0.0f;
-                                if (p > bestp) { bestp = p; besti = n; }
-                                if (sampling && live) ulog[n] = p;      // probabilities for the sequential CDF below
-                            }
+                            const int nn = n < N ? n : N - 1;
+                            const float e = expf((ulog[nn] - mx) - lse);
+                            const float p = (n < N && live && mk[nn] == 0) ? e : 0.0f;
+                            if (n < N && p > bestp) { bestp = p; besti = n; }
+                            if (sampling && live && n < N) ulog[n] = p;      // probabilities for the sequential CDF below
                         }
                         if (!sampling) {
 #pragma unroll
