@@ -679,15 +679,10 @@ class RLAgent(object):
             B = pnt.shape[0]
             inst = torch.arange(R, device=idx.device) % B               # instance of beam-major row w*B + b
             actions = pnt[inst[None, :].expand(T, R), idx]              # [T, R, D-1]
-            if decode_type == 'beam_search':                            # back-tracking, attention_agent.py:222-231
+            if decode_type == 'beam_search':
                 par = out.beam_parents.long()
                 self.last_beam_path = [p[:, None] for p in par]
-                ind = torch.arange(R, device=idx.device)
-                bt = [None] * T
-                for k in reversed(range(T)):
-                    bt[k] = actions[k][ind]
-                    ind = (inst + B * par[k])[ind]
-                actions = torch.stack(bt)
+                actions = torch.stack(self._backtrack(list(actions), list(par), B))
             R_out = self._reward(list(actions), pnt, W) if self.args.get('min_trucks') else out.R
             v = self._critic_value(decode_type)
             return (R_out, v, list(out.logprobs) if want_logprobs else None, list(actions), [i[:, None] for i in idx], pnt, None)
@@ -709,83 +704,101 @@ class RLAgent(object):
             return self.reward_func(actions, self.args['decode_len'], self.args['n_nodes'] - 1, depot)
         return self.reward_func(actions)
 
-    def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs):
-        """The reference loop, line for line, on device tensors (attention_agent.py:89-240)."""
+    # -- the step-by-step route: one decode_step / env_step launch per step ---------------------------
+    # Serves what the persistent kernels do not return or combine: per-step probability tables (want_probs) and beam search
+    # together with glimpses or UPS_old physics.  Semantics of attention_agent.py:89-240; rows are beam-major (row = w*B + b).
+    @staticmethod
+    def _pick_greedy(prob):
+        """argmax over the probabilities, first maximal index (:146-147)."""
         import torch
+        return torch.argmax(prob, 1, keepdim=True), None
+
+    def _pick_sampled(self, prob, step, uniforms, uniforms_retry):
+        """Inverse-CDF draw (:148-167): the first node whose running sum exceeds the row's uniform; if ANY row finds none,
+        every row redraws once with the second set of uniforms; a row failing again takes node 0."""
+        import torch
+        rows, n_nodes = prob.shape
+        cdf = torch.cumsum(prob, 1)
+
+        def draw(table):
+            u = (torch.as_tensor(table[step]) if table is not None else torch.rand(rows)).to(prob.device)[:, None]
+            beyond = ~(cdf > u)                                   # nodes whose running sum has not passed u yet
+            return beyond.all(1), beyond.long().sum(1, keepdim=True).clamp_(max=n_nodes - 1) * (~beyond.all(1, keepdim=True)).long()
+
+        failed, idx = draw(uniforms)
+        if bool(failed.any()):
+            failed, idx = draw(uniforms_retry)
+        return idx, None
+
+    def _pick_beam(self, prob, step, batch, width, carried):
+        """Per instance the `width` best of (log-probability so far + log prob) over width x n_nodes candidates (:169-205);
+        ties go to the lower flat index (tf.nn.top_k), step 0 looks at beam 0 only; returns node, parent beam, the parents'
+        probability rows and the new running log-probabilities."""
+        import torch
+        n_nodes = prob.shape[1]
+        if step == 0:
+            cand = torch.log(prob[:batch])
+        else:
+            cand = (torch.log(prob) + carried).view(width, batch, n_nodes).permute(1, 0, 2).reshape(batch, width * n_nodes)
+        order = torch.sort(cand, dim=1, descending=True, stable=True)[1][:, :width]         # [B, W], stable = lower index first
+        flat = order.t().reshape(-1, 1)                                                     # beam-major rows
+        score = torch.gather(cand, 1, order).t().reshape(-1, 1)
+        node, parent = flat % n_nodes, flat // n_nodes
+        src = (torch.arange(batch, device=prob.device).repeat(width)[:, None] + batch * parent)[:, 0]
+        return node, parent, prob[src], score
+
+    @staticmethod
+    def _backtrack(per_step, parents, batch):
+        """attention_agent.py:222-231: follow the parent pointers from the last step to the first, so that row r of every
+        step belongs to the beam that ENDS in row r.  per_step: list of [R, ...] tensors, parents: list of [R, 1] or [R]."""
+        import torch
+        rows = per_step[0].shape[0]
+        inst = torch.arange(rows, device=per_step[0].device) % batch
+        at = torch.arange(rows, device=per_step[0].device)
+        out = [None] * len(per_step)
+        for k in reversed(range(len(per_step))):
+            out[k] = per_step[k][at]
+            at = (inst + batch * parents[k].reshape(-1))[at]
+        return out
+
+    def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs):
+        import torch
+        if decode_type not in ('greedy', 'stochastic', 'beam_search'):
+            raise ValueError(decode_type)
         args, env = self.args, self.env
-        input_pnt = env.input_pnt
-        batch_size = input_pnt.shape[0]
-        dev = input_pnt.device
-        encoder_emb_inp = self.embedder_model(input_pnt.contiguous())                     # :96
-        beam_width = args['beam_width'] if decode_type == 'beam_search' else 1             # :98-102
-        self.beam_width = beam_width
-        env.reset(beam_width)                                                              # :110
-        R_ = batch_size * beam_width
-        BatchSequence = torch.arange(R_, device=dev)[:, None]                              # :112-114
-        actions_tmp, logprobs, probs, idxs = [], [], [], []
-        H = args['hidden_dim']
-        decoder_state = (torch.zeros(R_, H, device=dev), torch.zeros(R_, H, device=dev))   # :126-129
-        decoder_input = encoder_emb_inp[:, env.n_nodes - 1:env.n_nodes].repeat(beam_width, 1, 1)   # :133-134
-        context = encoder_emb_inp.repeat(beam_width, 1, 1)                                 # :137
-        BatchBeamSeq = torch.arange(batch_size, device=dev).repeat(beam_width)[:, None]
-        beam_path, log_beam_probs = [], []
-        pnt_t = input_pnt.repeat(beam_width, 1, 1)
-        for i in range(args['decode_len']):
-            logit, prob, logprob, decoder_state = self.decodeStep.step(decoder_input, context, env, decoder_state)   # :140
-            beam_parent = None
+        points = env.input_pnt
+        batch, dev = points.shape[0], points.device
+        width = args['beam_width'] if decode_type == 'beam_search' else 1
+        self.beam_width = width
+        rows = batch * width
+        emb = self.embedder_model(points.contiguous())
+        env.reset(width)
+        context, tiled_points = emb.repeat(width, 1, 1), points.repeat(width, 1, 1)
+        state = (torch.zeros(rows, args['hidden_dim'], device=dev), torch.zeros(rows, args['hidden_dim'], device=dev))
+        dec_in = context[:, env.n_nodes - 1:env.n_nodes]                  # the depot's embedding is the first decoder input
+        every = torch.arange(rows, device=dev)
+        visited, logprobs, probs, idxs, parents, carried = [], [], [], [], [], None
+        for step in range(args['decode_len']):
+            _, prob, _, state = self.decodeStep.step(dec_in, context, env, state)
             if decode_type == 'greedy':
-                idx = torch.argmax(prob, 1, keepdim=True)                                  # :147
-            elif decode_type == 'stochastic':                                             # :148-167
-                def my_multinomial(u):
-                    cum = torch.cumsum(prob, 1)
-                    rand = u[:, None].to(dev).expand(-1, env.n_nodes)
-                    sorted_ind = torch.arange(env.n_nodes, device=dev)[None, :].expand(R_, -1)
-                    tmp = (cum > rand).long() * sorted_ind + 10000 * (rand >= cum).long()
-                    return tmp, torch.argmin(tmp, 1, keepdim=True)
-                u1 = torch.as_tensor(uniforms[i]) if uniforms is not None else torch.rand(R_)
-                tmp, idx = my_multinomial(u1)
-                if bool((tmp.sum(1) > 10000 * env.n_nodes - 1).any()):
-                    u2 = torch.as_tensor(uniforms_retry[i]) if uniforms_retry is not None else torch.rand(R_)
-                    tmp, idx = my_multinomial(u2)
-            elif decode_type == 'beam_search':                                            # :169-205
-                if i == 0:
-                    log_beam_prob = torch.log(prob[:batch_size])
-                else:
-                    log_beam_prob = torch.log(prob) + log_beam_probs[-1]
-                    log_beam_prob = torch.cat(torch.split(log_beam_prob, batch_size, 0), 1)
-                # tf.nn.top_k orders ties by lower index: stable descending sort
-                order = torch.sort(log_beam_prob, dim=1, descending=True, stable=True)[1][:, :beam_width]
-                topk_logprob_val = torch.gather(log_beam_prob, 1, order)
-                topk_logprob_val = topk_logprob_val.t().reshape(-1, 1)
-                topk_logprob_ind = order.t().reshape(-1, 1)
-                idx = topk_logprob_ind % env.n_nodes
-                beam_parent = topk_logprob_ind // env.n_nodes
-                batchedBeamIdx = BatchBeamSeq + batch_size * beam_parent
-                prob = prob[batchedBeamIdx[:, 0]]
-                beam_path.append(beam_parent)
-                log_beam_probs.append(topk_logprob_val)
+                idx, parent = self._pick_greedy(prob)
+            elif decode_type == 'stochastic':
+                idx, parent = self._pick_sampled(prob, step, uniforms, uniforms_retry)
             else:
-                raise ValueError(decode_type)
-            env.step(idx, beam_parent)                                                     # :207
-            batched_idx = idx[:, 0]
-            decoder_input = context[BatchSequence[:, 0], batched_idx][:, None, :]          # :211-212
-            logprobs.append(torch.log(prob[BatchSequence[:, 0], batched_idx]))             # :214
+                idx, parent, prob, carried = self._pick_beam(prob, step, batch, width, carried)
+                parents.append(parent)
+            env.step(idx, parent)
+            chosen = idx[:, 0]
+            dec_in = context[every, chosen][:, None, :]
+            logprobs.append(torch.log(prob[every, chosen]))
             probs.append(prob)
             idxs.append(idx)
-            actions_tmp.append(pnt_t[BatchSequence[:, 0], batched_idx])                    # :219
-        if decode_type == 'beam_search':                                                   # :222-231
-            tmplst = []
-            tmpind = [BatchSequence]
-            for k in reversed(range(len(actions_tmp))):
-                tmplst = [actions_tmp[k][tmpind[-1][:, 0]]] + tmplst
-                tmpind += [(BatchBeamSeq + batch_size * beam_path[k])[tmpind[-1][:, 0]]]
-            actions = tmplst
-        else:
-            actions = actions_tmp
-        self.last_beam_path = beam_path
-        R = self._reward(actions, input_pnt, beam_width)                                   # :236-240
+            visited.append(tiled_points[every, chosen])
+        actions = self._backtrack(visited, parents, batch) if decode_type == 'beam_search' else visited
+        self.last_beam_path = parents
+        R = self._reward(actions, points, width)
         v = self._critic_value(decode_type)
-        return (R, v, logprobs, actions, idxs, input_pnt, probs if want_probs else None)
+        return (R, v, logprobs, actions, idxs, points, probs if want_probs else None)
 
     # -- evaluation ------------------------------------------------------------------------------
     def evaluate_batch(self, eval_type='greedy', backend="auto"):
