@@ -163,3 +163,55 @@ def test_result_file_format(tmp_path):
     assert vals == depot + c1 + depot + c2 + depot        # stops after the second customer, then the depot once
     pkg.data.write_results(str(f), [[d[:2] for d in route]], "vrp", 3)
     assert [float(t) for t in f.read_text().strip().split(" ")] == depot[:2] + c1[:2] + depot[:2] + c2[:2] + depot[:2]
+
+
+def test_host_selection_rules_match_the_oracle_on_cpu_tensors():
+    """The selection rules of the step-by-step route (host.RLAgent._pick_*; pure torch, so they run without a GPU) against the
+    oracle's as-written restatement: inverse-CDF draw incl. the whole-batch retry and the 'no node found -> node 0' rule,
+    beam top-k with ties to the lower flat index, and the back-tracking of beam parents."""
+    H = load_pkg().host
+    rnd = np.random.RandomState(0)
+    R, N = 64, 11
+    prob = rnd.dirichlet(np.ones(N) * 0.3, size=R).astype(np.float32)
+    prob[:, 3] = 0.0
+    prob /= prob.sum(1, keepdims=True)
+    u1, u2 = rnd.uniform(size=(1, R)).astype(np.float32), rnd.uniform(size=(1, R)).astype(np.float32)
+    agent = object.__new__(H.RLAgent)                      # the rules use no agent state
+    for force_fail in (False, True):
+        a1 = u1.copy()
+        if force_fail:
+            a1[0, 7] = 2.0                                  # beyond any CDF: every row must redraw from u2
+        idx, par = agent._pick_sampled(torch.from_numpy(prob), 0, a1, u2)
+        tmp, want = O.multinomial_as_written(prob, a1[0], N)
+        if (tmp.sum(1) > 10000 * N - 1).any():
+            tmp, want = O.multinomial_as_written(prob, u2[0], N)
+        assert par is None and np.array_equal(idx[:, 0].numpy(), want)
+    both = np.full((1, R), 2.0, np.float32)
+    idx, _ = agent._pick_sampled(torch.from_numpy(prob), 0, both, both)
+    assert (idx == 0).all()                                # argmin of an all-10000 row
+    # beam: B = 8 instances, W = 4 beams, duplicate candidates force the tie rule
+    B, W = 8, 4
+    p = rnd.dirichlet(np.ones(N), size=B * W).astype(np.float32)
+    p[:, 5] = p[:, 2]                                       # exact ties inside every row
+    carried = torch.from_numpy(np.log(rnd.dirichlet(np.ones(W), size=B).T.reshape(-1, 1)).astype(np.float32))
+    node, parent, pp, score = agent._pick_beam(torch.from_numpy(p), 1, B, W, carried)
+    lbp = np.log(p) + carried.numpy()
+    cand = np.concatenate(np.split(lbp, W, axis=0), 1)
+    order = np.argsort(-cand, axis=1, kind="stable")[:, :W]
+    assert np.array_equal(node[:, 0].numpy(), (order.T.reshape(-1) % N))
+    assert np.array_equal(parent[:, 0].numpy(), (order.T.reshape(-1) // N))
+    np.testing.assert_array_equal(score[:, 0].numpy(), np.take_along_axis(cand, order, 1).T.reshape(-1))
+    src = np.tile(np.arange(B), W) + B * parent[:, 0].numpy()
+    np.testing.assert_array_equal(pp.numpy(), p[src])
+    node0, parent0, _, _ = agent._pick_beam(torch.from_numpy(p), 0, B, W, None)
+    assert (parent0 == 0).all()                             # step 0 looks at beam 0 only
+    # back-tracking: row r of every step must belong to the beam that ends in row r
+    T = 6
+    parents = [torch.from_numpy(rnd.randint(0, W, size=(B * W, 1))) for _ in range(T)]
+    steps = [torch.arange(B * W) + 1000 * t for t in range(T)]
+    bt = H.RLAgent._backtrack(steps, parents, B)
+    for r in range(B * W):
+        at = r
+        for k in reversed(range(T)):
+            assert int(bt[k][r]) == 1000 * k + at
+            at = (r % B) + B * int(parents[k][at])
