@@ -188,6 +188,12 @@ int vrpb200_reward_min_trucks(vrpb200_handle* h, const float* d_actions, const f
 int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
                                   float* d_reward, void* stream);
 
+/* reward_func with a depot, UPS_old form (UPS_old/vrptw_ups_utils.py:400-428): 70/n_nodes x (steps at the depot - every one
+ * counts, column 0 is compared) + 30 x closed route length in equirectangular km over x, y (latitude, longitude in radians)
+ * / sum of the Euclidean distances to the depot over all A columns.  d_actions [T, R, A], d_depot [R, A] -> d_reward [R]. */
+int vrpb200_reward_min_trucks_ups_old(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R,
+                                      int A, float n_nodes, float* d_reward, void* stream);
+
 /* ---- REINFORCE pieces around the rollout (forward only) ------------------------------ *
  * Critic value v of RLAgent.build_model('stochastic') (model/attention_agent.py:243-270; critics
  * VRPTW/vrptw_attention.py:87-169, VRP/vrp_attention.py:79-140): n_process_blocks un-masked attention passes over the

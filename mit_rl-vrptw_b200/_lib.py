@@ -38,7 +38,8 @@ class Trace(C.Structure):
 EXPORTS = (
     "vrpb200_create", "vrpb200_destroy", "vrpb200_last_error", "vrpb200_version", "vrpb200_set_weights",
     "vrpb200_rollout", "vrpb200_rollout_host", "vrpb200_env_reset", "vrpb200_env_step", "vrpb200_embed",
-    "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_reward_min_trucks", "vrpb200_reward_min_trucks_ups", "vrpb200_last_launch",
+    "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_reward_min_trucks", "vrpb200_reward_min_trucks_ups", "vrpb200_reward_min_trucks_ups_old",
+    "vrpb200_last_launch",
     "vrpb200_pipe_peak", "vrpb200_critic", "vrpb200_reinforce_loss", "vrpb200_set_sampling_retry", "vrpb200_last_redraws",
 )
 
@@ -116,6 +117,7 @@ def load() -> C.CDLL:
     lib.vrpb200_reward.argtypes = [vp, f32p, i64, i64, i32, f32p, vp]
     lib.vrpb200_reward_min_trucks.argtypes = [vp, f32p, f32p, i64, i64, i32, C.c_float, f32p, vp]
     lib.vrpb200_reward_min_trucks_ups.argtypes = [vp, f32p, f32p, i64, i64, i32, f32p, vp]
+    lib.vrpb200_reward_min_trucks_ups_old.argtypes = [vp, f32p, f32p, i64, i64, i32, C.c_float, f32p, vp]
     lib.vrpb200_set_sampling_retry.argtypes = [vp, i32]
     lib.vrpb200_last_redraws.argtypes = [vp]
     lib.vrpb200_critic.argtypes = [vp, f32p, i64, f32p, vp]

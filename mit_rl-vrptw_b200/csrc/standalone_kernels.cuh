@@ -287,6 +287,8 @@ __global__ void reward_kernel(const float* __restrict__ actions, long long T, lo
 // + 30 x route length (first XY columns) / sum over steps of the distance to the depot over ALL A action columns
 // ups != 0: the UPS VRPTW form (UPS/vrptw_ups_utils.py:387-419): 100 x returns to the depot + route length (its great-circle
 // normaliser is computed by the reference but not used in the reward)
+// ups == 2: the UPS_old form (UPS_old/vrptw_ups_utils.py:400-428): EVERY step at the depot counts (no stay logic), the route is
+// the equirectangular km length, the normaliser stays the Euclidean distance to the depot over all A columns
 __global__ void reward_min_trucks_kernel(const float* __restrict__ actions, const float* __restrict__ depot, long long T, long long R,
                                          int A, int XY, float inv_n_nodes, int ups, float* reward) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -296,10 +298,12 @@ __global__ void reward_min_trucks_kernel(const float* __restrict__ actions, cons
     const float* last = actions + ((T - 1) * R + r) * A;
     float prev[4] = {0.f, 0.f, 0.f, 0.f};
     for (int c = 0; c < XY; ++c) prev[c] = last[c];
+    float px = last[0], py = last[1];
     for (long long t = 0; t < T; ++t) {
         const float* at = actions + (t * R + r) * A;
         const float interm = (at[0] == dp[0]) ? 1.0f : 0.0f;
         if (t == 0) visits = interm;
+        else if (ups == 2) visits = __fadd_rn(visits, interm);
         else {
             counter = __fadd_rn(__fmul_rn(counter, interm), interm);
             visits = __fadd_rn(visits, __fmul_rn(interm, counter < 1.5f ? 1.0f : 0.0f));
@@ -314,10 +318,12 @@ __global__ void reward_min_trucks_kernel(const float* __restrict__ actions, cons
                 prev[c] = at[c];
             }
         }
-        route = __fadd_rn(route, __fsqrt_rn(s));
+        route = __fadd_rn(route, ups == 2 ? geo_km_rn(px, py, at[0], at[1]) : __fsqrt_rn(s));
+        px = at[0];
+        py = at[1];
         maxlen = __fadd_rn(maxlen, __fsqrt_rn(m));
     }
-    reward[r] = ups ? __fadd_rn(__fmul_rn(100.0f, visits), route)
+    reward[r] = ups == 1 ? __fadd_rn(__fmul_rn(100.0f, visits), route)
                     : __fadd_rn(__fmul_rn(70.0f, __fmul_rn(inv_n_nodes, visits)), __fmul_rn(30.0f, __fdiv_rn(route, maxlen)));
 }
 

@@ -913,6 +913,18 @@ int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, con
     return VRPB200_OK;
 }
 
+int vrpb200_reward_min_trucks_ups_old(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R, int A,
+                                      float n_nodes, float* d_reward, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!d_actions || !d_depot || !d_reward || T < 1 || R < 1 || A < 2 || A > 4 || !(n_nodes > 0.0f))
+        return fail(h, VRPB200_E_ARG, "reward_min_trucks_ups_old: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    reward_min_trucks_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, d_depot, T, R, A, 2,
+                                                                                           (float)(1.0 / (double)n_nodes), 2, d_reward);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
 int vrpb200_last_launch(const vrpb200_handle* h, int32_t out[8]) {
     if (!h || !out) return VRPB200_E_ARG;
     memcpy(out, h->last_launch, sizeof h->last_launch);

@@ -287,15 +287,20 @@ class Engine:
         self._check(self.lib.vrpb200_reward(self.handle, _ptr(a), T, R, A, _ptr(out), self._stream()), "reward")
         return out
 
-    def reward_min_trucks(self, actions: torch.Tensor, depot: torch.Tensor, n_nodes: float, ups: bool = False) -> torch.Tensor:
-        """reward_func with a depot (VRPTW/vrptw_utils.py:384-395, 410-412; ups: UPS/vrptw_ups_utils.py:387-419):
-        actions [T, R, A], depot [R, A] -> [R]."""
+    def reward_min_trucks(self, actions: torch.Tensor, depot: torch.Tensor, n_nodes: float, ups: bool = False,
+                          ups_old: bool = False) -> torch.Tensor:
+        """reward_func with a depot (VRPTW/vrptw_utils.py:384-395, 410-412; ups: UPS/vrptw_ups_utils.py:387-419; ups_old:
+        UPS_old/vrptw_ups_utils.py:400-428): actions [T, R, A], depot [R, A] -> [R]."""
         a = self._f32(actions, "actions")
         d = self._f32(depot, "depot")
         T, R, A = a.shape
         if tuple(d.shape) != (R, A):
             raise VrpB200Error(f"depot must be [{R}, {A}]")
         out = torch.empty((R,), device=self.device)
+        if ups_old:
+            self._check(self.lib.vrpb200_reward_min_trucks_ups_old(self.handle, _ptr(a), _ptr(d), T, R, A, C.c_float(float(n_nodes)),
+                                                                   _ptr(out), self._stream()), "reward_min_trucks_ups_old")
+            return out
         if ups:
             self._check(self.lib.vrpb200_reward_min_trucks_ups(self.handle, _ptr(a), _ptr(d), T, R, A, _ptr(out), self._stream()),
                         "reward_min_trucks_ups")

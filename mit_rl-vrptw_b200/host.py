@@ -485,16 +485,19 @@ def reward_func(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None, _ups=F
 
 
 def reward_func_vrptw_ups_old(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):
-    """reward_func of UPS_old/vrptw_ups_utils.py:372-430, depot=None branch: the closed tour length in km over the
-    equirectangular distance (:416-424).  Its depot form (70/n x depot visits + 30 x km / Euclidean normaliser) is not built."""
+    """reward_func of UPS_old/vrptw_ups_utils.py:380-430.  depot=None: the closed tour length in km over the
+    equirectangular distance (:416-424).  depot [R, A]: 70/n_nodes x steps at the depot (every one counts, :401-405) + 30 x
+    that km length / sum of the Euclidean distances to the depot (:406-408, 426-427)."""
     import torch
-    if depot is not None:
-        raise NotImplementedError("UPS_old reward_func with a depot (min_trucks) is not part of the built path")
     sol = sample_solution if isinstance(sample_solution, torch.Tensor) else torch.stack(list(sample_solution), 0)
     sol = sol.to(device="cuda", dtype=torch.float32).contiguous()
     args = dict(task_name="vrptw", n_nodes=2, n_cust=1, input_dim=5, embedding_dim=1, hidden_dim=128, decode_len=1, capacity=1.0,
                 ups_old=True)
-    return _get_engine(args, lambda: _dummy_model_params(args), ("reward",)).reward(sol)
+    eng = _get_engine(args, lambda: _dummy_model_params(args), ("reward",))
+    if depot is None:
+        return eng.reward(sol)
+    dep = depot.to(device="cuda", dtype=torch.float32).contiguous()
+    return eng.reward_min_trucks(sol, dep, float(n_nodes), ups_old=True)
 
 
 def reward_func_vrptw_ups(sample_solution, decode_len=0.0, n_nodes=0.0, depot=None):

@@ -352,6 +352,24 @@ def reward_func_min_trucks_ups(actions: Sequence[np.ndarray], depot: np.ndarray)
     return dt(100.0) * visits + route
 
 
+def reward_func_min_trucks_ups_old(actions: Sequence[np.ndarray], depot: np.ndarray, decode_len: int, n_nodes: float) -> np.ndarray:
+    """``reward_func`` with a depot of the UPS_old package (UPS_old/vrptw_ups_utils.py:400-428): 70/n_nodes x (number of
+    steps at the depot: column 0 compared, EVERY step counts - this version has no "stay counts once" counter) + 30 x the
+    closed route length in equirectangular km (:421-424) / the sum of the EUCLIDEAN distances to the depot over all action
+    columns (:406-408; a km numerator over a coordinate-unit denominator, as written)."""
+    dt = actions[0].dtype.type
+    visits = (actions[0] == depot).astype(dt)[:, 0]
+    for i in range(1, len(actions)):
+        visits = visits + (actions[i] == depot).astype(dt)[:, 0]
+    max_length = np.stack([depot for _ in range(decode_len)], 0)
+    sol = np.stack(actions, 0)
+    max_lens = np.sum(np.power(np.sum(np.power(max_length - sol, dt(2)), 2), dt(0.5)), 0)
+    sol = sol[:, :, :2]
+    tilted = np.concatenate([sol[-1:], sol[:-1]], 0)
+    route = np.sum(_ups_old_km(sol[:, :, 0], sol[:, :, 1], tilted[:, :, 0], tilted[:, :, 1]), 0)
+    return dt(70.0) * (dt(1.0 / n_nodes) * visits) + dt(30.0) * (route / max_lens)
+
+
 # --------------------------------------------------------------------------- #
 # model pieces
 # --------------------------------------------------------------------------- #

@@ -267,6 +267,25 @@ def test_min_trucks_reward_ups_kernel_matches_reference_fixture():
 
 
 @pytest.mark.gpu
+def test_min_trucks_reward_ups_old_kernel_matches_reference_fixture():
+    """load_ups_old_components() hands out the UPS_old reward (UPS_old/vrptw_ups_utils.py:380-430); with a depot: 70/n x steps
+    at the depot + 30 x km route length / Euclidean normaliser -> vrpb200_reward_min_trucks_ups_old against the reference's own
+    output (cosf against numpy's float32 cos: 1e-5 relative)."""
+    import os
+    import torch
+    from tests.helpers import GOLDEN
+    pkg = load_pkg()
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    rf = pkg.host.load_ups_old_components()[2]
+    acts = [torch.from_numpy(a).cuda() for a in fx["vrptwupsold_actions"]]
+    dep = torch.from_numpy(fx["vrptwupsold_depot"]).cuda()
+    r = rf(acts, int(fx["vrptwupsold_T"]), float(fx["vrptwupsold_n_nodes"]), dep)
+    np.testing.assert_allclose(r.cpu().numpy(), fx["vrptwupsold_reward"], rtol=1e-5)
+    km = O.reward_func([a for a in fx["vrptwupsold_actions"]], tw=True, ups_old=True)
+    np.testing.assert_allclose(rf(acts).cpu().numpy(), km, rtol=1e-5)           # no depot: the km tour length
+
+
+@pytest.mark.gpu
 def test_evaluate_single_writes_reference_result_files(tmp_path):
     """evaluate_single (attention_agent.py:336-413) + _output_results (:416-471): one route per problem in the result file,
     each route a valid VRPTW route over the instance's nodes starting and ending at the depot."""

@@ -87,6 +87,24 @@ def test_min_trucks_reward_ups_form_matches_reference_code():
     assert (r >= 100.0).all()        # every route starts at ... or at least returns once to the depot in these fixtures
 
 
+def test_min_trucks_reward_ups_old_form_matches_reference_code():
+    """reward_func with a depot of the UPS_old package (UPS_old/vrptw_ups_utils.py:400-428: 70/n x steps at the depot, every
+    one counted, + 30 x km route length / Euclidean normaliser): the oracle against the output of the reference's own function,
+    bit for bit; and the "every step counts" difference to the VRPTW form is visible in the fixture."""
+    import os
+    from tests.helpers import GOLDEN
+    fx = np.load(os.path.join(GOLDEN, "reward_min_trucks.npz"))
+    acts = [a for a in fx["vrptwupsold_actions"]]
+    T, n = int(fx["vrptwupsold_T"]), float(fx["vrptwupsold_n_nodes"])
+    r = O.reward_func_min_trucks_ups_old(acts, fx["vrptwupsold_depot"], T, n)
+    np.testing.assert_array_equal(r, fx["vrptwupsold_reward"])
+    at_depot = (fx["vrptwupsold_idx"] == int(n) - 1).sum(0)                       # all steps at the depot, stays included
+    km = O.reward_func(acts, tw=True, ups_old=True)
+    sol = fx["vrptwupsold_actions"]
+    norm = np.sqrt(((fx["vrptwupsold_depot"][None] - sol) ** 2).sum(2)).sum(0)
+    np.testing.assert_allclose(r, 70.0 * at_depot / n + 30.0 * km / norm, rtol=1e-5)
+
+
 def test_min_trucks_reward_known_answer():
     """Hand-computed.  Depot (0,0); tour depot, depot, (3,4), depot, (1,1).  The reference's counter starts at 0 whatever
     step 0 is, so the stay at steps 0-1 counts twice (1 for step 0, 1 for step 1 with counter 1 < 1.5), the return at
