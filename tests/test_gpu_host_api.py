@@ -81,8 +81,10 @@ def test_ups_old_reward_is_km_tour_length():
     rf = pkg.host.load_ups_old_components()[2]
     r = rf([torch.from_numpy(a) for a in fx["actions"]])
     np.testing.assert_allclose(r.cpu().numpy(), fx["R"], rtol=2e-6)
-    with pytest.raises(NotImplementedError):
-        rf([torch.from_numpy(a) for a in fx["actions"]], 40, 20.0, torch.zeros(8, 4))
+    acts = [a for a in fx["actions"]]                   # with a depot: the UPS_old min_trucks form, against the oracle
+    dep = np.ascontiguousarray(fx["data"][:, -1, :-1]).astype(np.float32)
+    rd = rf([torch.from_numpy(a) for a in acts], len(acts), float(args["n_nodes"]), torch.from_numpy(dep))
+    np.testing.assert_allclose(rd.cpu().numpy(), O.reward_func_min_trucks_ups_old(acts, dep, len(acts), float(args["n_nodes"])), rtol=1e-5)
 
 
 @pytest.mark.parametrize("case", ["vrptw20_glimpse_tanh", "upsold_vrptw20_greedy"])
