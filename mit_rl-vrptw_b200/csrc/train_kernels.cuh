@@ -1,0 +1,126 @@
+// The backward / update side of RLAgent.build_train_step (model/attention_agent.py:272-322):
+//   actor_grad_rows_kernel   one block per row: actor_grad_row.h (teacher-forced LSTM forward + back-propagation through time)
+//   outer_reduce_kernel      dW[k, j] = sum over rows and steps of A[., k] B[., j]   (every kernel-matrix gradient)
+//   col_reduce_kernel        db[j]    = sum over rows and steps of B[., j]           (bias gradients)
+//   attention_small_grads_kernel   v, emb_* / proj_* (rank-1 structure of the scalar -> H chains), proj_q / proj_ref biases
+//   clip_adam_kernel         tf.clip_by_norm per variable (:303-307) + tf.train.AdamOptimizer.apply_gradients (:310-311)
+// Every sum runs in one fixed order (thread per output element, serial loop): gradients are bit-reproducible.
+#pragma once
+#include "actor_grad_row.h"
+#include "common.cuh"
+
+namespace vrpb200 {
+
+struct ActorGradBatch {   // per-row strides (in floats) of the work arrays; row r uses base + r * stride
+    const float* input;       // [R, N, D]
+    const int* idx;           // [T, R]
+    const float* weight;      // [R]
+    const float *demand, *mask, *load, *time;   // [T + 1][R][N], [T + 1][R]
+    float *hs, *cs, *act, *xin, *dx, *emb, *eref, *erefT, *dgates, *dq, *Dsum, *demb, *sums;
+    long long R;
+};
+
+__global__ void __launch_bounds__(128) actor_grad_rows_kernel(ActorGradWeights w, ActorGradDims d, ActorGradBatch b) {
+    const long long r = blockIdx.x;
+    const int H = kAgH, N = d.N, E = d.E, T = d.T;
+    ActorGradRow row;
+    row.input = b.input + r * N * d.D;
+    row.idx = b.idx + r;
+    row.idx_stride = b.R;
+    row.weight = b.weight[r];
+    row.demand = b.demand + r * N;
+    row.mask = b.mask + r * N;
+    row.node_stride = b.R * N;
+    row.load = b.load + r;
+    row.time = b.time ? b.time + r : nullptr;
+    row.scalar_stride = b.R;
+    row.hs = b.hs + r * (T + 1) * H;
+    row.cs = b.cs + r * (T + 1) * H;
+    row.act = b.act + r * T * 4 * H;
+    row.xin = b.xin + r * T * E;
+    row.dx = b.dx + r * T * E;
+    row.emb = b.emb + r * N * E;
+    row.eref = b.eref + r * N * H;
+    row.erefT = b.erefT + r * H * 128;
+    row.dgates = b.dgates + r * T * 4 * H;
+    row.dq = b.dq + r * T * H;
+    row.Dsum = b.Dsum + r * N * H;
+    row.demb = b.demb + r * N * E;
+    row.sums = b.sums + r * 5 * H;
+    actor_grad_row(w, d, row);
+}
+
+__global__ void idx_to_i64_kernel(const int* __restrict__ in, long long* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+// out[k * J + j] = sum_{r < R} sum_{t < Tn} A[r * sAr + t * sAt + k] * B[r * sBr + t * sBt + j]
+__global__ void outer_reduce_kernel(const float* __restrict__ A, long long sAr, long long sAt, const float* __restrict__ Bm,
+                                    long long sBr, long long sBt, long long R, int Tn, int K, int J, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)K * J) return;
+    const int k = (int)(i / J), j = (int)(i - (long long)k * J);
+    float s = 0.0f;
+    for (long long r = 0; r < R; ++r) {
+        const float* a = A + r * sAr + k;
+        const float* b = Bm + r * sBr + j;
+        float sr = 0.0f;
+        for (int t = 0; t < Tn; ++t) sr = fmaf(a[t * sAt], b[t * sBt], sr);
+        s += sr;
+    }
+    out[i] = s;
+}
+
+__global__ void col_reduce_kernel(const float* __restrict__ Bm, long long sBr, long long sBt, long long R, int Tn, int J,
+                                  float* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= J) return;
+    float s = 0.0f;
+    for (long long r = 0; r < R; ++r) {
+        const float* b = Bm + r * sBr + j;
+        float sr = 0.0f;
+        for (int t = 0; t < Tn; ++t) sr += b[t * sBt];
+        s += sr;
+    }
+    out[j] = s;
+}
+
+__global__ void __launch_bounds__(128) attention_small_grads_kernel(ActorGradWeights w, const float* __restrict__ sums, long long R,
+                                                                    int tw, SmallGradOut o) {
+    attention_small_grads(w, sums, R, tw, o);
+}
+
+// tf.clip_by_norm(grad, max_norm) per variable, then Adam (TF-1: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); m, v moments;
+// var -= lr_t m / (sqrt(v) + eps)).  One block per variable; the norm is summed in a fixed order.
+struct AdamVar {
+    float* var;
+    const float* grad;
+    float *m, *v;
+    long long n;
+};
+__global__ void __launch_bounds__(256) clip_adam_kernel(const AdamVar* __restrict__ vars, float max_norm, float lr_t, float beta1,
+                                                        float beta2, float eps) {
+    __shared__ float part[256];
+    const AdamVar a = vars[blockIdx.x];
+    float s = 0.0f;
+    for (long long i = threadIdx.x; i < a.n; i += 256) s = fmaf(a.grad[i], a.grad[i], s);
+    part[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if ((int)threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+        __syncthreads();
+    }
+    const float norm = sqrtf(part[0]);
+    const float scale = norm > max_norm ? max_norm / norm : 1.0f;    // clip_by_norm: t * clip / max(norm, clip)
+    for (long long i = threadIdx.x; i < a.n; i += 256) {
+        const float g = a.grad[i] * scale;
+        const float m = beta1 * a.m[i] + (1.0f - beta1) * g;
+        const float v = beta2 * a.v[i] + (1.0f - beta2) * g * g;
+        a.m[i] = m;
+        a.v[i] = v;
+        a.var[i] -= lr_t * m / (sqrtf(v) + eps);
+    }
+}
+
+}  // namespace vrpb200
