@@ -207,6 +207,26 @@ int vrpb200_critic(vrpb200_handle* h, const float* d_input, int64_t B, float* d_
 int vrpb200_reinforce_loss(vrpb200_handle* h, const float* d_R, const float* d_v, const float* d_logprob, int64_t T, int64_t R,
                            float* d_losses, void* stream);
 
+/* compute_gradients(actor_loss, Actor variables) of build_train_step (model/attention_agent.py:289-297): back-propagation of
+ *   L = sum_r d_weight[r] * sum_t log prob_t[r, d_idx[t, r]]        (d_weight[r] = (R[r] - v[r]) / B gives the reference's actor_loss)
+ * through the teacher-forced rollout - Env state along the tour d_idx (constants of the graph), BasicLSTMCell through time,
+ * the pointer attention, mask, log_softmax, and the embedding in both of its uses (shared/decode_step.py:97-128, 182-234;
+ * VRPTW/vrptw_attention.py:30-84; shared/embeddings.py:40-46).  d_input [B, N, input_dim]; d_idx [T, B] int32 (vrpb200_rollout's
+ * d_idx, greedy or stochastic, beam_width 1).  names / d_grads / n_elem: the TF variable names as in vrpb200_set_weights, one
+ * DEVICE buffer per variable (same element count as the variable) that receives its gradient; variables left out are skipped.
+ * n_glimpses must be 0; LSTM-input dropout is not applied (the keep-probability-1 graph is differentiated).  Work memory
+ * (~13 * T * hidden_dim floats per row) is owned by the handle.  Deterministic: every sum runs in one fixed order. */
+int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight, int n,
+                       const char* const* names, float* const* d_grads, const int64_t* n_elem, void* stream);
+
+/* clip_by_norm + AdamOptimizer.apply_gradients of build_train_step (model/attention_agent.py:303-311) for n variables at once:
+ * per variable g = grad * max_norm / max(||grad||, max_norm); m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
+ * var -= lr sqrt(1 - b2^step) / (1 - b1^step) * m / (sqrt(v) + eps)  (TF-1 Adam; step = 1 for the first update).
+ * Every pointer is a DEVICE buffer of n_elem[i] floats; d_m / d_v are the optimizer slots, zero before the first step. */
+int vrpb200_clip_adam(vrpb200_handle* h, int n, float* const* d_vars, const float* const* d_grads, float* const* d_m,
+                      float* const* d_v, const int64_t* n_elem, float max_norm, float lr, int64_t step, float beta1, float beta2,
+                      float eps, void* stream);
+
 /* Measured throughput of one SM pipe on the handle's device, for the roofline denominators that
  * MEASURED_PEAKS.json does not hold: kind 0 = MUFU (ex2/rcp, ops/s), 1 = FP32 FMA (FMA/s, 2 flop each).
  * Runs a register-only micro-benchmark on every SM for ~`iters` x 4096 ops per thread.  Synchronous. */

@@ -18,6 +18,7 @@
 #include "launchers.h"
 #include "standalone_kernels.cuh"
 #include "critic_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace vrpb200;
 
@@ -45,6 +46,8 @@ struct vrpb200_handle {
     float* d_critic = nullptr;      // critic constants (critic_kernels.cuh), null until set_weights saw Critic/* variables
     int critic_blocks = 0;
     float* d_loss = nullptr;        // [2] scratch of reinforce_loss
+    char* d_train_ws = nullptr;     // work arrays of vrpb200_actor_grad / vrpb200_clip_adam (grow-only)
+    size_t train_ws_bytes = 0;
     int whole_batch_retry = 0;      // vrpb200_set_sampling_retry
     int* d_retry = nullptr;         // [2][T]: retry_steps | fail_steps
     int last_redraws = 0;
@@ -170,6 +173,7 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (h->d_gatt) cudaFree(h->d_gatt);
     if (h->d_critic) cudaFree(h->d_critic);
     if (h->d_loss) cudaFree(h->d_loss);
+    if (h->d_train_ws) cudaFree(h->d_train_ws);
     if (h->d_retry) cudaFree(h->d_retry);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -922,6 +926,147 @@ int vrpb200_reward_min_trucks_ups_old(vrpb200_handle* h, const float* d_actions,
     reward_min_trucks_kernel<<<(unsigned)((R + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_actions, d_depot, T, R, A, 2,
                                                                                            (float)(1.0 / (double)n_nodes), 2, d_reward);
     CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+// ---- the backward / update side of build_train_step ---------------------------------------------------------
+namespace {
+int train_workspace(vrpb200_handle* h, size_t bytes) {
+    if (h->train_ws_bytes >= bytes) return VRPB200_OK;
+    if (h->d_train_ws) { cudaFree(h->d_train_ws); h->d_train_ws = nullptr; h->train_ws_bytes = 0; }
+    CUDA_TRY(h, cudaMalloc((void**)&h->d_train_ws, bytes));
+    h->train_ws_bytes = bytes;
+    return VRPB200_OK;
+}
+}  // namespace
+
+int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight, int n,
+                       const char* const* names, float* const* d_grads, const int64_t* n_elem, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights) return fail(h, VRPB200_E_STATE, "actor_grad before set_weights");
+    if (!d_input || !d_idx || !d_weight || B < 1 || n < 0 || (n > 0 && (!names || !d_grads || !n_elem)))
+        return fail(h, VRPB200_E_ARG, "actor_grad: bad argument");
+    const vrpb200_config& c = h->cfg;
+    if (c.n_glimpses != 0) return fail(h, VRPB200_E_ARG, "actor_grad: glimpses are not differentiated (n_glimpses must be 0)");
+    const int N = c.n_nodes, E = c.embedding_dim, D = c.input_dim, T = c.decode_len, H = kH, D1 = h->D1;
+    const long long R = B;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+
+    // expected variables: name -> (slot, elements)
+    const std::string att = "Actor/Decoder/Attention/", lstm = "Actor/Decoder/LSTM/rnn/multi_rnn_cell/cell_0/basic_lstm_cell/";
+    enum { G_EMB_K, G_EMB_B, G_LSTM_K, G_LSTM_B, G_V, G_PQ_K, G_PQ_B, G_PR_K, G_PR_B, G_EK0, G_EB0 = G_EK0 + 3, G_PK0 = G_EB0 + 3,
+           G_PB0 = G_PK0 + 3, G_COUNT = G_PB0 + 3 };
+    std::map<std::string, std::pair<int, int64_t>> known = {
+        {"Actor/Embedding/conv1d/kernel", {G_EMB_K, (int64_t)D1 * E}}, {"Actor/Embedding/conv1d/bias", {G_EMB_B, E}},
+        {lstm + "kernel", {G_LSTM_K, (int64_t)(E + H) * 4 * H}}, {lstm + "bias", {G_LSTM_B, 4 * H}},
+        {att + "v", {G_V, H}}, {att + "proj_q/kernel", {G_PQ_K, (int64_t)H * H}}, {att + "proj_q/bias", {G_PQ_B, H}},
+        {att + "proj_ref/kernel", {G_PR_K, (int64_t)E * H}}, {att + "proj_ref/bias", {G_PR_B, H}}};
+    const char* eb[3] = {"emb_d", "emb_ld", "emb_time"};
+    const char* pb[3] = {"proj_d", "proj_ld", "proj_t"};
+    for (int k = 0; k < (h->tw ? 3 : 2); ++k) {
+        known[att + eb[k] + "/kernel"] = {G_EK0 + k, H};
+        known[att + eb[k] + "/bias"] = {G_EB0 + k, H};
+        known[att + pb[k] + "/kernel"] = {G_PK0 + k, (int64_t)H * H};
+        known[att + pb[k] + "/bias"] = {G_PB0 + k, H};
+    }
+    float* out[G_COUNT] = {nullptr};
+    for (int i = 0; i < n; ++i) {
+        auto it = known.find(names[i] ? names[i] : "");
+        if (it == known.end()) return fail(h, VRPB200_E_ARG, "actor_grad: %s is not a variable of the differentiated graph", names[i] ? names[i] : "(null)");
+        if (n_elem[i] != it->second.second || !d_grads[i])
+            return fail(h, VRPB200_E_ARG, "actor_grad: %s has %lld elements, expected %lld", names[i], (long long)n_elem[i], (long long)it->second.second);
+        out[it->second.first] = d_grads[i];
+    }
+
+    // work arrays
+    size_t off = 0;
+    auto take = [&](size_t floats) { const size_t o = off; off += (floats * 4 + 255) / 256 * 256; return o; };
+    const size_t o_idx64 = take((size_t)T * R * 2);
+    const size_t o_dem = take((size_t)(T + 1) * R * N), o_msk = take((size_t)(T + 1) * R * N), o_load = take((size_t)(T + 1) * R);
+    const size_t o_time = take((size_t)(T + 1) * R), o_prev = take((size_t)(T + 1) * R * 2);
+    const size_t o_hs = take((size_t)R * (T + 1) * H), o_cs = take((size_t)R * (T + 1) * H), o_act = take((size_t)R * T * 4 * H);
+    const size_t o_xin = take((size_t)R * T * E), o_dx = take((size_t)R * T * E), o_emb = take((size_t)R * N * E);
+    const size_t o_eref = take((size_t)R * N * H), o_erefT = take((size_t)R * H * 128), o_dg = take((size_t)R * T * 4 * H);
+    const size_t o_dq = take((size_t)R * T * H), o_Ds = take((size_t)R * N * H), o_demb = take((size_t)R * N * E), o_sums = take((size_t)R * 5 * H);
+    if (int rc = train_workspace(h, off)) return rc;
+    char* ws = h->d_train_ws;
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+    long long* idx64 = reinterpret_cast<long long*>(ws + o_idx64);
+
+    // Env state seen by every step: Env.reset, then Env.step along the given tour (the tested stand-alone kernels)
+    idx_to_i64_kernel<<<(unsigned)(((long long)T * R + 255) / 256), 256, 0, st>>>(d_idx, idx64, (long long)T * R);
+    const int wpb = 8;
+    const unsigned egrid = (unsigned)((R + wpb - 1) / wpb);
+    env_reset_kernel<<<egrid, wpb * 32, 0, st>>>(d_input, R, 1, N, D, c.capacity, F(o_dem), F(o_load), h->tw ? F(o_time) : nullptr, F(o_msk),
+                                                 h->tw ? F(o_prev) : nullptr);
+    for (int t = 0; t < T; ++t) {
+        const size_t a = (size_t)t * R, b = (size_t)(t + 1) * R;
+        if (h->tw)
+            env_step_kernel<true><<<egrid, wpb * 32, 0, st>>>(d_input, R, 1, N, D, c.capacity, idx64 + a, nullptr, F(o_dem) + a * N,
+                                                              F(o_load) + a, F(o_time) + a, F(o_prev) + a * 2, F(o_dem) + b * N, F(o_load) + b,
+                                                              F(o_time) + b, F(o_msk) + b * N, F(o_prev) + b * 2, nullptr, c.physics);
+        else
+            env_step_kernel<false><<<egrid, wpb * 32, 0, st>>>(d_input, R, 1, N, D, c.capacity, idx64 + a, nullptr, F(o_dem) + a * N,
+                                                               F(o_load) + a, nullptr, nullptr, F(o_dem) + b * N, F(o_load) + b, nullptr,
+                                                               F(o_msk) + b * N, nullptr, nullptr, 0);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+
+    const RawAtt& ra = h->raw.att[0];
+    ActorGradWeights w{h->raw_emb_k, h->raw_emb_b, h->raw.lstm_k, h->raw.lstm_b, ra.v,
+                       ra.emb_d_k, ra.emb_d_b, ra.proj_d_k, ra.proj_d_b, ra.emb_ld_k, ra.emb_ld_b, ra.proj_ld_k, ra.proj_ld_b,
+                       ra.emb_t_k, ra.emb_t_b, ra.proj_t_k, ra.proj_t_b, ra.proj_q_k, ra.proj_q_b, ra.proj_ref_k, ra.proj_ref_b};
+    ActorGradDims dm{N, E, D, T, h->tw ? 1 : 0, c.use_tanh, c.mask_pointer, c.tanh_exploration, c.forget_bias};
+    ActorGradBatch bt{d_input, d_idx, d_weight, F(o_dem), F(o_msk), F(o_load), h->tw ? F(o_time) : nullptr,
+                      F(o_hs), F(o_cs), F(o_act), F(o_xin), F(o_dx), F(o_emb), F(o_eref), F(o_erefT), F(o_dg), F(o_dq), F(o_Ds), F(o_demb),
+                      F(o_sums), R};
+    actor_grad_rows_kernel<<<(unsigned)R, 128, 0, st>>>(w, dm, bt);
+    CUDA_TRY(h, cudaGetLastError());
+
+    // device-wide reductions, one fixed order
+    auto outer = [&](const float* A, long long sAr, long long sAt, const float* Bm, long long sBr, long long sBt, int Tn, int K, int J, float* o) {
+        if (o) outer_reduce_kernel<<<(unsigned)(((long long)K * J + 127) / 128), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, Tn, K, J, o);
+    };
+    auto cols = [&](const float* Bm, long long sBr, long long sBt, int Tn, int J, float* o) {
+        if (o) col_reduce_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(Bm, sBr, sBt, R, Tn, J, o);
+    };
+    if (out[G_LSTM_K]) {   // rows 0..E-1: the inputs x_t; rows E..E+H-1: the previous outputs h_{t-1}
+        outer(F(o_xin), (long long)T * E, E, F(o_dg), (long long)T * 4 * H, 4 * H, T, E, 4 * H, out[G_LSTM_K]);
+        outer(F(o_hs), (long long)(T + 1) * H, H, F(o_dg), (long long)T * 4 * H, 4 * H, T, H, 4 * H, out[G_LSTM_K] + (size_t)E * 4 * H);
+    }
+    cols(F(o_dg), (long long)T * 4 * H, 4 * H, T, 4 * H, out[G_LSTM_B]);
+    outer(F(o_hs) + H, (long long)(T + 1) * H, H, F(o_dq), (long long)T * H, H, T, H, H, out[G_PQ_K]);
+    outer(F(o_emb), (long long)N * E, E, F(o_Ds), (long long)N * H, H, N, E, H, out[G_PR_K]);
+    outer(d_input, (long long)N * D, D, F(o_demb), (long long)N * E, E, N, D1, E, out[G_EMB_K]);
+    cols(F(o_demb), (long long)N * E, E, N, E, out[G_EMB_B]);
+    SmallGradOut so{out[G_V], out[G_PQ_B], out[G_PR_B],
+                    {out[G_EK0], out[G_EK0 + 1], out[G_EK0 + 2]}, {out[G_EB0], out[G_EB0 + 1], out[G_EB0 + 2]},
+                    {out[G_PK0], out[G_PK0 + 1], out[G_PK0 + 2]}, {out[G_PB0], out[G_PB0 + 1], out[G_PB0 + 2]}};
+    attention_small_grads_kernel<<<1, 128, 0, st>>>(w, F(o_sums), R, h->tw ? 1 : 0, so);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_clip_adam(vrpb200_handle* h, int n, float* const* d_vars, const float* const* d_grads, float* const* d_m, float* const* d_v,
+                      const int64_t* n_elem, float max_norm, float lr, int64_t step, float beta1, float beta2, float eps, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (n < 1 || !d_vars || !d_grads || !d_m || !d_v || !n_elem || step < 1 || !(max_norm > 0.0f))
+        return fail(h, VRPB200_E_ARG, "clip_adam: bad argument");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    std::vector<AdamVar> hv(n);
+    for (int i = 0; i < n; ++i) {
+        if (!d_vars[i] || !d_grads[i] || !d_m[i] || !d_v[i] || n_elem[i] < 1) return fail(h, VRPB200_E_ARG, "clip_adam: variable %d: bad argument", i);
+        hv[i] = AdamVar{d_vars[i], d_grads[i], d_m[i], d_v[i], (long long)n_elem[i]};
+    }
+    AdamVar* dv = nullptr;
+    CUDA_TRY(h, cudaMallocAsync((void**)&dv, sizeof(AdamVar) * n, (cudaStream_t)stream));
+    CUDA_TRY(h, cudaMemcpyAsync(dv, hv.data(), sizeof(AdamVar) * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));   // hv is pageable host memory about to go out of scope
+    const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step));
+    clip_adam_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dv, max_norm, (float)lr_t, beta1, beta2, eps);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaFreeAsync(dv, (cudaStream_t)stream));
     return VRPB200_OK;
 }
 

@@ -280,6 +280,41 @@ class Engine:
                     "reinforce_loss")
         return out[0], out[1]
 
+    def actor_grad(self, input_data, idxs, weight, shapes: Dict[str, tuple]) -> Dict[str, torch.Tensor]:
+        """compute_gradients(actor_loss, Actor variables) (attention_agent.py:289-297): gradients of
+        sum_r weight[r] sum_t logprob[t, r] along the tour idxs [T, B] (int32, the rollout's).  shapes: variable name -> shape of
+        every variable whose gradient is wanted; returns name -> device tensor of that shape."""
+        x = self._f32(input_data, "input_data")
+        idx = idxs.to(device=self.device, dtype=torch.int32).contiguous()
+        w = self._f32(weight, "weight")
+        B = x.shape[0]
+        if tuple(idx.shape) != (self.args["decode_len"], B) or tuple(w.shape) != (B,):
+            raise VrpB200Error(f"idxs must be [{self.args['decode_len']}, {B}] and weight [{B}]")
+        names = sorted(shapes)
+        grads = {k: torch.zeros(tuple(shapes[k]), device=self.device, dtype=torch.float32) for k in names}
+        c_names = (C.c_char_p * len(names))(*[k.encode() for k in names])
+        c_ptrs = (C.c_void_p * len(names))(*[grads[k].data_ptr() for k in names])
+        c_sizes = (C.c_int64 * len(names))(*[grads[k].numel() for k in names])
+        self._check(self.lib.vrpb200_actor_grad(self.handle, _ptr(x), B, _ptr(idx), _ptr(w), len(names), c_names, c_ptrs, c_sizes,
+                                                self._stream()), "actor_grad")
+        return grads
+
+    def clip_adam(self, variables, grads, m, v, max_norm: float, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
+                  eps: float = 1e-8):
+        """tf.clip_by_norm per variable + one AdamOptimizer update (attention_agent.py:303-311), in place on the device tensors
+        variables[i], m[i], v[i] (lists of equal length; grads[i] is read)."""
+        n = len(variables)
+        for lst in (grads, m, v):
+            if len(lst) != n:
+                raise VrpB200Error("clip_adam: lists of different length")
+        for a in list(variables) + list(grads) + list(m) + list(v):
+            if not (a.is_cuda and a.dtype == torch.float32 and a.is_contiguous()):
+                raise VrpB200Error("clip_adam: contiguous float32 device tensors only")
+        arr = lambda lst: (C.c_void_p * n)(*[a.data_ptr() for a in lst])
+        sizes = (C.c_int64 * n)(*[a.numel() for a in variables])
+        self._check(self.lib.vrpb200_clip_adam(self.handle, n, arr(variables), arr(grads), arr(m), arr(v), sizes, float(max_norm), float(lr),
+                                               int(step), float(beta1), float(beta2), float(eps), self._stream()), "clip_adam")
+
     def reward(self, actions: torch.Tensor) -> torch.Tensor:
         a = self._f32(actions, "actions")
         T, R, A = a.shape

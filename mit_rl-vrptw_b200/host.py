@@ -573,7 +573,7 @@ class RLAgent(object):
 
     def __init__(self, args, prt, env, dataGen, reward_func, clAttentionActor, clAttentionCritic, is_train=False, _scope='',
                  store: Optional[VariableStore] = None, device: int = 0):
-        self.is_train = is_train       # forward side of the training step only: build_train_step() returns the losses
+        self.is_train = is_train
         if args.get('embedding_graph', 0) != 0:
             raise NotImplementedError("only embedding_graph=0 (LinearEmbedding) is on the rollout path")
         self.args = args
@@ -598,6 +598,7 @@ class RLAgent(object):
         self.last_time = None
         self._scope = _scope
         self._critic_built = False
+        self._adam = None                # device copies of the Actor variables + Adam slots (build_train_step)
 
     # -- checkpoint ------------------------------------------------------------------------------
     def Initialize(self, sess=None):
@@ -636,16 +637,47 @@ class RLAgent(object):
         st.get(sc + 'Linear/L2/bias', [1], init="zeros")
         self._critic_built = True
 
-    def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0):
-        """attention_agent.py:272-322, forward side: the stochastic rollout, the critic and the two losses.  Returns the
-        reference's list [actor_train_step, critic_train_step, actor_loss, critic_loss, actor_gra_and_var, critic_gra_and_var,
-        R, v, logprobs, probs, actions, idxs] with None in the optimizer / gradient slots: back-propagation through the
-        rollout and Adam are not built (out of scope of this round)."""
+    def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0, apply=True):
+        """attention_agent.py:272-322: ONE training step - the stochastic rollout, the critic, the two losses,
+        compute_gradients(actor_loss) over the Actor variables (vrpb200_actor_grad: back-propagation through the teacher-forced
+        rollout), per-variable clip_by_norm(max_grad_norm) and the Adam update with actor_net_lr (vrpb200_clip_adam; apply=False
+        only computes).  Returns the reference's list [actor_train_step, critic_train_step, actor_loss, critic_loss,
+        actor_gra_and_var, critic_gra_and_var, R, v, logprobs, probs, actions, idxs]: actor_train_step is the number of Adam
+        steps taken so far, actor_gra_and_var a list of (gradient tensor, variable name); the critic slots are None - the
+        critic's gradient is not built (its value and loss are), nor is LSTM-input dropout (keep-probability 1).  Glimpses are
+        not differentiated: with n_glimpses > 0 the actor slots are None as well."""
         import torch
         R, v, logprobs, actions, idxs, batch, probs = self.build_model('stochastic', uniforms=uniforms, uniforms_retry=uniforms_retry,
                                                                        seed=seed)
-        actor_loss, critic_loss = self.engine().reinforce_loss(R, v, torch.stack(logprobs))
-        return [None, None, actor_loss, critic_loss, None, None, R, v, logprobs, probs, actions, idxs]
+        eng = self.engine()
+        actor_loss, critic_loss = eng.reinforce_loss(R, v, torch.stack(logprobs))
+        if self.args['n_glimpses'] != 0:
+            return [None, None, actor_loss, critic_loss, None, None, R, v, logprobs, probs, actions, idxs]
+        rows = R.shape[0]
+        weight = (R - v) / float(rows)                 # d actor_loss / d sum_t logprob[t, r]; v enters as a constant (:286)
+        sc = self._scope + 'Actor/'
+        names = [k for k in self.store.vars if k.startswith(sc)]
+        shapes = {'Actor/' + k[len(sc):]: self.store.vars[k].shape for k in names}
+        grads = eng.actor_grad(self.env.input_data, torch.stack(idxs)[:, :, 0], weight, shapes)
+        gra_and_var = [(grads['Actor/' + k[len(sc):]], k) for k in names]
+        if apply:
+            st = self._adam
+            if st is None or st['version'] != self.store.version or st['names'] != names:   # first step, or variables re-assigned
+                dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+                old = st if st is not None and st['names'] == names else None
+                st = self._adam = dict(names=names, var=[dev(self.store.vars[k]) for k in names],
+                                       m=old['m'] if old else [torch.zeros_like(g) for g, _ in gra_and_var],
+                                       v=old['v'] if old else [torch.zeros_like(g) for g, _ in gra_and_var],
+                                       step=old['step'] if old else 0)
+            st['step'] += 1
+            eng.clip_adam(st['var'], [g for g, _ in gra_and_var], st['m'], st['v'], max_norm=self.args.get('max_grad_norm', 2.0),
+                          lr=self.args.get('actor_net_lr', 1e-4), step=st['step'])
+            for k, t in zip(names, st['var']):          # the variable collection stays the single source of truth
+                self.store.vars[k] = t.cpu().numpy().reshape(self.store.vars[k].shape)
+            self.store.version += 1
+            st['version'] = self.store.version
+        return [self._adam['step'] if self._adam else 0, None, actor_loss, critic_loss, gra_and_var, None, R, v, logprobs, probs,
+                actions, idxs]
 
     def engine(self):
         eargs = dict(self.args)

@@ -91,7 +91,7 @@ def clip_adam(var, grad, m, v, step, lr, max_norm, beta1=0.9, beta2=0.999, eps=1
     norm = np.sqrt(np.sum(g * g, dtype=f))
     if norm > max_norm:
         g = g * f(max_norm / norm)
-    m = f(beta1) * m + f(1 - beta1) * g
-    v = f(beta2) * v + f(1 - beta2) * g * g
+    m = f(beta1) * m + (f(1) - f(beta1)) * g       # 1 - beta in float32, as TF's ApplyAdam kernel forms it
+    v = f(beta2) * v + (f(1) - f(beta2)) * g * g
     lr_t = f(lr * np.sqrt(1 - beta2 ** step) / (1 - beta1 ** step))
     return var - lr_t * m / (np.sqrt(v) + f(eps)), m, v
