@@ -219,6 +219,15 @@ int vrpb200_reinforce_loss(vrpb200_handle* h, const float* d_R, const float* d_v
 int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight, int n,
                        const char* const* names, float* const* d_grads, const int64_t* n_elem, void* stream);
 
+/* compute_gradients(critic_loss, Critic variables) of build_train_step (model/attention_agent.py:290, 298-299):
+ * critic_loss = tf.losses.mean_squared_error(R, v), back-propagated through Linear/L2, relu, Linear/L1 and the n_process_blocks
+ * attention blocks of the critic (VRPTW/vrptw_attention.py:87-169, VRP/vrp_attention.py:79-140; emb_begin_tw / proj_end_tw receive
+ * the gradient of both windows).  The actor's embedding is a constant of this graph.  d_input [B, N, input_dim], d_R [B] (the
+ * rollout's tour lengths); names / d_grads / n_elem as in vrpb200_actor_grad, over the Critic/* variables; d_v [B] (may be NULL)
+ * receives the value v the gradient was taken at.  Needs the Critic/* variables in set_weights (VRPB200_E_STATE otherwise). */
+int vrpb200_critic_grad(vrpb200_handle* h, const float* d_input, int64_t B, const float* d_R, int n, const char* const* names,
+                        float* const* d_grads, const int64_t* n_elem, float* d_v, void* stream);
+
 /* clip_by_norm + AdamOptimizer.apply_gradients of build_train_step (model/attention_agent.py:303-311) for n variables at once:
  * per variable g = grad * max_norm / max(||grad||, max_norm); m = b1 m + (1 - b1) g; v = b2 v + (1 - b2) g^2;
  * var -= lr sqrt(1 - b2^step) / (1 - b1^step) * m / (sqrt(v) + eps)  (TF-1 Adam; step = 1 for the first update).

@@ -41,7 +41,7 @@ EXPORTS = (
     "vrpb200_attention", "vrpb200_decode_step", "vrpb200_reward", "vrpb200_reward_min_trucks", "vrpb200_reward_min_trucks_ups", "vrpb200_reward_min_trucks_ups_old",
     "vrpb200_last_launch",
     "vrpb200_pipe_peak", "vrpb200_critic", "vrpb200_reinforce_loss", "vrpb200_set_sampling_retry", "vrpb200_last_redraws",
-    "vrpb200_actor_grad", "vrpb200_clip_adam",
+    "vrpb200_actor_grad", "vrpb200_critic_grad", "vrpb200_clip_adam",
 )
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     lib.vrpb200_critic.argtypes = [vp, f32p, i64, f32p, vp]
     lib.vrpb200_reinforce_loss.argtypes = [vp, f32p, f32p, f32p, i64, i64, f32p, vp]
     lib.vrpb200_actor_grad.argtypes = [vp, f32p, i64, vp, f32p, i32, vp, vp, vp, vp]
+    lib.vrpb200_critic_grad.argtypes = [vp, f32p, i64, f32p, i32, vp, vp, vp, f32p, vp]
     lib.vrpb200_clip_adam.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, C.c_float, i64, C.c_float, C.c_float, C.c_float, vp]
     lib.vrpb200_last_launch.argtypes = [vp, C.POINTER(C.c_int32)]
     lib.vrpb200_pipe_peak.argtypes = [vp, i32, i32, C.POINTER(C.c_double)]

@@ -3,10 +3,12 @@
 //   outer_reduce_kernel      dW[k, j] = sum over rows and steps of A[., k] B[., j]   (every kernel-matrix gradient)
 //   col_reduce_kernel        db[j]    = sum over rows and steps of B[., j]           (bias gradients)
 //   attention_small_grads_kernel   v, emb_* / proj_* (rank-1 structure of the scalar -> H chains), proj_q / proj_ref biases
+//   critic_grad_rows_kernel / critic_small_grads_kernel   the same for critic_loss = mean_squared_error(R, v) (critic_grad_row.h)
 //   clip_adam_kernel         tf.clip_by_norm per variable (:303-307) + tf.train.AdamOptimizer.apply_gradients (:310-311)
 // Every sum runs in one fixed order (thread per output element, serial loop): gradients are bit-reproducible.
 #pragma once
 #include "actor_grad_row.h"
+#include "critic_grad_row.h"
 #include "common.cuh"
 
 namespace vrpb200 {
@@ -89,6 +91,37 @@ __global__ void col_reduce_kernel(const float* __restrict__ Bm, long long sBr, l
 __global__ void __launch_bounds__(128) attention_small_grads_kernel(ActorGradWeights w, const float* __restrict__ sums, long long R,
                                                                     int tw, SmallGradOut o) {
     attention_small_grads(w, sums, R, tw, o);
+}
+
+struct CriticGradBatch {
+    const float* input;     // [R, N, D]
+    const float* Rw;        // [R]
+    float *emb, *ee, *eeT, *prob, *hyin, *De, *sums, *dq, *l1, *dl1, *vdv;
+};
+
+__global__ void __launch_bounds__(128) critic_grad_rows_kernel(CriticGradWeights w, CriticGradDims d, CriticGradBatch b) {
+    const long long r = blockIdx.x;
+    const int H = kAgH, N = d.N, E = d.E, P = d.P;
+    CriticGradRow row;
+    row.input = b.input + r * N * d.D;
+    row.R = b.Rw[r];
+    row.emb = b.emb + r * N * E;
+    row.ee = b.ee + r * P * N * H;
+    row.eeT = b.eeT + r * P * H * 128;
+    row.prob = b.prob + r * P * 128;
+    row.hyin = b.hyin + r * (P + 1) * H;
+    row.De = b.De + r * P * N * H;
+    row.sums = b.sums + r * P * 4 * H;
+    row.dq = b.dq + r * P * H;
+    row.l1 = b.l1 + r * H;
+    row.dl1 = b.dl1 + r * H;
+    row.vdv = b.vdv + r * 2;
+    critic_grad_row(w, d, row);
+}
+
+__global__ void __launch_bounds__(128) critic_small_grads_kernel(CriticBlockWeights bw, const float* __restrict__ sums, long long R, int P,
+                                                                 int b, int tw, CriticSmallGradOut o) {
+    critic_small_grads(bw, sums, R, P, b, tw, o);
 }
 
 // tf.clip_by_norm(grad, max_norm) per variable, then Adam (TF-1: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t); m, v moments;

@@ -46,6 +46,8 @@ struct vrpb200_handle {
     float* d_critic = nullptr;      // critic constants (critic_kernels.cuh), null until set_weights saw Critic/* variables
     int critic_blocks = 0;
     float* d_loss = nullptr;        // [2] scratch of reinforce_loss
+    float* d_critic_raw = nullptr;  // raw Critic/* variables for vrpb200_critic_grad
+    CriticGradWeights critic_raw;   // device pointers into d_critic_raw (+ the actor's embedding)
     char* d_train_ws = nullptr;     // work arrays of vrpb200_actor_grad / vrpb200_clip_adam (grow-only)
     size_t train_ws_bytes = 0;
     int whole_batch_retry = 0;      // vrpb200_set_sampling_retry
@@ -174,6 +176,7 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (h->d_critic) cudaFree(h->d_critic);
     if (h->d_loss) cudaFree(h->d_loss);
     if (h->d_train_ws) cudaFree(h->d_train_ws);
+    if (h->d_critic_raw) cudaFree(h->d_critic_raw);
     if (h->d_retry) cudaFree(h->d_retry);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -436,6 +439,9 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         };
         std::vector<float> cb((size_t)nb * kCriticBlockFloats + kCriticTailFloats, 0.0f);
         std::vector<double> Au_prev(4 * H, 0.0), ce_prev(H, 0.0);
+        std::vector<float> craw;                       // raw copies for the back-propagation kernel
+        std::vector<size_t> craw_off;                  // 13 offsets per block, then 4 for the dense layers
+        auto putc = [&](const float* src, size_t cnt) { craw_off.push_back(craw.size()); if (src) craw.insert(craw.end(), src, src + cnt); };
         for (int i = 0; i < nb; ++i) {
             const std::string p = "Critic/Process/P" + std::to_string(i);
             const float* v = getc(p + "/v", H);
@@ -449,6 +455,8 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
                 pt_k = getc(p + "/proj_end_tw/kernel", H * H); pt_b = getc(p + "/proj_end_tw/bias", H);
             }
             if (!miss.empty()) break;
+            putc(v, H); putc(ed_k, H); putc(ed_b, H); putc(pd_k, (size_t)H * H); putc(pd_b, H); putc(pq_k, (size_t)H * H); putc(pq_b, H);
+            putc(pe_k, (size_t)E * H); putc(pe_b, H); putc(et_k, H); putc(et_b, H); putc(pt_k, (size_t)H * H); putc(pt_b, H);
             float* blk = &cb[(size_t)i * kCriticBlockFloats];
             std::vector<double> Au(4 * H, 0.0), ce(H, 0.0), cst(H, 0.0);
             for (int hh = 0; hh < H; ++hh) {
@@ -505,6 +513,21 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
         CUDA_TRY(h, cudaMalloc((void**)&h->d_critic, cb.size() * 4));
         CUDA_TRY(h, cudaMemcpy(h->d_critic, cb.data(), cb.size() * 4, cudaMemcpyHostToDevice));
         h->critic_blocks = nb;
+        putc(l1_k, (size_t)H * H); putc(l1_b, H); putc(l2_k, H); putc(l2_b, 1);
+        if (h->d_critic_raw) { cudaFree(h->d_critic_raw); h->d_critic_raw = nullptr; }
+        CUDA_TRY(h, cudaMalloc((void**)&h->d_critic_raw, craw.size() * 4));
+        CUDA_TRY(h, cudaMemcpy(h->d_critic_raw, craw.data(), craw.size() * 4, cudaMemcpyHostToDevice));
+        CriticGradWeights& cw = h->critic_raw;
+        memset(&cw, 0, sizeof cw);
+        cw.emb_k = d + o_emb_k; cw.emb_b = d + o_emb_b;
+        const float* cr = h->d_critic_raw;
+        for (int i = 0; i < nb; ++i) {
+            const size_t* o = &craw_off[(size_t)i * 13];
+            cw.blk[i] = CriticBlockWeights{cr + o[0], cr + o[1], cr + o[2], cr + o[3], cr + o[4], cr + o[5], cr + o[6], cr + o[7], cr + o[8],
+                                           cr + o[9], cr + o[10], cr + o[11], cr + o[12]};
+        }
+        const size_t* o = &craw_off[(size_t)nb * 13];
+        cw.l1_k = cr + o[0]; cw.l1_b = cr + o[1]; cw.l2_k = cr + o[2]; cw.l2_b = cr + o[3];
     }
     h->raw.lstm_k = d + o_lstm_k;
     h->raw.lstm_b = d + o_lstm_b;
@@ -1044,6 +1067,72 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
                     {out[G_EK0], out[G_EK0 + 1], out[G_EK0 + 2]}, {out[G_EB0], out[G_EB0 + 1], out[G_EB0 + 2]},
                     {out[G_PK0], out[G_PK0 + 1], out[G_PK0 + 2]}, {out[G_PB0], out[G_PB0 + 1], out[G_PB0 + 2]}};
     attention_small_grads_kernel<<<1, 128, 0, st>>>(w, F(o_sums), R, h->tw ? 1 : 0, so);
+    CUDA_TRY(h, cudaGetLastError());
+    return VRPB200_OK;
+}
+
+int vrpb200_critic_grad(vrpb200_handle* h, const float* d_input, int64_t B, const float* d_R, int n, const char* const* names,
+                        float* const* d_grads, const int64_t* n_elem, float* d_v, void* stream) {
+    if (!h) return VRPB200_E_ARG;
+    if (!h->have_weights || h->critic_blocks == 0) return fail(h, VRPB200_E_STATE, "critic_grad: set_weights has not seen the Critic/* variables");
+    if (!d_input || !d_R || B < 1 || n < 0 || (n > 0 && (!names || !d_grads || !n_elem))) return fail(h, VRPB200_E_ARG, "critic_grad: bad argument");
+    const vrpb200_config& c = h->cfg;
+    const int N = c.n_nodes, E = c.embedding_dim, D = c.input_dim, H = kH, P = h->critic_blocks;
+    const long long R = B;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    enum { C_V, C_EDK, C_EDB, C_PDK, C_PDB, C_PQK, C_PQB, C_PEK, C_PEB, C_ETK, C_ETB, C_PTK, C_PTB, C_PER_BLOCK };
+    const char* bn[C_PER_BLOCK] = {"v", "emb_d/kernel", "emb_d/bias", "proj_d/kernel", "proj_d/bias", "proj_q/kernel", "proj_q/bias",
+                                   "proj_e/kernel", "proj_e/bias", "emb_begin_tw/kernel", "emb_begin_tw/bias", "proj_end_tw/kernel",
+                                   "proj_end_tw/bias"};
+    const int64_t bsz[C_PER_BLOCK] = {H, H, H, (int64_t)H * H, H, (int64_t)H * H, H, (int64_t)E * H, H, H, H, (int64_t)H * H, H};
+    std::map<std::string, std::pair<int, int64_t>> known;
+    for (int b = 0; b < P; ++b)
+        for (int k = 0; k < (h->tw ? C_PER_BLOCK : C_ETK); ++k)
+            known["Critic/Process/P" + std::to_string(b) + "/" + bn[k]] = {b * C_PER_BLOCK + k, bsz[k]};
+    const int L0 = P * C_PER_BLOCK;
+    known["Critic/Linear/L1/kernel"] = {L0, (int64_t)H * H}; known["Critic/Linear/L1/bias"] = {L0 + 1, H};
+    known["Critic/Linear/L2/kernel"] = {L0 + 2, H}; known["Critic/Linear/L2/bias"] = {L0 + 3, 1};
+    std::vector<float*> out((size_t)L0 + 4, nullptr);
+    for (int i = 0; i < n; ++i) {
+        auto it = known.find(names[i] ? names[i] : "");
+        if (it == known.end()) return fail(h, VRPB200_E_ARG, "critic_grad: %s is not a variable of the critic", names[i] ? names[i] : "(null)");
+        if (n_elem[i] != it->second.second || !d_grads[i])
+            return fail(h, VRPB200_E_ARG, "critic_grad: %s has %lld elements, expected %lld", names[i], (long long)n_elem[i], (long long)it->second.second);
+        out[it->second.first] = d_grads[i];
+    }
+    size_t off = 0;
+    auto take = [&](size_t floats) { const size_t o = off; off += (floats * 4 + 255) / 256 * 256; return o; };
+    const size_t o_emb = take((size_t)R * N * E), o_ee = take((size_t)R * P * N * H), o_eeT = take((size_t)R * P * H * 128), o_prob = take((size_t)R * P * 128);
+    const size_t o_hy = take((size_t)R * (P + 1) * H), o_De = take((size_t)R * P * N * H), o_sums = take((size_t)R * P * 4 * H), o_dq = take((size_t)R * P * H);
+    const size_t o_l1 = take((size_t)R * H), o_dl1 = take((size_t)R * H), o_vdv = take((size_t)R * 2);
+    if (int rc = train_workspace(h, off)) return rc;
+    char* ws = h->d_train_ws;
+    auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
+    CriticGradDims dm{N, E, D, P, h->tw ? 1 : 0, 2.0f / (float)R};
+    CriticGradBatch bt{d_input, d_R, F(o_emb), F(o_ee), F(o_eeT), F(o_prob), F(o_hy), F(o_De), F(o_sums), F(o_dq), F(o_l1), F(o_dl1), F(o_vdv)};
+    critic_grad_rows_kernel<<<(unsigned)R, 128, 0, st>>>(h->critic_raw, dm, bt);
+    CUDA_TRY(h, cudaGetLastError());
+    auto outer = [&](const float* A, long long sAr, long long sAt, const float* Bm, long long sBr, long long sBt, int Tn, int K, int J, float* o) {
+        if (o) outer_reduce_kernel<<<(unsigned)(((long long)K * J + 127) / 128), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, Tn, K, J, o);
+    };
+    auto cols = [&](const float* Bm, long long sBr, long long sBt, int Tn, int J, float* o) {
+        if (o) col_reduce_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(Bm, sBr, sBt, R, Tn, J, o);
+    };
+    for (int b = 0; b < P; ++b) {
+        float** ob = &out[(size_t)b * C_PER_BLOCK];
+        const float* De = F(o_De) + (size_t)b * N * H;
+        outer(F(o_emb), (long long)N * E, E, De, (long long)P * N * H, H, N, E, H, ob[C_PEK]);
+        cols(De, (long long)P * N * H, H, N, H, ob[C_PEB]);
+        outer(F(o_hy) + (size_t)b * H, (long long)(P + 1) * H, 0, F(o_dq) + (size_t)b * H, (long long)P * H, 0, 1, H, H, ob[C_PQK]);
+        CriticSmallGradOut so{ob[C_V], ob[C_PQB], ob[C_EDK], ob[C_EDB], ob[C_PDK], ob[C_PDB], ob[C_ETK], ob[C_ETB], ob[C_PTK], ob[C_PTB]};
+        critic_small_grads_kernel<<<1, 128, 0, st>>>(h->critic_raw.blk[b], F(o_sums), R, P, b, h->tw ? 1 : 0, so);
+    }
+    outer(F(o_hy) + (size_t)P * H, (long long)(P + 1) * H, 0, F(o_dl1), H, 0, 1, H, H, out[L0]);
+    cols(F(o_dl1), H, 0, 1, H, out[L0 + 1]);
+    outer(F(o_l1), H, 0, F(o_vdv) + 1, 2, 0, 1, H, 1, out[L0 + 2]);
+    cols(F(o_vdv) + 1, 2, 0, 1, 1, out[L0 + 3]);
+    if (d_v) CUDA_TRY(h, cudaMemcpy2DAsync(d_v, 4, F(o_vdv), 8, 4, (size_t)R, cudaMemcpyDeviceToDevice, st));
     CUDA_TRY(h, cudaGetLastError());
     return VRPB200_OK;
 }

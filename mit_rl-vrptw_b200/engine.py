@@ -299,6 +299,24 @@ class Engine:
                                                 self._stream()), "actor_grad")
         return grads
 
+    def critic_grad(self, input_data, R, shapes: Dict[str, tuple]):
+        """compute_gradients(critic_loss, Critic variables) (attention_agent.py:290, 298-299): gradients of mean((R - v)^2);
+        returns (name -> device tensor, v [B])."""
+        x = self._f32(input_data, "input_data")
+        r = self._f32(R, "R")
+        B = x.shape[0]
+        if tuple(r.shape) != (B,):
+            raise VrpB200Error(f"R must be [{B}]")
+        names = sorted(shapes)
+        grads = {k: torch.zeros(tuple(shapes[k]), device=self.device, dtype=torch.float32) for k in names}
+        v = torch.empty((B,), device=self.device, dtype=torch.float32)
+        c_names = (C.c_char_p * len(names))(*[k.encode() for k in names])
+        c_ptrs = (C.c_void_p * len(names))(*[grads[k].data_ptr() for k in names])
+        c_sizes = (C.c_int64 * len(names))(*[grads[k].numel() for k in names])
+        self._check(self.lib.vrpb200_critic_grad(self.handle, _ptr(x), B, _ptr(r), len(names), c_names, c_ptrs, c_sizes, _ptr(v),
+                                                 self._stream()), "critic_grad")
+        return grads, v
+
     def clip_adam(self, variables, grads, m, v, max_norm: float, lr: float, step: int, beta1: float = 0.9, beta2: float = 0.999,
                   eps: float = 1e-8):
         """tf.clip_by_norm per variable + one AdamOptimizer update (attention_agent.py:303-311), in place on the device tensors

@@ -598,7 +598,7 @@ class RLAgent(object):
         self.last_time = None
         self._scope = _scope
         self._critic_built = False
-        self._adam = None                # device copies of the Actor variables + Adam slots (build_train_step)
+        self._adam = {}                  # 'actor' / 'critic' -> device copies of the variables + Adam slots (build_train_step)
 
     # -- checkpoint ------------------------------------------------------------------------------
     def Initialize(self, sess=None):
@@ -640,44 +640,59 @@ class RLAgent(object):
     def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0, apply=True):
         """attention_agent.py:272-322: ONE training step - the stochastic rollout, the critic, the two losses,
         compute_gradients(actor_loss) over the Actor variables (vrpb200_actor_grad: back-propagation through the teacher-forced
-        rollout), per-variable clip_by_norm(max_grad_norm) and the Adam update with actor_net_lr (vrpb200_clip_adam; apply=False
+        rollout) and compute_gradients(critic_loss) over the Critic variables (vrpb200_critic_grad), per-variable
+        clip_by_norm(max_grad_norm) and the two Adam updates with actor_net_lr / critic_net_lr (vrpb200_clip_adam; apply=False
         only computes).  Returns the reference's list [actor_train_step, critic_train_step, actor_loss, critic_loss,
-        actor_gra_and_var, critic_gra_and_var, R, v, logprobs, probs, actions, idxs]: actor_train_step is the number of Adam
-        steps taken so far, actor_gra_and_var a list of (gradient tensor, variable name); the critic slots are None - the
-        critic's gradient is not built (its value and loss are), nor is LSTM-input dropout (keep-probability 1).  Glimpses are
-        not differentiated: with n_glimpses > 0 the actor slots are None as well."""
+        actor_gra_and_var, critic_gra_and_var, R, v, logprobs, probs, actions, idxs]: the *_train_step slots hold the number of
+        Adam steps taken so far, the *_gra_and_var slots lists of (gradient tensor, variable name).  LSTM-input dropout is not
+        applied (keep-probability 1).  Glimpses are not differentiated: with n_glimpses > 0 the actor slots are None."""
         import torch
         R, v, logprobs, actions, idxs, batch, probs = self.build_model('stochastic', uniforms=uniforms, uniforms_retry=uniforms_retry,
                                                                        seed=seed)
         eng = self.engine()
         actor_loss, critic_loss = eng.reinforce_loss(R, v, torch.stack(logprobs))
-        if self.args['n_glimpses'] != 0:
-            return [None, None, actor_loss, critic_loss, None, None, R, v, logprobs, probs, actions, idxs]
         rows = R.shape[0]
-        weight = (R - v) / float(rows)                 # d actor_loss / d sum_t logprob[t, r]; v enters as a constant (:286)
-        sc = self._scope + 'Actor/'
-        names = [k for k in self.store.vars if k.startswith(sc)]
-        shapes = {'Actor/' + k[len(sc):]: self.store.vars[k].shape for k in names}
-        grads = eng.actor_grad(self.env.input_data, torch.stack(idxs)[:, :, 0], weight, shapes)
-        gra_and_var = [(grads['Actor/' + k[len(sc):]], k) for k in names]
-        if apply:
-            st = self._adam
-            if st is None or st['version'] != self.store.version or st['names'] != names:   # first step, or variables re-assigned
-                dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
-                old = st if st is not None and st['names'] == names else None
-                st = self._adam = dict(names=names, var=[dev(self.store.vars[k]) for k in names],
-                                       m=old['m'] if old else [torch.zeros_like(g) for g, _ in gra_and_var],
-                                       v=old['v'] if old else [torch.zeros_like(g) for g, _ in gra_and_var],
-                                       step=old['step'] if old else 0)
-            st['step'] += 1
-            eng.clip_adam(st['var'], [g for g, _ in gra_and_var], st['m'], st['v'], max_norm=self.args.get('max_grad_norm', 2.0),
-                          lr=self.args.get('actor_net_lr', 1e-4), step=st['step'])
-            for k, t in zip(names, st['var']):          # the variable collection stays the single source of truth
-                self.store.vars[k] = t.cpu().numpy().reshape(self.store.vars[k].shape)
-            self.store.version += 1
-            st['version'] = self.store.version
-        return [self._adam['step'] if self._adam else 0, None, actor_loss, critic_loss, gra_and_var, None, R, v, logprobs, probs,
-                actions, idxs]
+        out = [None, None, actor_loss, critic_loss, None, None, R, v, logprobs, probs, actions, idxs]
+        todo = []
+        if self.args['n_glimpses'] == 0:
+            sc = self._scope + 'Actor/'
+            names = [k for k in self.store.vars if k.startswith(sc)]
+            weight = (R - v) / float(rows)             # d actor_loss / d sum_t logprob[t, r]; v enters as a constant (:286)
+            grads = eng.actor_grad(self.env.input_data, torch.stack(idxs)[:, :, 0], weight,
+                                   {'Actor/' + k[len(sc):]: self.store.vars[k].shape for k in names})
+            out[4] = [(grads['Actor/' + k[len(sc):]], k) for k in names]
+            todo.append((0, 'actor', names, out[4], self.args.get('actor_net_lr', 1e-4)))
+        if self.clAttentionCritic is not None:
+            sc = self._scope + 'Critic/'
+            names = [k for k in self.store.vars if k.startswith(sc)]
+            grads, _ = eng.critic_grad(self.env.input_data, R, {'Critic/' + k[len(sc):]: self.store.vars[k].shape for k in names})
+            out[5] = [(grads['Critic/' + k[len(sc):]], k) for k in names]
+            todo.append((1, 'critic', names, out[5], self.args.get('critic_net_lr', 1e-4)))
+        for slot, kind, names, gv, lr in todo:
+            out[slot] = self._adam[kind]['step'] if kind in self._adam else 0
+            if apply:
+                out[slot] = self._apply_adam(eng, kind, names, [g for g, _ in gv], lr)
+        return out
+
+    def _apply_adam(self, eng, kind, names, grads, lr):
+        """clip_by_norm + Adam on device copies of the variables (attention_agent.py:303-311); the variable collection stays the
+        single source of truth and is re-read whenever something else assigned to it."""
+        import torch
+        st = self._adam.get(kind)
+        if st is None or st['names'] != names or any(self.store.vars[k] is not a for k, a in zip(names, st['host'])):
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+            keep = st is not None and st['names'] == names           # same variables, new values (a restore): the slots stay
+            st = self._adam[kind] = dict(names=names, var=[dev(self.store.vars[k]) for k in names],
+                                         m=st['m'] if keep else [torch.zeros_like(g) for g in grads],
+                                         v=st['v'] if keep else [torch.zeros_like(g) for g in grads], step=st['step'] if keep else 0)
+        st['step'] += 1
+        eng.clip_adam(st['var'], grads, st['m'], st['v'], max_norm=self.args.get('max_grad_norm', 2.0), lr=lr, step=st['step'])
+        st['host'] = []
+        for k, t in zip(names, st['var']):
+            self.store.vars[k] = t.cpu().numpy().reshape(self.store.vars[k].shape)
+            st['host'].append(self.store.vars[k])
+        self.store.version += 1
+        return st['step']
 
     def engine(self):
         eargs = dict(self.args)

@@ -38,3 +38,31 @@ extern "C" int actor_grad_host(const float* const* wp /*21 pointers in ActorGrad
     attention_small_grads(w, sums, R, tw, o);
     return 0;
 }
+
+#include "../../mit_rl-vrptw_b200/csrc/critic_grad_row.h"
+
+extern "C" int critic_grad_host(const float* const* wp /*110 pointers in CriticGradWeights order*/, int N, int E, int D, int P, int tw,
+                                long long R, const float* input, const float* Rw /*[R]*/, float* hyin /*[R,P+1,H]*/, float* De /*[R,P,N,H]*/,
+                                float* sums /*[R,P,4,H]*/, float* dq /*[R,P,H]*/, float* l1 /*[R,H]*/, float* dl1 /*[R,H]*/, float* vdv /*[R,2]*/,
+                                float* emb /*[R,N,E]*/, float* const* small /*[P][10] pointers in CriticSmallGradOut order*/) {
+    CriticGradWeights w;
+    static_assert(sizeof(CriticGradWeights) == 110 * sizeof(void*), "layout");
+    std::memcpy(&w, wp, sizeof w);
+    CriticGradDims d{N, E, D, P, tw, 2.0f / (float)R};
+    const int H = kAgH;
+    std::vector<float> ee((size_t)P * N * H), eeT((size_t)P * H * 128), prob((size_t)P * 128);
+    for (long long r = 0; r < R; ++r) {
+        CriticGradRow row;
+        row.input = input + r * N * D; row.R = Rw[r]; row.emb = emb + r * N * E; row.ee = ee.data(); row.eeT = eeT.data(); row.prob = prob.data();
+        row.hyin = hyin + r * (P + 1) * H; row.De = De + r * (long long)P * N * H; row.sums = sums + r * P * 4 * H; row.dq = dq + r * P * H;
+        row.l1 = l1 + r * H; row.dl1 = dl1 + r * H; row.vdv = vdv + r * 2;
+        critic_grad_row(w, d, row);
+    }
+    static_assert(sizeof(CriticSmallGradOut) == 10 * sizeof(void*), "layout");
+    for (int b = 0; b < P; ++b) {
+        CriticSmallGradOut o;
+        std::memcpy(&o, small + b * 10, sizeof o);
+        critic_small_grads(w.blk[b], sums, R, P, b, tw, o);
+    }
+    return 0;
+}

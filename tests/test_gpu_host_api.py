@@ -445,7 +445,7 @@ def test_rlagent_build_train_step_forward_side():
     rnd = np.random.RandomState(3)
     u1, u2 = rnd.uniform(size=(T, 32)).astype(np.float32), rnd.uniform(size=(T, 32)).astype(np.float32)
     step = agent.build_train_step(uniforms=u1, uniforms_retry=u2, apply=False)      # compute only: the variables stay as they are
-    assert len(step) == 12 and step[0] == 0 and step[1] is None
+    assert len(step) == 12 and step[0] == 0 and step[1] == 0
     names = {k for k in store.vars if k.startswith("Critic/")}
     assert "Critic/Process/P2/proj_end_tw/kernel" in names and "Critic/Linear/L2/bias" in names and len(names) == 3 * 13 + 4
     params = {k: v for k, v in store.vars.items() if k != "decoder_input"}

@@ -8,6 +8,8 @@ from oracle import restatement as O
 from oracle import train_torch as TT
 from tests.helpers import load_pkg
 from tests.test_actor_grad_cpu import check, make_case
+from tests.test_critic_grad_cpu import check as check_c
+from tests.test_critic_grad_cpu import make_case as make_case_c
 
 pytestmark = pytest.mark.gpu
 
@@ -65,6 +67,27 @@ def test_actor_gradient_follows_the_rollout_kernel():
         eng.actor_grad(x, out.idxs, torch.from_numpy(weight).cuda(), {"Actor/Decoder/Attention/v": (1, 7)})
 
 
+@pytest.mark.parametrize("task,B", [("vrptw10", 7), ("vrp10", 7), ("vrptw20", 128), ("vrptw50", 64)])
+def test_critic_gradient_matches_autograd(task, B):
+    """compute_gradients(critic_loss) (attention_agent.py:290, 298-299): every Critic variable's gradient of mean((R - v)^2) against
+    autograd through the as-written critic, and the value it was taken at against the pinned oracle."""
+    args, params, data, Rw = make_case_c(task, B, 41)
+    eng, torch, pkg = _engine(args, params)
+    names = [k for k in params if k.startswith("Critic/")]
+    got, v = eng.critic_grad(torch.from_numpy(data).cuda(), torch.from_numpy(Rw).cuda(), {k: params[k].shape for k in names})
+    torch.cuda.synchronize()
+    loss, want, v_ref = TT.critic_grads(params, args, data, Rw)
+    np.testing.assert_allclose(v.cpu().numpy(), v_ref, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(v.cpu().numpy(), eng.critic(torch.from_numpy(data).cuda()).cpu().numpy(), rtol=1e-4, atol=2e-6)
+    check_c({k: g.cpu().numpy() for k, g in got.items()}, want, names, max(np.abs(w).max() for w in want.values()))
+    again, _ = eng.critic_grad(torch.from_numpy(data).cuda(), torch.from_numpy(Rw).cuda(), {k: params[k].shape for k in names})
+    for k in names:
+        assert torch.equal(got[k], again[k]), k
+    eng2, _, _ = _engine(args, {k: a for k, a in params.items() if k.startswith("Actor/")})
+    with pytest.raises(pkg.VrpB200Error):
+        eng2.critic_grad(torch.from_numpy(data).cuda(), torch.from_numpy(Rw).cuda(), {})
+
+
 def test_clip_by_norm_and_adam_match_the_tf1_formulas():
     """attention_agent.py:303-311: per-variable clip_by_norm, then Adam with TF-1's bias-corrected step size; three steps on a
     clipped and an un-clipped variable against the numpy statement of the same formulas."""
@@ -88,15 +111,15 @@ def test_clip_by_norm_and_adam_match_the_tf1_formulas():
             np.testing.assert_allclose(dvar[i].cpu().numpy(), var[i], rtol=1e-5, atol=2e-7)
 
 
-def test_rlagent_train_step_updates_the_actor():
-    """RLAgent.build_train_step() end to end (attention_agent.py:272-322): gradients of the agent's own variables against
-    autograd, then two Adam steps against the numpy statement of clip_by_norm + Adam applied to those gradients; the store is
-    the updated variable collection afterwards and the next rollout uses it."""
+def test_rlagent_train_step_updates_actor_and_critic():
+    """RLAgent.build_train_step() end to end (attention_agent.py:272-322): the gradients of the agent's own Actor and Critic
+    variables against autograd, then two Adam steps of each optimizer against the numpy statement of clip_by_norm + Adam applied
+    to those gradients; the store is the updated variable collection afterwards and the next rollout uses it."""
     import torch
     pkg = load_pkg()
     H = pkg.host
     args = O.default_args("vrptw10")
-    args.update(actor_net_lr=1e-3, max_grad_norm=2.0)
+    args.update(actor_net_lr=1e-3, critic_net_lr=2e-3, max_grad_norm=2.0)
     comps = H.load_task_specific_components("vrptw", False)
     store = H.VariableStore(seed=5)
     env = comps[1](args)
@@ -105,25 +128,31 @@ def test_rlagent_train_step_updates_the_actor():
     env.input_data = torch.from_numpy(data)
     T = args["decode_len"]
     rnd = np.random.RandomState(3)
+    agent.build_train_step(uniforms=rnd.uniform(size=(T, 32)).astype(np.float32), uniforms_retry=rnd.uniform(size=(T, 32)).astype(np.float32),
+                           apply=False)                      # creates the Critic variables, changes nothing
     m, v = {}, {}
     for step_no in (1, 2):
         u1, u2 = rnd.uniform(size=(T, 32)).astype(np.float32), rnd.uniform(size=(T, 32)).astype(np.float32)
         before = {k: a.copy() for k, a in store.vars.items()}
         step = agent.build_train_step(uniforms=u1, uniforms_retry=u2)
-        assert step[0] == step_no and step[1] is None and step[5] is None
+        assert step[0] == step_no and step[1] == step_no
         R, vv = step[6].cpu().numpy(), step[7].cpu().numpy()
         idxs = torch.stack(step[11])[:, :, 0].cpu().numpy().astype(np.int32)
         params = {k: a for k, a in before.items() if k != "decoder_input"}
         _, want, _, _ = TT.actor_grads(params, args, data, idxs, ((R - vv) / 32).astype(np.float32))
+        _, want_c, v_ref = TT.critic_grads(params, args, data, R)
+        np.testing.assert_allclose(vv, v_ref, rtol=1e-4, atol=2e-6)
         got = {name: g.cpu().numpy() for g, name in step[4]}
-        assert set(got) == {k for k in params if k.startswith("Actor/")}
+        got_c = {name: g.cpu().numpy() for g, name in step[5]}
+        assert set(got) == {k for k in params if k.startswith("Actor/")} and set(got_c) == {k for k in params if k.startswith("Critic/")}
         check(got, want, list(got))
-        for k, g in got.items():
-            if k not in m:
-                m[k], v[k] = np.zeros_like(g), np.zeros_like(g)
-            new, m[k], v[k] = TT.clip_adam(before[k], g, m[k], v[k], step_no, 1e-3, 2.0)
-            np.testing.assert_allclose(store.vars[k], new, rtol=1e-5, atol=2e-7, err_msg=k)
-            assert np.abs(store.vars[k] - before[k]).max() > 1e-4, k          # Adam's first steps move every variable by ~lr
-        for k in before:
-            if not k.startswith("Actor/"):
-                np.testing.assert_array_equal(store.vars[k], before[k])     # critic variables: no gradient built, untouched
+        check_c(got_c, want_c, list(got_c), max(np.abs(w).max() for w in want_c.values()))
+        for grads, lr in ((got, 1e-3), (got_c, 2e-3)):
+            for k, g in grads.items():
+                if k not in m:
+                    m[k], v[k] = np.zeros_like(g), np.zeros_like(g)
+                new, m[k], v[k] = TT.clip_adam(before[k], g, m[k], v[k], step_no, lr, 2.0)
+                np.testing.assert_allclose(store.vars[k], new, rtol=1e-5, atol=2e-7, err_msg=k)
+                if np.abs(g).max() > 0:
+                    assert np.abs(store.vars[k] - before[k]).max() > 1e-4, k      # Adam's first steps move every variable by ~lr
+        np.testing.assert_array_equal(store.vars["decoder_input"], before["decoder_input"])
