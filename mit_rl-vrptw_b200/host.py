@@ -598,6 +598,7 @@ class RLAgent(object):
         self.last_time = None
         self._scope = _scope
         self._critic_built = False
+        self._train_calls = 0
         self._adam = {}                  # 'actor' / 'critic' -> device copies of the variables + Adam slots (build_train_step)
 
     # -- checkpoint ------------------------------------------------------------------------------
@@ -673,6 +674,22 @@ class RLAgent(object):
             if apply:
                 out[slot] = self._apply_adam(eng, kind, names, [g for g, _ in gv], lr)
         return out
+
+    def run_train_step(self, uniforms=None, uniforms_retry=None):
+        """attention_agent.py:530-556: draw the next training batch from the data generator, feed it to the Env and run the train
+        step on it.  (The reference also feeds args['dropout'] to the LSTM input and a feature-normalised copy of the batch that
+        only the graph embeddings read; neither is on this path.)  Without uniforms the sampling stream is the in-kernel one,
+        seeded by the step count."""
+        import torch
+        data = self.dataGen.get_train_next()
+        self.env.input_data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
+        self._train_calls += 1
+        return self.build_train_step(uniforms=uniforms, uniforms_retry=uniforms_retry,
+                                     seed=int(self.args.get('random_seed', 0)) * 1000003 + self._train_calls)
+
+    def save_model(self, path):
+        """saver.save (main.py:131): every variable of the collection under its TF name, as load_model reads it back."""
+        self.store.save(path)
 
     def _apply_adam(self, eng, kind, names, grads, lr):
         """clip_by_norm + Adam on device copies of the variables (attention_agent.py:303-311); the variable collection stays the

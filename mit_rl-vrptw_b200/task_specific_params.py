@@ -33,7 +33,7 @@ def default_args(task: str, **over) -> dict:
     a = dict(task=task, embedding_dim=30, hidden_dim=128, rnn_layers=1, n_glimpses=0, use_tanh=False,
              tanh_exploration=10.0, mask_glimpses=True, mask_pointer=True, forget_bias=1.0, beam_width=5,
              embedding_graph=0, min_trucks=False, ups=False, random_seed=24601, test_size=1000, batch_size=128,
-             dropout=0.1, decode_len=t.decode_len)
+             dropout=0.1, decode_len=t.decode_len, n_process_blocks=3, actor_net_lr=1e-4, critic_net_lr=1e-4, max_grad_norm=2.0)
     a.update(t._asdict())
     a.update(over)
     return a
