@@ -45,6 +45,8 @@ struct ActorGradWeights {   // raw variables, TF layout (device pointers in the 
     const float *emb_t_k, *emb_t_b, *proj_t_k, *proj_t_b;       // VRPTW only
     const float *proj_q_k, *proj_q_b;                           // [H, H], [H]
     const float *proj_ref_k, *proj_ref_b;                       // [E, H], [H]
+    const float *lstm_kT, *proj_q_kT;   // transposed copies [4H, E + H], [H(out), H(in)]: the backward products read along a thread's
+                                        // own input index, which is the contiguous one here (coalesced over the threads)
 };
 
 struct ActorGradDims {
@@ -123,13 +125,16 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
             s_hprev[i] = r.hs[t * H + i];
         AG_END
         AG_PAR(i)
-            float g4[4];
-            for (int a = 0; a < 4; ++a) {
-                const int j = a * H + i;
-                float s = w.lstm_b[j];
-                for (int k = 0; k < E; ++k) s += s_x[k] * w.lstm_k[k * 4 * H + j];
-                for (int k = 0; k < H; ++k) s += s_hprev[k] * w.lstm_k[(E + k) * 4 * H + j];
-                g4[a] = s;
+            float g4[4] = {w.lstm_b[i], w.lstm_b[H + i], w.lstm_b[2 * H + i], w.lstm_b[3 * H + i]};   // the four gates side by side:
+            for (int k = 0; k < E; ++k) {                                                               // four independent loads per k
+                const float* kr = w.lstm_k + (long long)k * 4 * H + i;
+                const float x = s_x[k];
+                g4[0] += x * kr[0]; g4[1] += x * kr[H]; g4[2] += x * kr[2 * H]; g4[3] += x * kr[3 * H];
+            }
+            for (int k = 0; k < H; ++k) {
+                const float* kr = w.lstm_k + (long long)(E + k) * 4 * H + i;
+                const float x = s_hprev[k];
+                g4[0] += x * kr[0]; g4[1] += x * kr[H]; g4[2] += x * kr[2 * H]; g4[3] += x * kr[3 * H];
             }
             const float si = ag_sigmoid(g4[0]), tj = tanhf(g4[1]), sf = ag_sigmoid(g4[2] + d.forget_bias), so = ag_sigmoid(g4[3]);
             const float cn = r.cs[t * H + i] * sf + si * tj;
@@ -201,7 +206,7 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
         AG_END
         AG_PAR(i)   // through proj_q into the LSTM output, then the cell of step t
             float dh = s_dh[i];
-            for (int h = 0; h < H; ++h) dh += w.proj_q_k[i * H + h] * s_dq[h];
+            for (int h = 0; h < H; ++h) dh += w.proj_q_kT[h * H + i] * s_dq[h];
             const float si = r.act[t * 4 * H + i], tj = r.act[t * 4 * H + H + i], sf = r.act[t * 4 * H + 2 * H + i], so = r.act[t * 4 * H + 3 * H + i];
             const float tc = tanhf(r.cs[(t + 1) * H + i]);
             const float dc = s_dc[i] + dh * so * (1.0f - tc * tc);
@@ -213,13 +218,13 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
         AG_END
         AG_PAR(i)   // into the previous LSTM output and the step's input
             float dh = 0.0f;
-            const float* kr = w.lstm_k + (long long)(E + i) * 4 * H;
-            for (int j = 0; j < 4 * H; ++j) dh += kr[j] * s_dg[j];
+            const float* kr = w.lstm_kT + E + i;
+            for (int j = 0; j < 4 * H; ++j) dh += kr[(long long)j * (E + H)] * s_dg[j];
             s_dh[i] = dh;
             if (i < E) {
                 float dxv = 0.0f;
-                const float* kx = w.lstm_k + (long long)i * 4 * H;
-                for (int j = 0; j < 4 * H; ++j) dxv += kx[j] * s_dg[j];
+                const float* kx = w.lstm_kT + i;
+                for (int j = 0; j < 4 * H; ++j) dxv += kx[(long long)j * (E + H)] * s_dg[j];
                 r.dx[t * E + i] = dxv;
             }
         AG_END

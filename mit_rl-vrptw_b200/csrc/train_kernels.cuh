@@ -57,35 +57,47 @@ __global__ void idx_to_i64_kernel(const int* __restrict__ in, long long* __restr
     if (i < n) out[i] = in[i];
 }
 
-// out[k * J + j] = sum_{r < R} sum_{t < Tn} A[r * sAr + t * sAt + k] * B[r * sBr + t * sBt + j]
+// part[y][k * J + j] = sum over the rows r of split y, then over t < Tn, of A[r * sAr + t * sAt + k] * B[r * sBr + t * sBt + j];
+// blockIdx.y = split (rows_per_split consecutive rows).  sum_splits_kernel adds the splits in order: two fixed-order stages.
 __global__ void outer_reduce_kernel(const float* __restrict__ A, long long sAr, long long sAt, const float* __restrict__ Bm,
-                                    long long sBr, long long sBt, long long R, int Tn, int K, int J, float* __restrict__ out) {
+                                    long long sBr, long long sBt, long long R, int rows_per_split, int Tn, int K, int J,
+                                    float* __restrict__ part) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)K * J) return;
     const int k = (int)(i / J), j = (int)(i - (long long)k * J);
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
     float s = 0.0f;
-    for (long long r = 0; r < R; ++r) {
+    for (long long r = r0; r < r1; ++r) {
         const float* a = A + r * sAr + k;
         const float* b = Bm + r * sBr + j;
         float sr = 0.0f;
         for (int t = 0; t < Tn; ++t) sr = fmaf(a[t * sAt], b[t * sBt], sr);
         s += sr;
     }
-    out[i] = s;
+    part[(long long)blockIdx.y * K * J + i] = s;
 }
 
-__global__ void col_reduce_kernel(const float* __restrict__ Bm, long long sBr, long long sBt, long long R, int Tn, int J,
-                                  float* __restrict__ out) {
+__global__ void col_reduce_kernel(const float* __restrict__ Bm, long long sBr, long long sBt, long long R, int rows_per_split, int Tn,
+                                  int J, float* __restrict__ part) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= J) return;
+    const long long r0 = (long long)blockIdx.y * rows_per_split, r1 = r0 + rows_per_split < R ? r0 + rows_per_split : R;
     float s = 0.0f;
-    for (long long r = 0; r < R; ++r) {
+    for (long long r = r0; r < r1; ++r) {
         const float* b = Bm + r * sBr + j;
         float sr = 0.0f;
         for (int t = 0; t < Tn; ++t) sr += b[t * sBt];
         s += sr;
     }
-    out[j] = s;
+    part[(long long)blockIdx.y * J + j] = s;
+}
+
+__global__ void sum_splits_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = 0.0f;
+    for (int y = 0; y < S; ++y) s += part[(long long)y * n + i];
+    out[i] = s;
 }
 
 __global__ void __launch_bounds__(128) attention_small_grads_kernel(ActorGradWeights w, const float* __restrict__ sums, long long R,

@@ -48,6 +48,8 @@ struct vrpb200_handle {
     float* d_loss = nullptr;        // [2] scratch of reinforce_loss
     float* d_critic_raw = nullptr;  // raw Critic/* variables for vrpb200_critic_grad
     CriticGradWeights critic_raw;   // device pointers into d_critic_raw (+ the actor's embedding)
+    void* d_adam_vars = nullptr;    // variable table of vrpb200_clip_adam
+    int adam_vars_cap = 0;
     char* d_train_ws = nullptr;     // work arrays of vrpb200_actor_grad / vrpb200_clip_adam (grow-only)
     size_t train_ws_bytes = 0;
     int whole_batch_retry = 0;      // vrpb200_set_sampling_retry
@@ -55,6 +57,7 @@ struct vrpb200_handle {
     int last_redraws = 0;
     RawModel raw;
     const float *raw_emb_k = nullptr, *raw_emb_b = nullptr;
+    const float *raw_lstm_kT = nullptr, *raw_pq_kT = nullptr;   // [4H, E + H], pointer module's proj_q [H(out), H(in)]
     // staging of the *_host call: kChunks in-flight chunks, one stream each
     static constexpr int kChunks = 3;
     float* dev_in[kChunks] = {nullptr, nullptr, nullptr};
@@ -177,6 +180,7 @@ int vrpb200_destroy(vrpb200_handle* h) {
     if (h->d_loss) cudaFree(h->d_loss);
     if (h->d_train_ws) cudaFree(h->d_train_ws);
     if (h->d_critic_raw) cudaFree(h->d_critic_raw);
+    if (h->d_adam_vars) cudaFree(h->d_adam_vars);
     if (h->d_retry) cudaFree(h->d_retry);
     for (int i = 0; i < vrpb200_handle::kChunks; ++i) {
         if (h->dev_in[i]) cudaFree(h->dev_in[i]);
@@ -379,6 +383,12 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     // raw copies for the stand-alone (as-written) kernels
     const size_t o_emb_k = put(emb_k, (size_t)D1 * E), o_emb_b = put(emb_b, E);
     const size_t o_lstm_k = put(lstm_k, (size_t)(E + H) * 4 * H), o_lstm_b = put(lstm_b, 4 * H);
+    std::vector<float> lstm_kT((size_t)4 * H * (E + H)), pq_kT((size_t)H * H);   // transposed copies for the back-propagation kernel
+    for (int k = 0; k < E + H; ++k)
+        for (int j = 0; j < 4 * H; ++j) lstm_kT[(size_t)j * (E + H) + k] = lstm_k[(size_t)k * 4 * H + j];
+    for (int k = 0; k < H; ++k)
+        for (int j = 0; j < H; ++j) pq_kT[(size_t)j * H + k] = rh[natt - 1].pq_k[(size_t)k * H + j];
+    const size_t o_lstm_kT = put(lstm_kT.data(), lstm_kT.size()), o_pq_kT = put(pq_kT.data(), pq_kT.size());
     struct RawOff { size_t v, ed_k, ed_b, eld_k, eld_b, et_k, et_b, pd_k, pd_b, pld_k, pld_b, pt_k, pt_b, pq_k, pq_b, pr_k, pr_b; };
     std::vector<RawOff> ro(natt);
     for (int a = 0; a < natt; ++a) {
@@ -534,6 +544,8 @@ int vrpb200_set_weights(vrpb200_handle* h, int n, const char* const* names, cons
     h->raw.n_glimpses = c.n_glimpses;
     h->raw_emb_k = d + o_emb_k;
     h->raw_emb_b = d + o_emb_b;
+    h->raw_lstm_kT = d + o_lstm_kT;
+    h->raw_pq_kT = d + o_pq_kT;
     h->have_weights = true;
     return VRPB200_OK;
 }
@@ -1012,6 +1024,9 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
     const size_t o_xin = take((size_t)R * T * E), o_dx = take((size_t)R * T * E), o_emb = take((size_t)R * N * E);
     const size_t o_eref = take((size_t)R * N * H), o_erefT = take((size_t)R * H * 128), o_dg = take((size_t)R * T * 4 * H);
     const size_t o_dq = take((size_t)R * T * H), o_Ds = take((size_t)R * N * H), o_demb = take((size_t)R * N * E), o_sums = take((size_t)R * 5 * H);
+    const int S = (int)std::min<long long>(R, 32);                  // splits of the device-wide reductions (fixed, so the order is)
+    const int rps = (int)((R + S - 1) / S);
+    const size_t o_part = take((size_t)S * H * 4 * H);
     if (int rc = train_workspace(h, off)) return rc;
     char* ws = h->d_train_ws;
     auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
@@ -1036,10 +1051,10 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
     }
     CUDA_TRY(h, cudaGetLastError());
 
-    const RawAtt& ra = h->raw.att[0];
+    const RawAtt& ra = h->raw.att[0];   // n_glimpses == 0: module 0 is the pointer
     ActorGradWeights w{h->raw_emb_k, h->raw_emb_b, h->raw.lstm_k, h->raw.lstm_b, ra.v,
                        ra.emb_d_k, ra.emb_d_b, ra.proj_d_k, ra.proj_d_b, ra.emb_ld_k, ra.emb_ld_b, ra.proj_ld_k, ra.proj_ld_b,
-                       ra.emb_t_k, ra.emb_t_b, ra.proj_t_k, ra.proj_t_b, ra.proj_q_k, ra.proj_q_b, ra.proj_ref_k, ra.proj_ref_b};
+                       ra.emb_t_k, ra.emb_t_b, ra.proj_t_k, ra.proj_t_b, ra.proj_q_k, ra.proj_q_b, ra.proj_ref_k, ra.proj_ref_b, h->raw_lstm_kT, h->raw_pq_kT};
     ActorGradDims dm{N, E, D, T, h->tw ? 1 : 0, c.use_tanh, c.mask_pointer, c.tanh_exploration, c.forget_bias};
     ActorGradBatch bt{d_input, d_idx, d_weight, F(o_dem), F(o_msk), F(o_load), h->tw ? F(o_time) : nullptr,
                       F(o_hs), F(o_cs), F(o_act), F(o_xin), F(o_dx), F(o_emb), F(o_eref), F(o_erefT), F(o_dg), F(o_dq), F(o_Ds), F(o_demb),
@@ -1049,10 +1064,15 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
 
     // device-wide reductions, one fixed order
     auto outer = [&](const float* A, long long sAr, long long sAt, const float* Bm, long long sBr, long long sBt, int Tn, int K, int J, float* o) {
-        if (o) outer_reduce_kernel<<<(unsigned)(((long long)K * J + 127) / 128), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, Tn, K, J, o);
+        if (!o) return;
+        const long long nel = (long long)K * J;
+        outer_reduce_kernel<<<dim3((unsigned)((nel + 127) / 128), (unsigned)S), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, rps, Tn, K, J, F(o_part));
+        sum_splits_kernel<<<(unsigned)((nel + 127) / 128), 128, 0, st>>>(F(o_part), S, nel, o);
     };
     auto cols = [&](const float* Bm, long long sBr, long long sBt, int Tn, int J, float* o) {
-        if (o) col_reduce_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(Bm, sBr, sBt, R, Tn, J, o);
+        if (!o) return;
+        col_reduce_kernel<<<dim3((unsigned)((J + 127) / 128), (unsigned)S), 128, 0, st>>>(Bm, sBr, sBt, R, rps, Tn, J, F(o_part));
+        sum_splits_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(F(o_part), S, J, o);
     };
     if (out[G_LSTM_K]) {   // rows 0..E-1: the inputs x_t; rows E..E+H-1: the previous outputs h_{t-1}
         outer(F(o_xin), (long long)T * E, E, F(o_dg), (long long)T * 4 * H, 4 * H, T, E, 4 * H, out[G_LSTM_K]);
@@ -1106,6 +1126,9 @@ int vrpb200_critic_grad(vrpb200_handle* h, const float* d_input, int64_t B, cons
     const size_t o_emb = take((size_t)R * N * E), o_ee = take((size_t)R * P * N * H), o_eeT = take((size_t)R * P * H * 128), o_prob = take((size_t)R * P * 128);
     const size_t o_hy = take((size_t)R * (P + 1) * H), o_De = take((size_t)R * P * N * H), o_sums = take((size_t)R * P * 4 * H), o_dq = take((size_t)R * P * H);
     const size_t o_l1 = take((size_t)R * H), o_dl1 = take((size_t)R * H), o_vdv = take((size_t)R * 2);
+    const int S = (int)std::min<long long>(R, 32);
+    const int rps = (int)((R + S - 1) / S);
+    const size_t o_part = take((size_t)S * H * H);
     if (int rc = train_workspace(h, off)) return rc;
     char* ws = h->d_train_ws;
     auto F = [&](size_t o) { return reinterpret_cast<float*>(ws + o); };
@@ -1114,10 +1137,15 @@ int vrpb200_critic_grad(vrpb200_handle* h, const float* d_input, int64_t B, cons
     critic_grad_rows_kernel<<<(unsigned)R, 128, 0, st>>>(h->critic_raw, dm, bt);
     CUDA_TRY(h, cudaGetLastError());
     auto outer = [&](const float* A, long long sAr, long long sAt, const float* Bm, long long sBr, long long sBt, int Tn, int K, int J, float* o) {
-        if (o) outer_reduce_kernel<<<(unsigned)(((long long)K * J + 127) / 128), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, Tn, K, J, o);
+        if (!o) return;
+        const long long nel = (long long)K * J;
+        outer_reduce_kernel<<<dim3((unsigned)((nel + 127) / 128), (unsigned)S), 128, 0, st>>>(A, sAr, sAt, Bm, sBr, sBt, R, rps, Tn, K, J, F(o_part));
+        sum_splits_kernel<<<(unsigned)((nel + 127) / 128), 128, 0, st>>>(F(o_part), S, nel, o);
     };
     auto cols = [&](const float* Bm, long long sBr, long long sBt, int Tn, int J, float* o) {
-        if (o) col_reduce_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(Bm, sBr, sBt, R, Tn, J, o);
+        if (!o) return;
+        col_reduce_kernel<<<dim3((unsigned)((J + 127) / 128), (unsigned)S), 128, 0, st>>>(Bm, sBr, sBt, R, rps, Tn, J, F(o_part));
+        sum_splits_kernel<<<(unsigned)((J + 127) / 128), 128, 0, st>>>(F(o_part), S, J, o);
     };
     for (int b = 0; b < P; ++b) {
         float** ob = &out[(size_t)b * C_PER_BLOCK];
@@ -1148,14 +1176,17 @@ int vrpb200_clip_adam(vrpb200_handle* h, int n, float* const* d_vars, const floa
         if (!d_vars[i] || !d_grads[i] || !d_m[i] || !d_v[i] || n_elem[i] < 1) return fail(h, VRPB200_E_ARG, "clip_adam: variable %d: bad argument", i);
         hv[i] = AdamVar{d_vars[i], d_grads[i], d_m[i], d_v[i], (long long)n_elem[i]};
     }
-    AdamVar* dv = nullptr;
-    CUDA_TRY(h, cudaMallocAsync((void**)&dv, sizeof(AdamVar) * n, (cudaStream_t)stream));
+    if (h->adam_vars_cap < n) {   // the variable table lives in a small buffer of the handle
+        if (h->d_adam_vars) { CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream)); cudaFree(h->d_adam_vars); h->d_adam_vars = nullptr; }
+        CUDA_TRY(h, cudaMalloc(&h->d_adam_vars, sizeof(AdamVar) * (size_t)n));
+        h->adam_vars_cap = n;
+    }
+    AdamVar* dv = static_cast<AdamVar*>(h->d_adam_vars);
+    // pageable source: the runtime stages it before the call returns, so hv may go out of scope; stream order protects dv
     CUDA_TRY(h, cudaMemcpyAsync(dv, hv.data(), sizeof(AdamVar) * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
-    CUDA_TRY(h, cudaStreamSynchronize((cudaStream_t)stream));   // hv is pageable host memory about to go out of scope
     const double lr_t = (double)lr * std::sqrt(1.0 - std::pow((double)beta2, (double)step)) / (1.0 - std::pow((double)beta1, (double)step));
     clip_adam_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dv, max_norm, (float)lr_t, beta1, beta2, eps);
     CUDA_TRY(h, cudaGetLastError());
-    CUDA_TRY(h, cudaFreeAsync(dv, (cudaStream_t)stream));
     return VRPB200_OK;
 }
 

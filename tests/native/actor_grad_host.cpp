@@ -7,7 +7,7 @@
 
 using namespace vrpb200;
 
-extern "C" int actor_grad_host(const float* const* wp /*21 pointers in ActorGradWeights order*/, int N, int E, int D, int T, int tw,
+extern "C" int actor_grad_host(const float* const* wp /*23 pointers in ActorGradWeights order*/, int N, int E, int D, int T, int tw,
                                int use_tanh, int mask_pointer, float C, float forget_bias, long long R, const float* input,
                                const int* idx /*[T,R]*/, const float* weight, const float* demand /*[T,R,N]*/,
                                const float* mask, const float* load /*[T,R]*/, const float* time,
@@ -15,7 +15,7 @@ extern "C" int actor_grad_host(const float* const* wp /*21 pointers in ActorGrad
                                float* sums /*[R,5,H]*/, float* hs /*[R,T+1,H]*/, float* xin /*[R,T,E]*/, float* emb /*[R,N,E]*/,
                                float* const* small /*15 pointers in SmallGradOut order*/) {
     ActorGradWeights w;
-    static_assert(sizeof(ActorGradWeights) == 21 * sizeof(void*), "layout");
+    static_assert(sizeof(ActorGradWeights) == 23 * sizeof(void*), "layout");
     std::memcpy(&w, wp, sizeof w);
     ActorGradDims d{N, E, D, T, tw, use_tanh, mask_pointer, C, forget_bias};
     const int H = kAgH;

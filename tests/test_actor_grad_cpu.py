@@ -33,7 +33,11 @@ def weight_arrays(params, tw):
         e, p = ("emb_time", "proj_t") if blk == "t" else ("emb_" + blk, "proj_" + blk)
         order += [f"{ATT}/{e}/kernel", f"{ATT}/{e}/bias", f"{ATT}/{p}/kernel", f"{ATT}/{p}/bias"]
     order += [f"{ATT}/proj_q/kernel", f"{ATT}/proj_q/bias", f"{ATT}/proj_ref/kernel", f"{ATT}/proj_ref/bias"]
-    return order, [g(n) if n in params else z for n in order]
+    arrs = [g(n) if n in params else z for n in order]
+    E = params["Actor/Embedding/conv1d/kernel"].shape[-1]
+    arrs.append(np.ascontiguousarray(np.asarray(params[LSTM + "/kernel"], np.float32).reshape(E + 128, 512).T).reshape(-1))   # lstm_kT
+    arrs.append(np.ascontiguousarray(np.asarray(params[ATT + "/proj_q/kernel"], np.float32).reshape(128, 128).T).reshape(-1))  # proj_q_kT
+    return order, arrs
 
 
 def run_host(lib, params, args, data, idxs, weight, st):

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests/gpu_train_pending.py tests/test_gpu_train.py -m gpu -q --timeout 180 --timeout-method=thread -p no:cacheprovider -k "learns or updates" > gpurun_out/r5f_train_tests.log 2>&1; tail -40 gpurun_out/r5f_train_tests.log
-for cfg in "vrptw100 128" "vrptw100 1024" "vrp10 128"; do timeout 120 python tools/time_train_step.py $cfg 2>&1 | tail -2 >> gpurun_out/r5f_train_timing.txt; done; cat gpurun_out/r5f_train_timing.txt
+timeout 400 python -m pytest tests/test_gpu_train.py -m gpu -q --timeout 180 --timeout-method=thread -p no:cacheprovider > gpurun_out/r5h_train_tests.log 2>&1; tail -30 gpurun_out/r5h_train_tests.log
+rm -f gpurun_out/r5h_train_timing.txt
+for cfg in "vrptw100 128" "vrptw100 1024" "vrp10 128"; do timeout 120 python tools/time_train_step.py $cfg 2>&1 | tail -2 >> gpurun_out/r5h_train_timing.txt; done; cat gpurun_out/r5h_train_timing.txt
