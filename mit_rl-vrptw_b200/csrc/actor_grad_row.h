@@ -74,6 +74,7 @@ struct ActorGradRow {
 };
 
 AG_FN float ag_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
+AG_FN int ag_node(int idx, int N) { return idx < 0 ? 0 : (idx >= N ? N - 1 : idx); }   // a caller's bad index must not read out of bounds
 
 AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, const ActorGradRow& r) {
     constexpr int H = kAgH;
@@ -119,7 +120,7 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
 
     // ---- forward: the LSTM along the given tour (the attention does not feed back into the state) ---------------------------
     for (int t = 0; t < T; ++t) {
-        const int node = t == 0 ? N - 1 : r.idx[(long long)(t - 1) * r.idx_stride];   // depot first (attention_agent.py:133-137)
+        const int node = t == 0 ? N - 1 : ag_node(r.idx[(long long)(t - 1) * r.idx_stride], N);   // depot first (attention_agent.py:133-137)
         AG_PAR(i)
             if (i < E) { const float x = r.emb[node * E + i]; s_x[i] = x; r.xin[t * E + i] = x; }
             s_hprev[i] = r.hs[t * H + i];
@@ -150,7 +151,7 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
         const float* msk = r.mask + (long long)t * r.node_stride;
         const float load = r.load[(long long)t * r.scalar_stride];
         const float time = d.tw ? r.time[(long long)t * r.scalar_stride] : 0.0f;
-        const int chosen = r.idx[(long long)t * r.idx_stride];
+        const int chosen = ag_node(r.idx[(long long)t * r.idx_stride], N);
         AG_PAR(i)
             s_hprev[i] = r.hs[(t + 1) * H + i];        // the query of step t is the LSTM output of step t
         AG_END
@@ -243,7 +244,7 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
     AG_PAR(i)
         if (i < E)
             for (int t = 0; t < T; ++t) {
-                const int node = t == 0 ? N - 1 : r.idx[(long long)(t - 1) * r.idx_stride];
+                const int node = t == 0 ? N - 1 : ag_node(r.idx[(long long)(t - 1) * r.idx_stride], N);
                 r.demb[node * E + i] += r.dx[t * E + i];
             }
     AG_END

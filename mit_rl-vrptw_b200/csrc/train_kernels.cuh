@@ -52,9 +52,9 @@ __global__ void __launch_bounds__(128) actor_grad_rows_kernel(ActorGradWeights w
     actor_grad_row(w, d, row);
 }
 
-__global__ void idx_to_i64_kernel(const int* __restrict__ in, long long* __restrict__ out, long long n) {
+__global__ void idx_to_i64_kernel(const int* __restrict__ in, long long* __restrict__ out, long long n, int N) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = in[i];
+    if (i < n) out[i] = ag_node(in[i], N);
 }
 
 // part[y][k * J + j] = sum over the rows r of split y, then over t < Tn, of A[r * sAr + t * sAt + k] * B[r * sBr + t * sBt + j];

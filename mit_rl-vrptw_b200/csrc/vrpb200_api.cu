@@ -1033,7 +1033,7 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
     long long* idx64 = reinterpret_cast<long long*>(ws + o_idx64);
 
     // Env state seen by every step: Env.reset, then Env.step along the given tour (the tested stand-alone kernels)
-    idx_to_i64_kernel<<<(unsigned)(((long long)T * R + 255) / 256), 256, 0, st>>>(d_idx, idx64, (long long)T * R);
+    idx_to_i64_kernel<<<(unsigned)(((long long)T * R + 255) / 256), 256, 0, st>>>(d_idx, idx64, (long long)T * R, N);
     const int wpb = 8;
     const unsigned egrid = (unsigned)((R + wpb - 1) / wpb);
     env_reset_kernel<<<egrid, wpb * 32, 0, st>>>(d_input, R, 1, N, D, c.capacity, F(o_dem), F(o_load), h->tw ? F(o_time) : nullptr, F(o_msk),
