@@ -40,3 +40,29 @@ for it in range(4):
     tot = t_roll + t_crit + t_loss + t_ag + t_cg + t_adam
     print(f"{task} B={B} it {it}: rollout {t_roll:.3f} critic {t_crit:.3f} losses {t_loss:.3f} actor_grad {t_ag:.3f} critic_grad {t_cg:.3f} "
           f"clip+adam {t_adam:.3f}  total {tot:.3f} ms = {B / tot * 1e3:.0f} instances/s", flush=True)
+
+# the same step on the host cores: stochastic rollout + critic + both gradient sets by torch autograd through the as-written graph
+# (oracle/train_torch.py; test infrastructure, timed here as the CPU baseline of the training step), then the update in numpy
+if os.environ.get("VRPB200_TRAIN_CPU", "1") == "1":
+    import json, time
+    from oracle import restatement_torch as RT, train_torch as TT
+    torch.set_num_threads(os.cpu_count())
+    xd = x.cpu().numpy()
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        u = np.random.RandomState(1).uniform(size=(args["decode_len"], B)).astype(np.float32)
+        Rc, idxc = RT.rollout(params, args, xd, "stochastic", uniforms=u, uniforms_retry=u)
+        _, gcr, vc = TT.critic_grads(params, args, xd, Rc)
+        _, gac, _, _ = TT.actor_grads(params, args, xd, idxc, ((Rc - vc) / B).astype(np.float32))
+        for k, g in list(gac.items()) + list(gcr.items()):
+            TT.clip_adam(params[k], g, np.zeros_like(g), np.zeros_like(g), 1, 1e-4, 2.0)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    print(json.dumps({"metric": "REINFORCE training step (rollout + critic + both gradients + clip + Adam), instances/s", "task": task,
+                      "batch": B, "gpu_ms_per_step": round(tot, 3), "gpu_instances_per_s": round(B / tot * 1e3, 1),
+                      "cpu_baseline": {"value": round(B / best, 2), "unit": "instances/s", "ms_per_step": round(best * 1e3, 1),
+                                       "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "the same batch, best of 2; torch-CPU autograd through the as-written graph"},
+                      "pieces_ms": {"rollout": round(t_roll, 3), "critic": round(t_crit, 3), "losses": round(t_loss, 3),
+                                    "actor_grad": round(t_ag, 3), "critic_grad": round(t_cg, 3), "clip_adam": round(t_adam, 3)}}), flush=True)
