@@ -214,10 +214,13 @@ int vrpb200_reinforce_loss(vrpb200_handle* h, const float* d_R, const float* d_v
  * VRPTW/vrptw_attention.py:30-84; shared/embeddings.py:40-46).  d_input [B, N, input_dim]; d_idx [T, B] int32 (vrpb200_rollout's
  * d_idx, greedy or stochastic, beam_width 1).  names / d_grads / n_elem: the TF variable names as in vrpb200_set_weights, one
  * DEVICE buffer per variable (same element count as the variable) that receives its gradient; variables left out are skipped.
- * n_glimpses must be 0; LSTM-input dropout is not applied (the keep-probability-1 graph is differentiated).  Indices outside
+ * d_input_scale [T, B, embedding_dim] or NULL: the LSTM-input dropout of DropoutWrapper(input_keep_prob = 1 - dropout)
+ * (shared/decode_step.py:177-179) as keep-mask / keep-probability - step t's input is the chosen node's embedding times
+ * d_input_scale[t, b, :]; it must be the scale the tour was decoded with (NULL: no dropout).  n_glimpses must be 0.  Indices outside
  * [0, N) are clamped.  Work memory (~13 * T * hidden_dim floats per row: 1.4 MB per row at VRPTW-100, sized for training batches,
  * VRPB200_E_CUDA if it cannot be allocated) is owned by the handle.  Deterministic: every sum runs in one fixed order. */
-int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight, int n,
+int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight,
+                       const float* d_input_scale, int n,
                        const char* const* names, float* const* d_grads, const int64_t* n_elem, void* stream);
 
 /* compute_gradients(critic_loss, Critic variables) of build_train_step (model/attention_agent.py:290, 298-299):

@@ -123,7 +123,7 @@ def load() -> C.CDLL:
     lib.vrpb200_last_redraws.argtypes = [vp]
     lib.vrpb200_critic.argtypes = [vp, f32p, i64, f32p, vp]
     lib.vrpb200_reinforce_loss.argtypes = [vp, f32p, f32p, f32p, i64, i64, f32p, vp]
-    lib.vrpb200_actor_grad.argtypes = [vp, f32p, i64, vp, f32p, i32, vp, vp, vp, vp]
+    lib.vrpb200_actor_grad.argtypes = [vp, f32p, i64, vp, f32p, f32p, i32, vp, vp, vp, vp]
     lib.vrpb200_critic_grad.argtypes = [vp, f32p, i64, f32p, i32, vp, vp, vp, f32p, vp]
     lib.vrpb200_clip_adam.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, C.c_float, i64, C.c_float, C.c_float, C.c_float, vp]
     lib.vrpb200_last_launch.argtypes = [vp, C.POINTER(C.c_int32)]

@@ -59,6 +59,8 @@ struct ActorGradRow {
     const int* idx;            // chosen node of step t at idx[t * idx_stride]
     long long idx_stride;
     float weight;
+    const float* xscale;       // LSTM-input dropout (shared/decode_step.py:177-179): the step's input is emb[node] * xscale[t * xscale_stride + k],
+    long long xscale_stride;   // xscale = keep-mask / keep-probability; null = no dropout
     // Env state SEEN by step t (before the step's decision): demand / mask at [t * node_stride + n], load / time at [t * scalar_stride]
     const float *demand, *mask, *load, *time;
     long long node_stride, scalar_stride;
@@ -122,7 +124,11 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
     for (int t = 0; t < T; ++t) {
         const int node = t == 0 ? N - 1 : ag_node(r.idx[(long long)(t - 1) * r.idx_stride], N);   // depot first (attention_agent.py:133-137)
         AG_PAR(i)
-            if (i < E) { const float x = r.emb[node * E + i]; s_x[i] = x; r.xin[t * E + i] = x; }
+            if (i < E) {
+                float x = r.emb[node * E + i];
+                if (r.xscale) x *= r.xscale[(long long)t * r.xscale_stride + i];
+                s_x[i] = x; r.xin[t * E + i] = x;
+            }
             s_hprev[i] = r.hs[t * H + i];
         AG_END
         AG_PAR(i)
@@ -245,7 +251,7 @@ AG_FN void actor_grad_row(const ActorGradWeights& w, const ActorGradDims& d, con
         if (i < E)
             for (int t = 0; t < T; ++t) {
                 const int node = t == 0 ? N - 1 : ag_node(r.idx[(long long)(t - 1) * r.idx_stride], N);
-                r.demb[node * E + i] += r.dx[t * E + i];
+                r.demb[node * E + i] += r.xscale ? r.dx[t * E + i] * r.xscale[(long long)t * r.xscale_stride + i] : r.dx[t * E + i];
             }
     AG_END
 }

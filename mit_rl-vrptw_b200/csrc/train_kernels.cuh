@@ -17,6 +17,7 @@ struct ActorGradBatch {   // per-row strides (in floats) of the work arrays; row
     const float* input;       // [R, N, D]
     const int* idx;           // [T, R]
     const float* weight;      // [R]
+    const float* xscale;      // [T, R, E] LSTM-input dropout scale, or null
     const float *demand, *mask, *load, *time;   // [T + 1][R][N], [T + 1][R]
     float *hs, *cs, *act, *xin, *dx, *emb, *eref, *erefT, *dgates, *dq, *Dsum, *demb, *sums;
     long long R;
@@ -30,6 +31,8 @@ __global__ void __launch_bounds__(128) actor_grad_rows_kernel(ActorGradWeights w
     row.idx = b.idx + r;
     row.idx_stride = b.R;
     row.weight = b.weight[r];
+    row.xscale = b.xscale ? b.xscale + r * E : nullptr;
+    row.xscale_stride = b.R * E;
     row.demand = b.demand + r * N;
     row.mask = b.mask + r * N;
     row.node_stride = b.R * N;

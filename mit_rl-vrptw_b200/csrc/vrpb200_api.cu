@@ -975,7 +975,8 @@ int train_workspace(vrpb200_handle* h, size_t bytes) {
 }
 }  // namespace
 
-int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight, int n,
+int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const int32_t* d_idx, const float* d_weight,
+                       const float* d_input_scale, int n,
                        const char* const* names, float* const* d_grads, const int64_t* n_elem, void* stream) {
     if (!h) return VRPB200_E_ARG;
     if (!h->have_weights) return fail(h, VRPB200_E_STATE, "actor_grad before set_weights");
@@ -1056,7 +1057,7 @@ int vrpb200_actor_grad(vrpb200_handle* h, const float* d_input, int64_t B, const
                        ra.emb_d_k, ra.emb_d_b, ra.proj_d_k, ra.proj_d_b, ra.emb_ld_k, ra.emb_ld_b, ra.proj_ld_k, ra.proj_ld_b,
                        ra.emb_t_k, ra.emb_t_b, ra.proj_t_k, ra.proj_t_b, ra.proj_q_k, ra.proj_q_b, ra.proj_ref_k, ra.proj_ref_b, h->raw_lstm_kT, h->raw_pq_kT};
     ActorGradDims dm{N, E, D, T, h->tw ? 1 : 0, c.use_tanh, c.mask_pointer, c.tanh_exploration, c.forget_bias};
-    ActorGradBatch bt{d_input, d_idx, d_weight, F(o_dem), F(o_msk), F(o_load), h->tw ? F(o_time) : nullptr,
+    ActorGradBatch bt{d_input, d_idx, d_weight, d_input_scale, F(o_dem), F(o_msk), F(o_load), h->tw ? F(o_time) : nullptr,
                       F(o_hs), F(o_cs), F(o_act), F(o_xin), F(o_dx), F(o_emb), F(o_eref), F(o_erefT), F(o_dg), F(o_dq), F(o_Ds), F(o_demb),
                       F(o_sums), R};
     actor_grad_rows_kernel<<<(unsigned)R, 128, 0, st>>>(w, dm, bt);

@@ -280,22 +280,26 @@ class Engine:
                     "reinforce_loss")
         return out[0], out[1]
 
-    def actor_grad(self, input_data, idxs, weight, shapes: Dict[str, tuple]) -> Dict[str, torch.Tensor]:
+    def actor_grad(self, input_data, idxs, weight, shapes: Dict[str, tuple], input_scale=None) -> Dict[str, torch.Tensor]:
         """compute_gradients(actor_loss, Actor variables) (attention_agent.py:289-297): gradients of
         sum_r weight[r] sum_t logprob[t, r] along the tour idxs [T, B] (int32, the rollout's).  shapes: variable name -> shape of
-        every variable whose gradient is wanted; returns name -> device tensor of that shape."""
+        every variable whose gradient is wanted; returns name -> device tensor of that shape.  input_scale [T, B, E]: the LSTM-input
+        dropout scale (keep-mask / keep-probability) the tour was decoded with, None = no dropout."""
         x = self._f32(input_data, "input_data")
         idx = idxs.to(device=self.device, dtype=torch.int32).contiguous()
         w = self._f32(weight, "weight")
         B = x.shape[0]
         if tuple(idx.shape) != (self.args["decode_len"], B) or tuple(w.shape) != (B,):
             raise VrpB200Error(f"idxs must be [{self.args['decode_len']}, {B}] and weight [{B}]")
+        xs = None if input_scale is None else self._f32(input_scale, "input_scale")
+        if xs is not None and tuple(xs.shape) != (self.args["decode_len"], B, self.args["embedding_dim"]):
+            raise VrpB200Error(f"input_scale must be [{self.args['decode_len']}, {B}, {self.args['embedding_dim']}]")
         names = sorted(shapes)
         grads = {k: torch.zeros(tuple(shapes[k]), device=self.device, dtype=torch.float32) for k in names}
         c_names = (C.c_char_p * len(names))(*[k.encode() for k in names])
         c_ptrs = (C.c_void_p * len(names))(*[grads[k].data_ptr() for k in names])
         c_sizes = (C.c_int64 * len(names))(*[grads[k].numel() for k in names])
-        self._check(self.lib.vrpb200_actor_grad(self.handle, _ptr(x), B, _ptr(idx), _ptr(w), len(names), c_names, c_ptrs, c_sizes,
+        self._check(self.lib.vrpb200_actor_grad(self.handle, _ptr(x), B, _ptr(idx), _ptr(w), _ptr(xs), len(names), c_names, c_ptrs, c_sizes,
                                                 self._stream()), "actor_grad")
         return grads
 

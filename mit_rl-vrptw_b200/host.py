@@ -638,18 +638,26 @@ class RLAgent(object):
         st.get(sc + 'Linear/L2/bias', [1], init="zeros")
         self._critic_built = True
 
-    def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0, apply=True):
+    def build_train_step(self, uniforms=None, uniforms_retry=None, seed=0, apply=True, input_scale=None):
         """attention_agent.py:272-322: ONE training step - the stochastic rollout, the critic, the two losses,
         compute_gradients(actor_loss) over the Actor variables (vrpb200_actor_grad: back-propagation through the teacher-forced
         rollout) and compute_gradients(critic_loss) over the Critic variables (vrpb200_critic_grad), per-variable
         clip_by_norm(max_grad_norm) and the two Adam updates with actor_net_lr / critic_net_lr (vrpb200_clip_adam; apply=False
         only computes).  Returns the reference's list [actor_train_step, critic_train_step, actor_loss, critic_loss,
         actor_gra_and_var, critic_gra_and_var, R, v, logprobs, probs, actions, idxs]: the *_train_step slots hold the number of
-        Adam steps taken so far, the *_gra_and_var slots lists of (gradient tensor, variable name).  LSTM-input dropout is not
-        applied (keep-probability 1).  Glimpses are not differentiated: with n_glimpses > 0 the actor slots are None."""
+        Adam steps taken so far, the *_gra_and_var slots lists of (gradient tensor, variable name).  input_scale [T, B, E]: the
+        LSTM-input dropout of the reference's decodeStep.dropout feed as keep-mask / keep-probability (None: keep-probability 1);
+        the tour is then decoded step by step with the scaled inputs and the gradient is taken through the same scale.
+        Glimpses are not differentiated: with n_glimpses > 0 the actor slots are None."""
         import torch
+        if input_scale is not None:
+            input_scale = torch.as_tensor(input_scale, dtype=torch.float32).to("cuda").contiguous()
+            if uniforms is None:                    # the step-by-step route draws on the host side of the ABI
+                gen = torch.Generator(device="cuda").manual_seed(int(seed))
+                shape = (self.args['decode_len'], self.env.input_data.shape[0])
+                uniforms, uniforms_retry = (torch.rand(shape, device="cuda", generator=gen) for _ in range(2))
         R, v, logprobs, actions, idxs, batch, probs = self.build_model('stochastic', uniforms=uniforms, uniforms_retry=uniforms_retry,
-                                                                       seed=seed)
+                                                                       seed=seed, input_scale=input_scale)
         eng = self.engine()
         actor_loss, critic_loss = eng.reinforce_loss(R, v, torch.stack(logprobs))
         rows = R.shape[0]
@@ -660,7 +668,7 @@ class RLAgent(object):
             names = [k for k in self.store.vars if k.startswith(sc)]
             weight = (R - v) / float(rows)             # d actor_loss / d sum_t logprob[t, r]; v enters as a constant (:286)
             grads = eng.actor_grad(self.env.input_data, torch.stack(idxs)[:, :, 0], weight,
-                                   {'Actor/' + k[len(sc):]: self.store.vars[k].shape for k in names})
+                                   {'Actor/' + k[len(sc):]: self.store.vars[k].shape for k in names}, input_scale=input_scale)
             out[4] = [(grads['Actor/' + k[len(sc):]], k) for k in names]
             todo.append((0, 'actor', names, out[4], self.args.get('actor_net_lr', 1e-4)))
         if self.clAttentionCritic is not None:
@@ -677,15 +685,21 @@ class RLAgent(object):
 
     def run_train_step(self, uniforms=None, uniforms_retry=None):
         """attention_agent.py:530-556: draw the next training batch from the data generator, feed it to the Env and run the train
-        step on it.  (The reference also feeds args['dropout'] to the LSTM input and a feature-normalised copy of the batch that
-        only the graph embeddings read; neither is on this path.)  Without uniforms the sampling stream is the in-kernel one,
-        seeded by the step count."""
+        step on it with decodeStep.dropout = args['dropout'] (:543): a fresh keep-mask of the LSTM inputs per step, row and
+        embedding component, drawn on the device from a generator seeded by (random_seed, step count).  (The feature-normalised
+        copy of the batch the reference also feeds is read by the graph embeddings only, which are not on this path.)  With
+        dropout 0 the rollout is the fused kernel's, its sampling stream seeded the same way."""
         import torch
         data = self.dataGen.get_train_next()
         self.env.input_data = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
         self._train_calls += 1
-        return self.build_train_step(uniforms=uniforms, uniforms_retry=uniforms_retry,
-                                     seed=int(self.args.get('random_seed', 0)) * 1000003 + self._train_calls)
+        seed = int(self.args.get('random_seed', 0)) * 1000003 + self._train_calls
+        scale, rate = None, float(self.args.get('dropout', 0.0) or 0.0)
+        if rate > 0.0 and self.args['n_glimpses'] == 0:
+            gen = torch.Generator(device="cuda").manual_seed(seed ^ 0x5DEECE66D)
+            shape = (self.args['decode_len'], data.shape[0], self.args['embedding_dim'])
+            scale = (torch.rand(shape, device="cuda", generator=gen) < (1.0 - rate)).float() / (1.0 - rate)     # tf.nn.dropout
+        return self.build_train_step(uniforms=uniforms, uniforms_retry=uniforms_retry, seed=seed, input_scale=scale)
 
     def save_model(self, path):
         """saver.save (main.py:131): every variable of the collection under its TF name, as load_model reads it back."""
@@ -718,14 +732,16 @@ class RLAgent(object):
 
     # -- the rollout -----------------------------------------------------------------------------
     def build_model(self, decode_type="greedy", uniforms=None, uniforms_retry=None, seed=0, want_probs=False,
-                    backend="auto", want_logprobs=True):
+                    backend="auto", want_logprobs=True, input_scale=None):
         """attention_agent.py:84-272.  backend 'fused' = the persistent rollout kernel, 'stepwise' = the reference's
         loop over RNNDecodeStep.step / Env.step on device state (per-step probabilities, and beam search combined with
         glimpses or UPS_old physics, take this route), 'auto' picks."""
         import torch
         special = self.args['n_glimpses'] != 0 or bool(self.args.get('ups_old'))   # fused in the FP32-pipe kernel, no beams
+        if input_scale is not None:                 # [T, rows, E] LSTM-input dropout scale (training): the step-by-step route applies it
+            input_scale = torch.as_tensor(input_scale, dtype=torch.float32).to("cuda")
         fused_ok = decode_type in ("greedy", "stochastic", "beam_search") and not want_probs and \
-            not (special and decode_type == "beam_search")
+            not (special and decode_type == "beam_search") and input_scale is None
         if backend == "auto":
             backend = "fused" if fused_ok else "stepwise"
         if backend == "fused":
@@ -753,7 +769,7 @@ class RLAgent(object):
             R_out = self._reward(list(actions), pnt, W) if self.args.get('min_trucks') else out.R
             v = self._critic_value(decode_type)
             return (R_out, v, list(out.logprobs) if want_logprobs else None, list(actions), [i[:, None] for i in idx], pnt, None)
-        return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs)
+        return self._build_model_stepwise(decode_type, uniforms, uniforms_retry, want_probs, input_scale)
 
     def _critic_value(self, decode_type):
         """attention_agent.py:243-270: v = 0 unless decoding stochastically; then the critic's value of every instance."""
@@ -828,7 +844,7 @@ class RLAgent(object):
             at = (inst + batch * parents[k].reshape(-1))[at]
         return out
 
-    def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs):
+    def _build_model_stepwise(self, decode_type, uniforms, uniforms_retry, want_probs, input_scale=None):
         import torch
         if decode_type not in ('greedy', 'stochastic', 'beam_search'):
             raise ValueError(decode_type)
@@ -846,6 +862,8 @@ class RLAgent(object):
         every = torch.arange(rows, device=dev)
         visited, logprobs, probs, idxs, parents, carried = [], [], [], [], [], None
         for step in range(args['decode_len']):
+            if input_scale is not None:               # DropoutWrapper(input_keep_prob): the cell sees the scaled input (decode_step.py:177-179)
+                dec_in = dec_in * input_scale[step][:, None, :]
             _, prob, _, state = self.decodeStep.step(dec_in, context, env, state)
             if decode_type == 'greedy':
                 idx, parent = self._pick_greedy(prob)

@@ -14,9 +14,10 @@ import torch
 from . import restatement_torch as RT
 
 
-def teacher_forced_logprobs(p, args, x, idxs):
+def teacher_forced_logprobs(p, args, x, idxs, input_scale=None):
     """Per-step log prob of the given decisions, [T, B] (attention_agent.py:139-220 with idx fixed), and the Env state seen by
-    every step (demand [T,B,N], mask [T,B,N], load [T,B], time [T,B])."""
+    every step (demand [T,B,N], mask [T,B,N], load [T,B], time [T,B]).  input_scale [T, B, E]: the LSTM-input dropout of
+    DropoutWrapper(input_keep_prob) (shared/decode_step.py:177-179) as keep-mask / keep-probability."""
     env = RT.Env(args, x)
     B, N, T = env.batch_size, env.n_nodes, args["decode_len"]
     emb = RT.conv1d_k1(env.input_pnt, p["Actor/Embedding/conv1d/kernel"], p["Actor/Embedding/conv1d/bias"])
@@ -28,6 +29,8 @@ def teacher_forced_logprobs(p, args, x, idxs):
     for t in range(T):
         st["demand"].append(env.demand.clone()); st["mask"].append(env.mask.clone()); st["load"].append(env.load.clone())
         st["time"].append(env.time.clone() if env.tw else torch.zeros([B]))
+        if input_scale is not None:
+            decoder_input = decoder_input * torch.as_tensor(input_scale[t], dtype=torch.float32)[:, None, :]
         logit, prob, logprob, (c, h) = RT.decode_step(p, args, decoder_input, emb, env, c, h)
         idx = torch.as_tensor(idxs[t]).long()
         lps.append(torch.log(prob[rows, idx]))          # attention_agent.py:214
@@ -36,12 +39,12 @@ def teacher_forced_logprobs(p, args, x, idxs):
     return torch.stack(lps), {k: torch.stack(v).numpy() for k, v in st.items()}
 
 
-def actor_grads(params, args, data, idxs, weight):
+def actor_grads(params, args, data, idxs, weight, input_scale=None):
     """Gradients of  sum_r weight[r] sum_t logprob[t, r]  w.r.t. every Actor variable (weight = (R - v) / B gives
     compute_gradients(actor_loss), attention_agent.py:289-297).  Returns (loss, {name: grad}, env states)."""
     p = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32)).requires_grad_(k.startswith("Actor/")) for k, v in params.items()}
     x = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32))
-    lps, st = teacher_forced_logprobs(p, args, x, idxs)
+    lps, st = teacher_forced_logprobs(p, args, x, idxs, input_scale)
     loss = (torch.as_tensor(weight, dtype=torch.float32) * lps.sum(0)).sum()
     names = [k for k in p if k.startswith("Actor/")]
     grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)

@@ -13,7 +13,7 @@ extern "C" int actor_grad_host(const float* const* wp /*23 pointers in ActorGrad
                                const float* mask, const float* load /*[T,R]*/, const float* time,
                                float* dgates /*[R,T,4H]*/, float* dq /*[R,T,H]*/, float* Dsum /*[R,N,H]*/, float* demb /*[R,N,E]*/,
                                float* sums /*[R,5,H]*/, float* hs /*[R,T+1,H]*/, float* xin /*[R,T,E]*/, float* emb /*[R,N,E]*/,
-                               float* const* small /*15 pointers in SmallGradOut order*/) {
+                               float* const* small /*15 pointers in SmallGradOut order*/, const float* xscale /*[T,R,E] or null*/) {
     ActorGradWeights w;
     static_assert(sizeof(ActorGradWeights) == 23 * sizeof(void*), "layout");
     std::memcpy(&w, wp, sizeof w);
@@ -24,6 +24,7 @@ extern "C" int actor_grad_host(const float* const* wp /*23 pointers in ActorGrad
         ActorGradRow row;
         row.input = input + r * N * D;
         row.idx = idx + r; row.idx_stride = R; row.weight = weight[r];
+        row.xscale = xscale ? xscale + r * E : nullptr; row.xscale_stride = R * E;
         row.demand = demand + r * N; row.mask = mask + r * N; row.node_stride = R * N;
         row.load = load + r; row.time = time ? time + r : nullptr; row.scalar_stride = R;
         row.hs = hs + r * (T + 1) * H; row.cs = cs.data(); row.act = act.data(); row.xin = xin + r * T * E; row.dx = dx.data();

@@ -40,7 +40,7 @@ def weight_arrays(params, tw):
     return order, arrs
 
 
-def run_host(lib, params, args, data, idxs, weight, st):
+def run_host(lib, params, args, data, idxs, weight, st, input_scale=None):
     tw = args["task_name"] == "vrptw"
     N, E, D, T, H = args["n_nodes"], args["embedding_dim"], args["input_dim"], args["decode_len"], 128
     R = data.shape[0]
@@ -62,12 +62,14 @@ def run_host(lib, params, args, data, idxs, weight, st):
     small_names += [f"{ATT}/{p}/kernel" for _, p in blocks] + [f"{ATT}/{p}/bias" for _, p in blocks]
     small = {n: np.zeros(np.asarray(params[n]).size if n in params else 1, np.float32) for n in small_names}
     sp = (fp * len(small_names))(*[ptr(small[n]) if n in params else None for n in small_names])
-    lib.actor_grad_host.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_float, C.c_longlong] + [C.c_void_p] * 16
+    lib.actor_grad_host.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.c_float, C.c_float, C.c_longlong] + [C.c_void_p] * 17
+    xs = None if input_scale is None else f32(input_scale)
     vp = lambda a: a.ctypes.data_as(C.c_void_p)
     rc = lib.actor_grad_host(C.cast(wp, C.c_void_p), N, E, D, T, int(tw), int(args["use_tanh"]), int(args["mask_pointer"]),
                              float(args["tanh_exploration"]), float(args["forget_bias"]), R, vp(x), vp(idx), vp(wt), vp(demand),
                              vp(mask), vp(load), vp(time) if tw else None, vp(out["dgates"]), vp(out["dq"]), vp(out["Dsum"]),
-                             vp(out["demb"]), vp(out["sums"]), vp(out["hs"]), vp(out["xin"]), vp(out["emb"]), C.cast(sp, C.c_void_p))
+                             vp(out["demb"]), vp(out["sums"]), vp(out["hs"]), vp(out["xin"]), vp(out["emb"]), C.cast(sp, C.c_void_p),
+                             None if xs is None else vp(xs))
     assert rc == 0
     # the device-wide reductions of train_kernels.cuh (outer_reduce / col_reduce), in numpy
     g = {n: small[n].reshape(np.asarray(params[n]).shape) for n in small_names if n in params}
@@ -110,3 +112,24 @@ def test_actor_gradient_algebra_matches_autograd(hostlib, task, over):
     names = [k for k in params if k.startswith("Actor/")]
     assert set(names) == set(got), set(names) ^ set(got)
     check(got, want, names)
+
+
+def dropout_scale(args, B, seed, rate=0.3):
+    """keep-mask / keep-probability of tf.nn.dropout on the LSTM input, [T, B, E]."""
+    keep = 1.0 - rate
+    rnd = np.random.RandomState(seed)
+    return ((rnd.uniform(size=(args["decode_len"], B, args["embedding_dim"])) < keep) / keep).astype(np.float32)
+
+
+@pytest.mark.parametrize("task", ["vrptw10", "vrp10"])
+def test_actor_gradient_with_lstm_input_dropout(hostlib, task):
+    """DropoutWrapper(input_keep_prob = 1 - dropout) (shared/decode_step.py:177-179) given the mask: the scaled LSTM inputs in the
+    forward sweep and the same scale on the way back into the embedding."""
+    args, params, data, idxs, weight = make_case(task, 6, 33)
+    scale = dropout_scale(args, 6, 5)
+    loss, want, st, _ = TT.actor_grads(params, args, data, idxs, weight, scale)
+    _, plain, _, _ = TT.actor_grads(params, args, data, idxs, weight)
+    got = run_host(hostlib, params, args, data, idxs, weight, st, scale)
+    names = [k for k in params if k.startswith("Actor/")]
+    check(got, want, names)
+    assert np.abs(want[LSTM + "/kernel"] - plain[LSTM + "/kernel"]).max() > 1e-3 * np.abs(plain[LSTM + "/kernel"]).max()   # the mask matters

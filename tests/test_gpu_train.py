@@ -7,7 +7,7 @@ import pytest
 from oracle import restatement as O
 from oracle import train_torch as TT
 from tests.helpers import load_pkg
-from tests.test_actor_grad_cpu import check, make_case
+from tests.test_actor_grad_cpu import check, dropout_scale, make_case
 from tests.test_critic_grad_cpu import check as check_c
 from tests.test_critic_grad_cpu import make_case as make_case_c
 
@@ -188,3 +188,55 @@ def test_run_train_step_learns(tmp_path):
     agent2.Initialize(None)
     for k in ("Actor/Decoder/Attention/v", "Actor/Embedding/conv1d/kernel"):
         np.testing.assert_array_equal(store2.vars[k], store.vars[k])
+
+
+@pytest.mark.parametrize("task,B", [("vrptw10", 6), ("vrp20", 64)])
+def test_actor_gradient_with_lstm_input_dropout(task, B):
+    """vrpb200_actor_grad with d_input_scale (DropoutWrapper(input_keep_prob), shared/decode_step.py:177-179, given the mask)
+    against autograd through the graph with the same scaled LSTM inputs."""
+    import torch
+    pkg = load_pkg()
+    args, params, data, idxs, weight = make_case(task, B, 33)
+    scale = dropout_scale(args, B, 5)
+    eng = pkg.Engine(args, device=0)
+    eng.set_weights(params)
+    names = [k for k in params if k.startswith("Actor/")]
+    got = eng.actor_grad(torch.from_numpy(data).cuda(), torch.from_numpy(idxs).cuda(), torch.from_numpy(weight).cuda(),
+                         {k: params[k].shape for k in names}, input_scale=torch.from_numpy(scale).cuda())
+    _, want, _, _ = TT.actor_grads(params, args, data, idxs, weight, scale)
+    check({k: v.cpu().numpy() for k, v in got.items()}, want, names)
+    with pytest.raises(pkg.VrpB200Error):
+        eng.actor_grad(torch.from_numpy(data).cuda(), torch.from_numpy(idxs).cuda(), torch.from_numpy(weight).cuda(),
+                       {k: params[k].shape for k in names}, input_scale=torch.from_numpy(scale[:-1]).cuda())
+
+
+def test_train_step_with_dropout_decodes_and_differentiates_the_same_graph():
+    """build_train_step(input_scale=...): the tour is decoded step by step with the scaled LSTM inputs (its log-probabilities are
+    the teacher-forced oracle's under the same scale) and the gradient is taken through that scale; run_train_step draws the
+    mask from args['dropout'] (attention_agent.py:543)."""
+    import torch
+    pkg = load_pkg()
+    H = pkg.host
+    args = O.default_args("vrptw10")
+    comps = H.load_task_specific_components("vrptw", False)
+    store = H.VariableStore(seed=5)
+    env = comps[1](args)
+    agent = H.RLAgent(args, None, env, None, comps[2], comps[3], comps[4], is_train=True, store=store)
+    B, T = 32, args["decode_len"]
+    data = O.create_dataset("vrptw10", B, seed=9).astype(np.float32)
+    env.input_data = torch.from_numpy(data)
+    rnd = np.random.RandomState(3)
+    u1, u2 = rnd.uniform(size=(T, B)).astype(np.float32), rnd.uniform(size=(T, B)).astype(np.float32)
+    scale = dropout_scale(args, B, 7, rate=0.25)
+    step = agent.build_train_step(uniforms=u1, uniforms_retry=u2, apply=False, input_scale=scale)
+    plain = agent.build_train_step(uniforms=u1, uniforms_retry=u2, apply=False)
+    R, vv = step[6].cpu().numpy(), step[7].cpu().numpy()
+    idxs = torch.stack(step[11])[:, :, 0].cpu().numpy().astype(np.int32)
+    params = {k: a for k, a in store.vars.items() if k != "decoder_input"}
+    _, want, _, lps = TT.actor_grads(params, args, data, idxs, ((R - vv) / B).astype(np.float32), scale)
+    np.testing.assert_allclose(torch.stack(step[8]).cpu().numpy(), lps, rtol=2e-4, atol=2e-5)
+    got = {name: g.cpu().numpy() for g, name in step[4]}
+    check(got, want, list(got))
+    assert not np.array_equal(idxs, torch.stack(plain[11])[:, :, 0].cpu().numpy())        # the mask changes the sampled tours
+    ref = O.rollout(params, args, data, "stochastic", uniforms=u1, uniforms_retry=u2)      # and without it the fused kernel's tours
+    assert (torch.stack(plain[11])[:, :, 0].cpu().numpy() == ref.idxs).all(0).mean() >= 0.9      # are the reference graph's
