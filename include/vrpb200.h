@@ -194,7 +194,7 @@ int vrpb200_reward_min_trucks_ups(vrpb200_handle* h, const float* d_actions, con
 int vrpb200_reward_min_trucks_ups_old(vrpb200_handle* h, const float* d_actions, const float* d_depot, int64_t T, int64_t R,
                                       int A, float n_nodes, float* d_reward, void* stream);
 
-/* ---- REINFORCE pieces around the rollout (forward only) ------------------------------ *
+/* ---- REINFORCE pieces around the rollout: value, losses, gradients, update ------------------------------ *
  * Critic value v of RLAgent.build_model('stochastic') (model/attention_agent.py:243-270; critics
  * VRPTW/vrptw_attention.py:87-169, VRP/vrp_attention.py:79-140): n_process_blocks un-masked attention passes over the
  * initial instance + Linear/L1 (relu) + Linear/L2.  Needs the Critic/Process/P<i>/{v, emb_d, proj_d, proj_q, proj_e

@@ -1,6 +1,6 @@
 // Critic value and REINFORCE losses: v of RLAgent.build_model('stochastic') (model/attention_agent.py:243-270,
 // critics VRPTW/vrptw_attention.py:87-169 and VRP/vrp_attention.py:79-140) and the two losses of build_train_step
-// (attention_agent.py:286-294).  Forward only: the rollout kernel already emits the per-step log-probabilities.
+// (attention_agent.py:286-294).  The rollout kernel already emits the per-step log-probabilities; the gradients live in train_kernels.cuh.
 //
 // The critic is n_process_blocks attention passes over the INITIAL instance (demand, time windows, actor embedding), none of
 // them masked: hy_0 = 0; (e_i, u_i) = AttentionCritic_i(hy_i); hy_{i+1} = softmax(u_i) . e_i; v = L2(relu(L1(hy_last))).
