@@ -133,3 +133,20 @@ def test_actor_gradient_with_lstm_input_dropout(hostlib, task):
     names = [k for k in params if k.startswith("Actor/")]
     check(got, want, names)
     assert np.abs(want[LSTM + "/kernel"] - plain[LSTM + "/kernel"]).max() > 1e-3 * np.abs(plain[LSTM + "/kernel"]).max()   # the mask matters
+
+
+def test_actor_gradient_is_additive_over_rows_and_linear_in_the_weights(hostlib):
+    """Size-independent properties of the gradient kernel's source: the gradient of a batch is the sum of the gradients of its
+    halves (rows are independent; only the device-wide reductions join them) and it is linear in the per-row weights."""
+    args, params, data, idxs, weight = make_case("vrptw10", 8, 35)
+    _, _, st, _ = TT.actor_grads(params, args, data, idxs, weight)
+    whole = run_host(hostlib, params, args, data, idxs, weight, st)
+    half = lambda sl: run_host(hostlib, params, args, data[sl], idxs[:, sl], weight[sl], {k: v[:, sl] for k, v in st.items()})
+    a, b = half(slice(0, 3)), half(slice(3, 8))
+    twice = run_host(hostlib, params, args, data, idxs, 2.0 * weight, st)
+    for n in whole:
+        scale = np.abs(whole[n]).max()
+        np.testing.assert_allclose(a[n] + b[n], whole[n], rtol=1e-5, atol=1e-6 * scale, err_msg=n)
+        np.testing.assert_allclose(twice[n], 2.0 * whole[n], rtol=1e-6, atol=1e-7 * scale, err_msg=n)
+    zero = run_host(hostlib, params, args, data, idxs, 0.0 * weight, st)
+    assert all(np.abs(g).max() == 0 for g in zero.values())
