@@ -102,3 +102,36 @@ def test_critic_gradient_algebra_matches_autograd(hostlib, task):  # noqa: F811
     assert set(names) == set(got), set(names) ^ set(got)
     check(got, want, names, max(np.abs(w).max() for w in want.values()))
     assert np.abs(want["Critic/Process/P0/proj_q/kernel"]).max() == 0 and np.abs(want["Critic/Process/P1/proj_q/kernel"]).max() > 0
+
+
+def test_critic_gradient_is_the_slope_of_the_loss(hostlib):  # noqa: F811
+    """Independent of autograd: the kernel source's own value v gives the loss mean((R - v)^2); its central finite difference
+    along a random direction of a variable equals the directional derivative formed from the kernel source's gradient."""
+    args, params, data, Rw = make_case("vrptw10", 5, 43)
+    got, v0 = run_host(hostlib, params, args, data, Rw)
+    rnd = np.random.RandomState(0)
+    for name in ("Critic/Process/P1/proj_q/kernel", "Critic/Process/P0/emb_begin_tw/kernel", "Critic/Process/P2/proj_e/kernel",
+                 "Critic/Linear/L1/kernel", "Critic/Process/P1/v"):
+        direction = rnd.normal(size=params[name].shape)
+        direction /= np.linalg.norm(direction)
+        eps = 2e-2
+        loss = []
+        for sgn in (+1.0, -1.0):
+            p = dict(params)
+            p[name] = (params[name].astype(np.float64) + sgn * eps * direction).astype(np.float32)
+            _, v = run_host(hostlib, p, args, data, Rw)
+            loss.append(np.mean((Rw.astype(np.float64) - v.astype(np.float64)) ** 2))
+        slope = (loss[0] - loss[1]) / (2 * eps)
+        want = float((got[name].astype(np.float64) * direction).sum())
+        assert abs(slope - want) <= 2e-2 * abs(want) + 1e-4, (name, slope, want)
+
+
+def test_critic_gradient_is_additive_over_rows(hostlib):  # noqa: F811
+    """Rows are independent up to the device-wide reductions and the 2 / B factor of the mean."""
+    args, params, data, Rw = make_case("vrp10", 8, 45)
+    whole, _ = run_host(hostlib, params, args, data, Rw)
+    a, _ = run_host(hostlib, params, args, data[:3], Rw[:3])
+    b, _ = run_host(hostlib, params, args, data[3:], Rw[3:])
+    ref = max(np.abs(g).max() for g in whole.values())      # block 0's gradients are tiny sums of cancelling terms: absolute floor
+    for n in whole:
+        np.testing.assert_allclose((3 * a[n] + 5 * b[n]) / 8, whole[n], rtol=1e-5, atol=1e-6 * ref, err_msg=n)
